@@ -1,0 +1,103 @@
+"""ctypes binding of the C ABI declared in include/emf_b200.h.
+
+The product has exactly one compute path: libemf_b200.so (hand-written sm_100a CUDA).  If the
+library is missing this module raises at import of the first op -- there is no CPU or PyTorch
+fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libemf_b200.so")
+
+EMF_OK = 0
+EMF_ERR_INVALID = -1
+EMF_ERR_CUDA = -2
+EMF_ERR_UNSUPPORTED = -3
+EMF_MAX_VOLUMES = 96
+
+
+class EmfError(RuntimeError):
+    pass
+
+
+class Image(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("pitch", C.c_size_t), ("width", C.c_int), ("height", C.c_int)]
+
+
+class Pose(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3)]
+
+
+class TsdfParams(C.Structure):
+    _fields_ = [("max_tsdf_weight", C.c_float), ("assoc_sigma", C.c_float), ("alpha", C.c_float),
+                ("uni_prior", C.c_float)]
+
+
+class Volume(C.Structure):
+    _fields_ = [("tsdf", C.c_void_p), ("weights", C.c_void_p), ("grads", C.c_void_p), ("fg_probs", C.c_void_p),
+                ("res", C.c_int * 3), ("voxel_size", C.c_float), ("truncdist", C.c_float), ("id", C.c_int)]
+
+
+_P = C.POINTER
+_SIGS = {
+    "emf_compute_points": [_P(Image), _P(Image), _P(C.c_float), C.c_void_p],
+    "emf_update_tsdf": [_P(Image), _P(Image), C.c_void_p, C.c_void_p, _P(Pose), _P(C.c_float), _P(C.c_int),
+                        C.c_float, C.c_float, C.c_float, C.c_void_p],
+    "emf_compute_tsdf_grads": [C.c_void_p, C.c_void_p, _P(C.c_int), C.c_void_p],
+    "emf_raycast_tsdf": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _P(Image), _P(Image), _P(Image), _P(Image),
+                         _P(Pose), _P(C.c_float), _P(C.c_int), C.c_float, C.c_float, C.c_void_p, C.c_void_p],
+    "emf_get_volume_vals": [C.c_void_p, _P(Image), _P(Pose), _P(C.c_int), C.c_float, _P(Image), C.c_void_p],
+    "emf_update_fgbg_probs": [_P(Image), _P(Image), C.c_void_p, C.c_void_p, C.c_void_p, _P(Pose), _P(C.c_float),
+                              _P(C.c_int), C.c_float, C.c_void_p],
+    "emf_compute_fg_probs": [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    "emf_compute_association": [_P(Volume), _P(Image), _P(Pose), _P(TsdfParams), _P(Image), _P(Image), C.c_void_p],
+    "emf_assoc_weights": [C.c_int, _P(Volume), _P(Pose), _P(Image), _P(TsdfParams), _P(Image), C.c_int, _P(Image),
+                          C.c_void_p],
+    "emf_assoc_normalise": [C.c_int, _P(Image), _P(Image), C.c_void_p],
+    "emf_raycast_volumes": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(C.c_int), _P(Image), _P(Image),
+                            _P(Image), _P(Image), C.c_void_p],
+    "emf_raycast_composite": [C.c_int, _P(C.c_int), _P(C.c_int), _P(Image), _P(Image), _P(Image), _P(Image),
+                              _P(Image), _P(Image), _P(Image), _P(Image), C.c_int, _P(Image), _P(Image), _P(Image),
+                              _P(Image), C.c_void_p, C.c_void_p],
+    "emf_integrate_volumes": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(Image), _P(Image), C.c_float,
+                              C.c_void_p],
+    "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],
+}
+EXPORTED = sorted(list(_SIGS) + ["emf_version"])
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libemf_b200.so (once).  Raises EmfError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EmfError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                "(run `python -m emfusion_b200.build` or __graft_entry__.build()); "
+                "emfusion_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        L.emf_version.restype = C.c_char_p
+        L.emf_version.argtypes = []
+        _lib = L
+    return _lib
+
+
+_ERR = {EMF_ERR_INVALID: "invalid argument", EMF_ERR_CUDA: "CUDA error", EMF_ERR_UNSUPPORTED: "unsupported"}
+
+
+def check(rc: int, what: str) -> None:
+    if rc != EMF_OK:
+        raise EmfError(f"{what} failed: {_ERR.get(rc, rc)}")
+
+
+def version() -> str:
+    return lib().emf_version().decode()

@@ -1,0 +1,441 @@
+// raycast.cu -- per-pixel volume raycast for one or many volumes in ONE launch,
+// the gradient pass, and the depth-ordered composite.
+//
+// Replaces emf::cuda::TSDF::raycastTSDF (reference src/core/cuda/TSDF.cu:466-601),
+// emf::ObjTSDF::raycast's two full-volume weight-masking passes
+// (src/core/ObjTSDF.cpp:209-210), emf::TSDF::updateGradients
+// (src/core/TSDF.cpp:120-123) and the ~8K+6 OpenCV launches of
+// emf::EMFusion::raycast's composite (src/core/EMFusion.cpp:760-794).
+//
+// Differences in mechanism, none in result:
+//  * the weight trilinear of a march sample is only evaluated when the sample
+//    is a back-face candidate (f < 0 && f' > 0) -- its only consumer;
+//  * the object weight mask (fgProb > 0.5) is applied at the 8 corners of a
+//    weight gather instead of materialising raycastWeights per frame;
+//  * normals come from on-the-fly forward differences when no gradient volume
+//    is supplied (same single fp32 subtraction per component => same bits);
+//  * a volume is only traced inside the screen rectangle of its box.
+#include "common.cuh"
+
+namespace emfb {
+
+struct RayVol {
+    const float* tsdf;
+    const float* weights;
+    const float* fg_probs;   // nullable
+    const float* grads;      // nullable (float3 per voxel)
+    float* ray; size_t ray_pitch;
+    float* vert; size_t vert_pitch;
+    float* norm; size_t norm_pitch;
+    uint8_t* mask; size_t mask_pitch;
+    float R[9];              // T_CO
+    float t[3];
+    int rx, ry, rz;
+    float voxel, trunc;
+    int x0, y0, x1, y1;      // screen rect (exclusive upper)
+    int tiles_x;             // tiles per rect row
+    int first_block;
+};
+
+struct RayParams {
+    RayVol v[EMF_MAX_VOLUMES];
+    int n_vol;
+    int w, h;
+    float K[9];
+    int32_t* hit_voxel;      // optional (single-volume API)
+    int write_all;           // 1: batched semantics (ray/mask written for every pixel of the rect)
+};
+
+constexpr int kTileW = 16, kTileH = 8;   // CTA tile; warp = 8 x 4 pixels
+constexpr int kRayThreads = kTileW * kTileH;
+
+__device__ __forceinline__ float weight_at(const RayVol& V, int64_t idx) {
+    float w = __ldg(V.weights + idx);
+    if (V.fg_probs) w = (__ldg(V.fg_probs + idx) > 0.5f) ? w : 0.0f;
+    return w;
+}
+
+__device__ __forceinline__ float trilinear_weight(const RayVol& V, float vx, float vy, float vz) {
+    const TriSetup s(vx, vy, vz, V.rx, V.ry);
+    const int64_t b00 = s.base, b01 = b00 + V.rx, b10 = b00 + (int64_t)V.ry * V.rx, b11 = b10 + V.rx;
+    return s.combine(weight_at(V, b00), weight_at(V, b00 + 1), weight_at(V, b01), weight_at(V, b01 + 1),
+                     weight_at(V, b10), weight_at(V, b10 + 1), weight_at(V, b11), weight_at(V, b11 + 1));
+}
+
+// forward-difference gradient at integer voxel (x,y,z); zero on the last plane of each axis
+// (reference src/core/cuda/TSDF.cu:436-447 after the setTo(0) of src/core/TSDF.cpp:121)
+__device__ __forceinline__ void grad_at(const RayVol& V, int x, int y, int z, float g[3]) {
+    if (V.grads) {
+        const float* p = V.grads + 3 * (((int64_t)z * V.ry + y) * V.rx + x);
+        g[0] = __ldg(p); g[1] = __ldg(p + 1); g[2] = __ldg(p + 2);
+        return;
+    }
+    if (x >= V.rx - 1 || y >= V.ry - 1 || z >= V.rz - 1) { g[0] = g[1] = g[2] = 0.f; return; }
+    const float* p = V.tsdf + ((int64_t)z * V.ry + y) * V.rx + x;
+    const float f = __ldg(p);
+    g[0] = fsub(__ldg(p + 1), f);
+    g[1] = fsub(__ldg(p + V.rx), f);
+    g[2] = fsub(__ldg(p + (int64_t)V.ry * V.rx), f);
+}
+
+__device__ __forceinline__ void trilinear_grad(const RayVol& V, float vx, float vy, float vz, float out[3]) {
+    const TriSetup s(vx, vy, vz, V.rx, V.ry);
+    const int lx = __float2int_rz(vx), ly = __float2int_rz(vy), lz = __float2int_rz(vz);
+    float g[8][3];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) grad_at(V, lx + (c & 1), ly + ((c >> 1) & 1), lz + (c >> 2), g[c]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        out[k] = s.combine(g[0][k], g[1][k], g[2][k], g[3][k], g[4][k], g[5][k], g[6][k], g[7][k]);
+}
+
+__global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__ RayParams P) {
+    int lo = 0, hi = P.n_vol - 1;
+    const int b = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.v[mid].first_block <= b) lo = mid; else hi = mid - 1;
+    }
+    const RayVol& V = P.v[lo];
+    const int lb = b - V.first_block;
+    const int ty = lb / V.tiles_x, tx = lb - ty * V.tiles_x;
+    // warp = 8x4 pixel patch inside the 16x8 CTA tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = V.x0 + tx * kTileW + (warp & 1) * 8 + (lane & 7);
+    const int y = V.y0 + ty * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= V.x1 || y >= V.y1) return;
+
+    float* ray_px = (float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x;
+    uint8_t* mask_px = V.mask + (size_t)y * V.mask_pitch + x;
+    float out_t = 0.0f;
+    bool hit = false;
+    float hvx = 0.f, hvy = 0.f, hvz = 0.f, hmx = 0.f, hmy = 0.f, hmz = 0.f;
+
+    const float s = V.voxel;
+    const float frx = (float)V.rx, fry = (float)V.ry, frz = (float)V.rz;
+    const float ux = fdiv(fsub((float)x, P.K[2]), P.K[0]);
+    const float uy = fdiv(fsub((float)y, P.K[5]), P.K[4]);
+    // rot_CO * (ux, uy, 1)
+    const float rayx = fadd(V.R[2], ffma(V.R[0], ux, fmul(V.R[1], uy)));
+    const float rayy = fadd(V.R[5], ffma(V.R[3], ux, fmul(V.R[4], uy)));
+    const float rayz = fadd(V.R[8], ffma(V.R[6], ux, fmul(V.R[7], uy)));
+    const float rn = norm3(rayx, rayy, rayz);
+    const float dx = fdiv(rayx, rn), dy = fdiv(rayy, rn), dz = fdiv(rayz, rn);
+    // boxBounds = (volSize - 1) / 2 * voxelSize with INTEGER division (TSDF.cu:490)
+    const float bx = fmul((float)((V.rx - 1) / 2), s);
+    const float by = fmul((float)((V.ry - 1) / 2), s);
+    const float bz = fmul((float)((V.rz - 1) / 2), s);
+    const float ox = V.t[0], oy = V.t[1], oz = V.t[2];
+    const float tin = fmaxf(fmaxf(fdiv(fsub(dx > 0.f ? -bx : bx, ox), dx), fdiv(fsub(dy > 0.f ? -by : by, oy), dy)),
+                            fdiv(fsub(dz > 0.f ? -bz : bz, oz), dz));
+    const float tout = fminf(fminf(fdiv(fsub(dx > 0.f ? bx : -bx, ox), dx), fdiv(fsub(dy > 0.f ? by : -by, oy), dy)),
+                             fdiv(fsub(dz > 0.f ? bz : -bz, oz), dz));
+    float tcur = fadd(s, tin);
+    float tmax = fsub(tout, s);
+    const float old = P.write_all ? 0.0f : *ray_px;   // in/out far clip (TSDF.cu:496-500)
+    if (old != 0.0f) tmax = fminf(old, tmax);
+
+    if (!(tcur >= tmax)) {
+        const float hxh = fmul((float)(V.rx - 1), 0.5f), hyh = fmul((float)(V.ry - 1), 0.5f),
+                    hzh = fmul((float)(V.rz - 1), 0.5f);
+        const float half_s = fmul(s, 0.5f);
+        float step = V.trunc;
+        float vx, vy, vz;
+        for (;;) {   // coarse skip (TSDF.cu:509-515)
+            vx = fadd(hxh, fdiv(ffma(dx, tcur, ox), s));
+            vy = fadd(hyh, fdiv(ffma(dy, tcur, oy), s));
+            vz = fadd(hzh, fdiv(ffma(dz, tcur, oz), s));
+            if (out_of(vx, vy, vz, 1.0f, frx, fry, frz) && tcur < tmax) tcur = fadd(step, tcur);
+            else break;
+        }
+        // still outside => the reference's march loop cannot run (tcur >= tmax): defined as no hit
+        if (!out_of(vx, vy, vz, 1.0f, frx, fry, frz) && vx == vx && vy == vy && vz == vz) {
+            float f = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
+            if (fabsf(f) < 1.0f) step = s;
+            if (fabsf(f) < 0.8f) step = half_s;
+            for (;;) {
+                tcur = fadd(tcur, step);
+                if (!(tcur <= tmax)) break;
+                vx = fadd(hxh, fdiv(ffma(dx, tcur, ox), s));
+                vy = fadd(hyh, fdiv(ffma(dy, tcur, oy), s));
+                vz = fadd(hzh, fdiv(ffma(dz, tcur, oz), s));
+                if (out_of(vx, vy, vz, 2.0f, frx, fry, frz)) continue;
+                const float fn = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
+                // back face (TSDF.cu:532): the weight sample is only needed for this test
+                if (f < 0.0f && fn > 0.0f) {
+                    if (trilinear_weight(V, vx, vy, vz) > 0.0f) break;
+                }
+                if (fabsf(fn) < 1.0f) step = s;
+                if (fabsf(fn) < 0.8f) step = half_s;
+                if (f > 0.0f && fn < 0.0f) {   // front face (TSDF.cu:540)
+                    const float ts = fsub(tcur, fdiv(fmul(f, step), fsub(fn, f)));
+                    const float mx = fmul(dx, ts), my = fmul(dy, ts), mz = fmul(dz, ts);
+                    const float sx = fadd(hxh, fdiv(fadd(ox, mx), s));
+                    const float sy = fadd(hyh, fdiv(fadd(oy, my), s));
+                    const float sz = fadd(hzh, fdiv(fadd(oz, mz), s));
+                    if (out_of(sx, sy, sz, 2.0f, frx, fry, frz)) continue;   // f keeps its old value
+                    if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
+                        hit = true; out_t = ts;
+                        hvx = sx; hvy = sy; hvz = sz; hmx = mx; hmy = my; hmz = mz;
+                        break;
+                    }
+                }
+                f = fn;
+            }
+        }
+    }
+
+    if (hit) {
+        float g[3];
+        trilinear_grad(V, hvx, hvy, hvz, g);
+        float* vp = (float*)((char*)V.vert + (size_t)y * V.vert_pitch) + 3 * x;
+        float* np = (float*)((char*)V.norm + (size_t)y * V.norm_pitch) + 3 * x;
+        // transpose(rot_CO) * (t* dir)
+        vp[0] = dot_yxz(V.R[0], V.R[3], V.R[6], hmx, hmy, hmz);
+        vp[1] = dot_yxz(V.R[1], V.R[4], V.R[7], hmx, hmy, hmz);
+        vp[2] = dot_yxz(V.R[2], V.R[5], V.R[8], hmx, hmy, hmz);
+        const float gn = norm3(g[0], g[1], g[2]);
+        const float nx = fdiv(g[0], gn), ny = fdiv(g[1], gn), nz = fdiv(g[2], gn);
+        np[0] = dot_yxz(V.R[0], V.R[3], V.R[6], nx, ny, nz);
+        np[1] = dot_yxz(V.R[1], V.R[4], V.R[7], nx, ny, nz);
+        np[2] = dot_yxz(V.R[2], V.R[5], V.R[8], nx, ny, nz);
+        *ray_px = out_t;
+        *mask_px = 1;
+        if (P.hit_voxel) {
+            int32_t* hv = P.hit_voxel + 3 * ((size_t)y * P.w + x);
+            hv[0] = __float2int_rz(hvx); hv[1] = __float2int_rz(hvy); hv[2] = __float2int_rz(hvz);
+        }
+    } else if (P.write_all) {
+        *ray_px = 0.0f;
+        *mask_px = 0;
+    }
+}
+
+static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const emf_image* ray,
+                        const emf_image* vert, const emf_image* norm, const emf_image* mask, const int* rect,
+                        int w, int h) {
+    if (!v.tsdf || !v.weights || !res_ok(v.res)) return EMF_ERR_INVALID;
+    if (!image_ok(ray, 4) || !image_ok(vert, 12) || !image_ok(norm, 12) || !image_ok(mask, 1)) return EMF_ERR_INVALID;
+    if (ray->width != w || ray->height != h || !same_size(ray, vert) || !same_size(ray, norm) || !same_size(ray, mask))
+        return EMF_ERR_INVALID;
+    d.tsdf = v.tsdf; d.weights = v.weights; d.fg_probs = v.fg_probs; d.grads = v.grads;
+    d.ray = (float*)ray->ptr; d.ray_pitch = ray->pitch;
+    d.vert = (float*)vert->ptr; d.vert_pitch = vert->pitch;
+    d.norm = (float*)norm->ptr; d.norm_pitch = norm->pitch;
+    d.mask = (uint8_t*)mask->ptr; d.mask_pitch = mask->pitch;
+    for (int k = 0; k < 9; ++k) d.R[k] = T.R[k];
+    for (int k = 0; k < 3; ++k) d.t[k] = T.t[k];
+    d.rx = v.res[0]; d.ry = v.res[1]; d.rz = v.res[2];
+    d.voxel = v.voxel_size; d.trunc = v.truncdist;
+    int x0 = 0, y0 = 0, x1 = w, y1 = h;
+    if (rect) {
+        x0 = rect[0] < 0 ? 0 : rect[0]; y0 = rect[1] < 0 ? 0 : rect[1];
+        x1 = rect[2] > w ? w : rect[2]; y1 = rect[3] > h ? h : rect[3];
+        if (x1 < x0) x1 = x0;
+        if (y1 < y0) y1 = y0;
+    }
+    d.x0 = x0; d.y0 = y0; d.x1 = x1; d.y1 = y1;
+    d.tiles_x = (x1 - x0 + kTileW - 1) / kTileW;
+    return EMF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient volume (only for consumers that want the materialised float3 array)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_grads(const float* __restrict__ tsdf, float* __restrict__ grads,
+                                               int rx, int ry, int rz) {
+    const int64_t n = (int64_t)rx * ry * rz;
+    const int64_t plane = (int64_t)rx * ry;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / rx;
+        const int x = (int)(i - row * rx);
+        const int z = (int)(row / ry);
+        const int y = (int)(row - (int64_t)z * ry);
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if (x < rx - 1 && y < ry - 1 && z < rz - 1) {
+            const float f = __ldg(tsdf + i);
+            gx = fsub(__ldg(tsdf + i + 1), f);
+            gy = fsub(__ldg(tsdf + i + rx), f);
+            gz = fsub(__ldg(tsdf + i + plane), f);
+        }
+        float* g = grads + 3 * i;
+        g[0] = gx; g[1] = gy; g[2] = gz;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// composite (reference src/core/EMFusion.cpp:760-794)
+// ---------------------------------------------------------------------------------------------
+struct CompObj {
+    const float* ray; size_t ray_pitch;
+    const float* vert; size_t vert_pitch;
+    const float* norm; size_t norm_pitch;
+    const uint8_t* mask; size_t mask_pitch;
+    int x0, y0, x1, y1;
+    int id;
+};
+struct CompParams {
+    CompObj o[EMF_MAX_VOLUMES];
+    int n_obj;
+    int w, h, boundary;
+    const float* bg_ray; size_t bg_ray_pitch;
+    const float* bg_vert; size_t bg_vert_pitch;
+    const float* bg_norm; size_t bg_norm_pitch;
+    const uint8_t* bg_mask; size_t bg_mask_pitch;
+    float* ray; size_t ray_pitch;
+    float* vert; size_t vert_pitch;
+    float* norm; size_t norm_pitch;
+    uint8_t* seg; size_t seg_pitch;
+    int32_t* vis_count;
+};
+
+__global__ void __launch_bounds__(256) k_composite(const __grid_constant__ CompParams P) {
+    __shared__ int s_cnt[EMF_MAX_VOLUMES];
+    for (int k = threadIdx.x; k < P.n_obj; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < P.w && y < P.h) {
+        float r = 0.0f;
+        int win = -1;
+        for (int k = 0; k < P.n_obj; ++k) {
+            const CompObj& O = P.o[k];
+            if (x < O.x0 || x >= O.x1 || y < O.y0 || y >= O.y1) continue;
+            if (!O.mask[(size_t)y * O.mask_pitch + x]) continue;
+            const float t = *((const float*)((const char*)O.ray + (size_t)y * O.ray_pitch) + x);
+            if (r <= 0.0f || t < r) { r = t; win = k; }
+        }
+        int seg = 0;
+        if (win >= 0) seg = P.o[win].id > 255 ? 255 : P.o[win].id;   // CV_8U saturate
+        const bool bgm = P.bg_mask[(size_t)y * P.bg_mask_pitch + x] != 0;
+        if (bgm) {
+            const float bt = *((const float*)((const char*)P.bg_ray + (size_t)y * P.bg_ray_pitch) + x);
+            if (fsub(r, bt) > 0.05f) seg = 0;
+        }
+        *((float*)((char*)P.ray + (size_t)y * P.ray_pitch) + x) = r;
+        P.seg[(size_t)y * P.seg_pitch + x] = (uint8_t)seg;
+        const float* vs; const float* ns;
+        if (seg == 0) {
+            vs = (const float*)((const char*)P.bg_vert + (size_t)y * P.bg_vert_pitch) + 3 * x;
+            ns = (const float*)((const char*)P.bg_norm + (size_t)y * P.bg_norm_pitch) + 3 * x;
+        } else {
+            const CompObj& O = P.o[win];
+            vs = (const float*)((const char*)O.vert + (size_t)y * O.vert_pitch) + 3 * x;
+            ns = (const float*)((const char*)O.norm + (size_t)y * O.norm_pitch) + 3 * x;
+        }
+        float* vo = (float*)((char*)P.vert + (size_t)y * P.vert_pitch) + 3 * x;
+        float* no = (float*)((char*)P.norm + (size_t)y * P.norm_pitch) + 3 * x;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+        if (seg != 0 || bgm) { v0 = vs[0]; v1 = vs[1]; v2 = vs[2]; n0 = ns[0]; n1 = ns[1]; n2 = ns[2]; }
+        vo[0] = v0; vo[1] = v1; vo[2] = v2; no[0] = n0; no[1] = n1; no[2] = n2;
+        if (seg != 0 && P.o[win].id == seg && x >= P.boundary && x < P.w - P.boundary && y >= P.boundary &&
+            y < P.h - P.boundary)
+            atomicAdd(&s_cnt[win], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < P.n_obj; k += blockDim.x)
+        if (s_cnt[k]) atomicAdd(P.vis_count + k, s_cnt[k]);
+}
+
+}  // namespace emfb
+
+using namespace emfb;
+
+extern "C" EMF_API int emf_raycast_tsdf(const float* tsdf, const float* grads, const float* weights, const float* fg_probs,
+                                const emf_image* raylengths, const emf_image* vertices, const emf_image* normals,
+                                const emf_image* mask, const emf_pose* T_co, const float K[9], const int res[3],
+                                float voxel_size, float truncdist, int32_t* hit_voxel, emf_stream_t stream) {
+    if (!T_co || !K || !res || !raylengths) return EMF_ERR_INVALID;
+    emf_volume v;
+    v.tsdf = (float*)tsdf; v.weights = (float*)weights; v.grads = grads; v.fg_probs = fg_probs;
+    v.res[0] = res[0]; v.res[1] = res[1]; v.res[2] = res[2];
+    v.voxel_size = voxel_size; v.truncdist = truncdist; v.id = 0;
+    RayParams P;
+    const int w = raylengths->width, h = raylengths->height;
+    const int rc = fill_ray_vol(P.v[0], v, *T_co, raylengths, vertices, normals, mask, nullptr, w, h);
+    if (rc != EMF_OK) return rc;
+    P.v[0].first_block = 0;
+    P.n_vol = 1; P.w = w; P.h = h;
+    for (int k = 0; k < 9; ++k) P.K[k] = K[k];
+    P.hit_voxel = hit_voxel; P.write_all = 0;
+    const int blocks = P.v[0].tiles_x * ((h + kTileH - 1) / kTileH);
+    k_raycast<<<blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
+                                   const int* rects, const emf_image* ray_out, const emf_image* vert_out,
+                                   const emf_image* norm_out, const emf_image* mask_out, emf_stream_t stream) {
+    if (n_vol <= 0 || !vols || !T_co || !K || !ray_out || !vert_out || !norm_out || !mask_out) return EMF_ERR_INVALID;
+    if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
+    RayParams P;
+    const int w = ray_out[0].width, h = ray_out[0].height;
+    int64_t blocks = 0;
+    for (int i = 0; i < n_vol; ++i) {
+        const int rc = fill_ray_vol(P.v[i], vols[i], T_co[i], &ray_out[i], &vert_out[i], &norm_out[i], &mask_out[i],
+                                    rects ? rects + 4 * i : nullptr, w, h);
+        if (rc != EMF_OK) return rc;
+        P.v[i].first_block = (int)blocks;
+        blocks += (int64_t)P.v[i].tiles_x * ((P.v[i].y1 - P.v[i].y0 + kTileH - 1) / kTileH);
+    }
+    if (blocks == 0) return EMF_OK;
+    P.n_vol = n_vol; P.w = w; P.h = h;
+    for (int k = 0; k < 9; ++k) P.K[k] = K[k];
+    P.hit_voxel = nullptr; P.write_all = 1;
+    k_raycast<<<(unsigned)blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_compute_tsdf_grads(const float* tsdf, float* grads, const int res[3], emf_stream_t stream) {
+    if (!tsdf || !grads || !res_ok(res)) return EMF_ERR_INVALID;
+    const int64_t n = (int64_t)res[0] * res[1] * res[2];
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    k_grads<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(tsdf, grads, res[0], res[1], res[2]);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_raycast_composite(int n_obj, const int* ids, const int* rects, const emf_image* obj_ray,
+                                     const emf_image* obj_vert, const emf_image* obj_norm, const emf_image* obj_mask,
+                                     const emf_image* bg_ray, const emf_image* bg_vert, const emf_image* bg_norm,
+                                     const emf_image* bg_mask, int boundary, const emf_image* ray,
+                                     const emf_image* vert, const emf_image* norm, const emf_image* seg,
+                                     int32_t* vis_count, emf_stream_t stream) {
+    if (n_obj < 0 || n_obj > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
+    if (!image_ok(bg_ray, 4) || !image_ok(bg_vert, 12) || !image_ok(bg_norm, 12) || !image_ok(bg_mask, 1) ||
+        !image_ok(ray, 4) || !image_ok(vert, 12) || !image_ok(norm, 12) || !image_ok(seg, 1))
+        return EMF_ERR_INVALID;
+    if (n_obj > 0 && (!ids || !obj_ray || !obj_vert || !obj_norm || !obj_mask || !vis_count)) return EMF_ERR_INVALID;
+    CompParams P;
+    const int w = ray->width, h = ray->height;
+    for (int k = 0; k < n_obj; ++k) {
+        if (!image_ok(&obj_ray[k], 4) || !image_ok(&obj_vert[k], 12) || !image_ok(&obj_norm[k], 12) ||
+            !image_ok(&obj_mask[k], 1))
+            return EMF_ERR_INVALID;
+        CompObj& o = P.o[k];
+        o.ray = (const float*)obj_ray[k].ptr; o.ray_pitch = obj_ray[k].pitch;
+        o.vert = (const float*)obj_vert[k].ptr; o.vert_pitch = obj_vert[k].pitch;
+        o.norm = (const float*)obj_norm[k].ptr; o.norm_pitch = obj_norm[k].pitch;
+        o.mask = (const uint8_t*)obj_mask[k].ptr; o.mask_pitch = obj_mask[k].pitch;
+        o.x0 = 0; o.y0 = 0; o.x1 = w; o.y1 = h;
+        if (rects) {
+            o.x0 = rects[4 * k] < 0 ? 0 : rects[4 * k]; o.y0 = rects[4 * k + 1] < 0 ? 0 : rects[4 * k + 1];
+            o.x1 = rects[4 * k + 2] > w ? w : rects[4 * k + 2]; o.y1 = rects[4 * k + 3] > h ? h : rects[4 * k + 3];
+        }
+        o.id = ids[k];
+    }
+    P.n_obj = n_obj; P.w = w; P.h = h; P.boundary = boundary;
+    P.bg_ray = (const float*)bg_ray->ptr; P.bg_ray_pitch = bg_ray->pitch;
+    P.bg_vert = (const float*)bg_vert->ptr; P.bg_vert_pitch = bg_vert->pitch;
+    P.bg_norm = (const float*)bg_norm->ptr; P.bg_norm_pitch = bg_norm->pitch;
+    P.bg_mask = (const uint8_t*)bg_mask->ptr; P.bg_mask_pitch = bg_mask->pitch;
+    P.ray = (float*)ray->ptr; P.ray_pitch = ray->pitch;
+    P.vert = (float*)vert->ptr; P.vert_pitch = vert->pitch;
+    P.norm = (float*)norm->ptr; P.norm_pitch = norm->pitch;
+    P.seg = (uint8_t*)seg->ptr; P.seg_pitch = seg->pitch;
+    P.vis_count = vis_count;
+    if (n_obj > 0) cudaMemsetAsync(vis_count, 0, sizeof(int32_t) * n_obj, (cudaStream_t)stream);
+    const dim3 grid((w + 31) / 32, (h + 7) / 8);
+    k_composite<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    return launch_status();
+}

@@ -1,0 +1,195 @@
+"""Level-1 operator API on torch CUDA tensors -- the Python mirror of
+emf::cuda::TSDF::* / emf::cuda::ObjTSDF::* / emf::cuda::EMFusion::computePoints
+(reference include/EMFusion/core/cuda/{TSDF,ObjTSDF,EMFusion}.cuh).  Every function is one
+call through the C ABI on torch's current stream; tensors are only used for their device
+pointer, shape and stride.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Image, Pose, TsdfParams, Volume, check
+from .poses import Affine
+
+
+def _stream(stream=None) -> int:
+    if stream is None:
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, torch.cuda.Stream):
+        return stream.cuda_stream
+    return int(stream)
+
+
+def image(t: torch.Tensor) -> Image:
+    """2-D (H, W) or 3-D (H, W, C) CUDA tensor, rows contiguous -> emf_image."""
+    if not t.is_cuda:
+        raise _lib.EmfError("emfusion_b200 operates on CUDA tensors only (no CPU fallback)")
+    if t.dim() == 3:
+        if t.stride(2) != 1 or t.stride(1) != t.shape[2]:
+            raise _lib.EmfError("image channels must be interleaved and contiguous")
+    elif t.dim() == 2:
+        if t.stride(1) != 1:
+            raise _lib.EmfError("image rows must be contiguous")
+    else:
+        raise _lib.EmfError("image must be (H, W) or (H, W, C)")
+    return Image(t.data_ptr(), t.stride(0) * t.element_size(), t.shape[1], t.shape[0])
+
+
+def images(ts: Sequence[torch.Tensor]):
+    arr = (Image * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = image(t)
+    return arr
+
+
+def pose(a: Affine) -> Pose:
+    p = Pose()
+    p.R[:] = a.rotation32().tolist()
+    p.t[:] = a.translation32().tolist()
+    return p
+
+
+def poses(aa: Sequence[Affine]):
+    arr = (Pose * len(aa))()
+    for i, a in enumerate(aa):
+        arr[i] = pose(a)
+    return arr
+
+
+def _f9(K) -> C.Array:
+    return (C.c_float * 9)(*np.asarray(K, dtype=np.float32).reshape(9).tolist())
+
+
+def _i3(res) -> C.Array:
+    return (C.c_int * 3)(*[int(r) for r in res])
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise _lib.EmfError("volume arrays must be contiguous CUDA tensors")
+    return t.data_ptr()
+
+
+def volume(tsdf, weights, res, voxel_size, truncdist, grads=None, fg_probs=None, vid=0) -> Volume:
+    v = Volume()
+    v.tsdf = _ptr(tsdf)
+    v.weights = _ptr(weights)
+    v.grads = _ptr(grads)
+    v.fg_probs = _ptr(fg_probs)
+    v.res[:] = [int(r) for r in res]
+    v.voxel_size = float(voxel_size)
+    v.truncdist = float(truncdist)
+    v.id = int(vid)
+    return v
+
+
+def tsdf_params(max_tsdf_weight=64.0, assoc_sigma=0.02, alpha=0.8, uni_prior=1.0) -> TsdfParams:
+    return TsdfParams(max_tsdf_weight, assoc_sigma, alpha, uni_prior)
+
+
+# ---- level 1 --------------------------------------------------------------------------------
+def computePoints(depth, points, intr, stream=None):
+    check(_lib.lib().emf_compute_points(image(depth), image(points), _f9(intr), _stream(stream)), "computePoints")
+
+
+def updateTSDF(depth, assocWeights, tsdfVol, tsdfWeights, rel_pose_OC: Affine, intr, volumeRes, voxelSize,
+               truncdist, maxWeight, stream=None):
+    check(_lib.lib().emf_update_tsdf(image(depth), image(assocWeights), _ptr(tsdfVol), _ptr(tsdfWeights),
+                                     pose(rel_pose_OC), _f9(intr), _i3(volumeRes), voxelSize, truncdist, maxWeight,
+                                     _stream(stream)), "updateTSDF")
+
+
+def computeTSDFGrads(tsdfVol, tsdfGrads, volumeRes, stream=None):
+    check(_lib.lib().emf_compute_tsdf_grads(_ptr(tsdfVol), _ptr(tsdfGrads), _i3(volumeRes), _stream(stream)),
+          "computeTSDFGrads")
+
+
+def raycastTSDF(tsdfVol, tsdfGrads, tsdfWeights, raylengths, vertices, normals, mask, rel_pose_CO: Affine, intr,
+                volumeRes, voxelSize, truncdist, fgProbs=None, hit_voxel=None, stream=None):
+    check(_lib.lib().emf_raycast_tsdf(_ptr(tsdfVol), _ptr(tsdfGrads), _ptr(tsdfWeights), _ptr(fgProbs),
+                                      image(raylengths), image(vertices), image(normals), image(mask),
+                                      pose(rel_pose_CO), _f9(intr), _i3(volumeRes), voxelSize, truncdist,
+                                      _ptr(hit_voxel), _stream(stream)), "raycastTSDF")
+
+
+def getVolumeVals(vol, points, rel_pose_CO: Affine, volumeRes, voxelSize, vals, stream=None):
+    check(_lib.lib().emf_get_volume_vals(_ptr(vol), image(points), pose(rel_pose_CO), _i3(volumeRes), voxelSize,
+                                         image(vals), _stream(stream)), "getVolumeVals")
+
+
+def updateFgBgProbs(mask, occluded_mask, tsdfVol, tsdfWeights, fgBgProbs, rel_pose_OC: Affine, intr, volumeRes,
+                    voxelSize, stream=None):
+    check(_lib.lib().emf_update_fgbg_probs(image(mask), image(occluded_mask), _ptr(tsdfVol), _ptr(tsdfWeights),
+                                           _ptr(fgBgProbs), pose(rel_pose_OC), _f9(intr), _i3(volumeRes), voxelSize,
+                                           _stream(stream)), "updateFgBgProbs")
+
+
+def computeFgProbs(fgBgProbs, fgProbs, fgVolMask=None, stream=None):
+    check(_lib.lib().emf_compute_fg_probs(_ptr(fgBgProbs), fgProbs.numel(), _ptr(fgProbs), _ptr(fgVolMask),
+                                          _stream(stream)), "computeFgProbs")
+
+
+# ---- level 2 / 3 ----------------------------------------------------------------------------
+def computeAssociation(vol: Volume, points, rel_pose_CO: Affine, params: TsdfParams, associationWeights,
+                       associationMask=None, stream=None):
+    check(_lib.lib().emf_compute_association(C.byref(vol), image(points), pose(rel_pose_CO), C.byref(params),
+                                             image(associationWeights),
+                                             image(associationMask) if associationMask is not None else None,
+                                             _stream(stream)), "computeAssociation")
+
+
+def _vol_array(vols: Sequence[Volume]):
+    arr = (Volume * len(vols))()
+    for i, v in enumerate(vols):
+        arr[i] = v
+    return arr
+
+
+def assocWeights(vols, rel_poses_CO, points, params: TsdfParams, assoc_out, mode=0, norm=None, stream=None):
+    check(_lib.lib().emf_assoc_weights(len(vols), _vol_array(vols), poses(rel_poses_CO), image(points),
+                                       C.byref(params), images(assoc_out), mode,
+                                       image(norm) if norm is not None else None, _stream(stream)), "assocWeights")
+
+
+def assocNormalise(assoc_io, norm, stream=None):
+    check(_lib.lib().emf_assoc_normalise(len(assoc_io), images(assoc_io), image(norm), _stream(stream)),
+          "assocNormalise")
+
+
+def volumeScreenRect(volumeRes, voxelSize, rel_pose_CO: Affine, intr, width, height):
+    out = (C.c_int * 4)()
+    check(_lib.lib().emf_volume_screen_rect(_i3(volumeRes), voxelSize, pose(rel_pose_CO), _f9(intr), width, height,
+                                            out), "volumeScreenRect")
+    return list(out)
+
+
+def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out, mask_out, stream=None):
+    flat = (C.c_int * (4 * len(vols)))(*[int(v) for r in rects for v in r]) if rects is not None else None
+    check(_lib.lib().emf_raycast_volumes(len(vols), _vol_array(vols), poses(rel_poses_CO), _f9(intr), flat,
+                                         images(ray_out), images(vert_out), images(norm_out), images(mask_out),
+                                         _stream(stream)), "raycastVolumes")
+
+
+def raycastComposite(ids, rects, obj_ray, obj_vert, obj_norm, obj_mask, bg_ray, bg_vert, bg_norm, bg_mask, boundary,
+                     ray, vert, norm, seg, vis_count, stream=None):
+    n = len(ids)
+    ids_a = (C.c_int * max(n, 1))(*[int(i) for i in ids])
+    flat = (C.c_int * max(4 * n, 1))(*[int(v) for r in rects for v in r]) if rects is not None else None
+    check(_lib.lib().emf_raycast_composite(n, ids_a, flat, images(obj_ray) if n else None,
+                                           images(obj_vert) if n else None, images(obj_norm) if n else None,
+                                           images(obj_mask) if n else None, image(bg_ray), image(bg_vert),
+                                           image(bg_norm), image(bg_mask), boundary, image(ray), image(vert),
+                                           image(norm), image(seg), _ptr(vis_count), _stream(stream)),
+          "raycastComposite")
+
+
+def integrateVolumes(vols, rel_poses_OC, intr, depth, assoc, maxWeight, stream=None):
+    check(_lib.lib().emf_integrate_volumes(len(vols), _vol_array(vols), poses(rel_poses_OC), _f9(intr), image(depth),
+                                           images(assoc), maxWeight, _stream(stream)), "integrateVolumes")

@@ -1,0 +1,196 @@
+/*
+ * emf_b200.h -- C ABI of the B200-native multi-volume TSDF engine.
+ *
+ * This is the drop-in boundary for EM-Fusion's dense hot path (SURVEY.md
+ * section 8b).  Every entry point takes plain pointers, sizes and a CUDA
+ * stream; nothing allocates, frees or synchronises; all work is asynchronous
+ * on the given stream (as the reference's level-1 operators are,
+ * /root/reference/src/core/cuda/TSDF.cu:422).  Return value: EMF_OK or a
+ * negative EMF_ERR_* code; nothing throws across the boundary.
+ *
+ * Conventions shared with the reference:
+ *  - volumes are continuous float arrays, element (z*Ry + y, x), x fastest
+ *    (reference src/core/TSDF.cpp:35-42); all pointers 16-byte aligned;
+ *  - images are 2-D device arrays with a byte pitch (cv::cuda::GpuMat::step);
+ *  - poses are RELATIVE poses already composed by the caller exactly as the
+ *    reference host code does (src/core/TSDF.cpp:112,141,162): row-major 3x3
+ *    rotation + translation, packed floats like cv::Matx33f::val / cv::Vec3f::val;
+ *  - intrinsics are the row-major 3x3 camera matrix (cv::Matx33f).
+ *
+ * Paths below are relative to /root/reference.
+ */
+#ifndef EMF_B200_H
+#define EMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMF_OK 0
+#define EMF_ERR_INVALID (-1)     /* bad argument (null pointer, size, alignment) */
+#define EMF_ERR_CUDA (-2)        /* CUDA launch error (cudaPeekAtLastError) */
+#define EMF_ERR_UNSUPPORTED (-3) /* valid but unsupported (e.g. too many volumes in one batch) */
+
+#if defined(__GNUC__)
+#define EMF_API __attribute__((visibility("default")))
+#else
+#define EMF_API
+#endif
+
+#define EMF_MAX_VOLUMES 96 /* volumes per batched call (background + objects) */
+
+typedef struct CUstream_st* emf_stream_t; /* == cudaStream_t; NULL = default stream */
+
+/* 2-D device image (cv::cuda::GpuMat header): ptr, byte pitch, width, height. */
+typedef struct emf_image {
+    void* ptr;
+    size_t pitch;
+    int width;
+    int height;
+} emf_image;
+
+/* Relative rigid pose: x' = R x + t. */
+typedef struct emf_pose {
+    float R[9];
+    float t[3];
+} emf_pose;
+
+/* TSDFParams subset consumed by the path (include/EMFusion/core/data.h:32-71). */
+typedef struct emf_tsdf_params {
+    float max_tsdf_weight; /* 64  */
+    float assoc_sigma;     /* 0.02 */
+    float alpha;           /* 0.8 */
+    float uni_prior;       /* 1.0 */
+} emf_tsdf_params;
+
+/* One TSDF volume (emf::TSDF / emf::ObjTSDF device state,
+ * include/EMFusion/core/TSDF.h:285-300, ObjTSDF.h:197-215). */
+typedef struct emf_volume {
+    float* tsdf;           /* tsdfVol      Rx*Ry*Rz floats */
+    float* weights;        /* tsdfWeights  Rx*Ry*Rz floats */
+    const float* grads;    /* tsdfGrads (float3 per voxel) or NULL: gradients are then taken on the fly */
+    const float* fg_probs; /* fgProbs (objects) or NULL (background) */
+    int res[3];            /* volumeRes (x, y, z) */
+    float voxel_size;
+    float truncdist;
+    int id;                /* 0 = background, >0 = ObjTSDF::id */
+} emf_volume;
+
+/* ---------------------------------------------------------------------------
+ * Level 1: operator API -- one symbol per reference free function.
+ * ------------------------------------------------------------------------- */
+
+/* emf::cuda::EMFusion::computePoints, include/EMFusion/core/cuda/EMFusion.cuh:39-40
+ * (src/core/cuda/EMFusion.cu:29-61).  depth: W x H f32; points: W x H float3. */
+EMF_API int emf_compute_points(const emf_image* depth, const emf_image* points, const float K[9], emf_stream_t stream);
+
+/* emf::cuda::TSDF::updateTSDF, include/EMFusion/core/cuda/TSDF.cuh:115-123
+ * (src/core/cuda/TSDF.cu:327-427).  T_oc = cam_pose^-1 * pose. */
+EMF_API int emf_update_tsdf(const emf_image* depth, const emf_image* assoc_weights, float* tsdf, float* weights,
+                    const emf_pose* T_oc, const float K[9], const int res[3], float voxel_size,
+                    float truncdist, float max_weight, emf_stream_t stream);
+
+/* emf::TSDF::updateGradients = setTo(0) + emf::cuda::TSDF::computeTSDFGrads,
+ * src/core/TSDF.cpp:120-123, include/EMFusion/core/cuda/TSDF.cuh:133-135.
+ * One pass; the zero planes are written by the same kernel. grads: float3 per voxel. */
+EMF_API int emf_compute_tsdf_grads(const float* tsdf, float* grads, const int res[3], emf_stream_t stream);
+
+/* emf::cuda::TSDF::raycastTSDF, include/EMFusion/core/cuda/TSDF.cuh:160-169
+ * (src/core/cuda/TSDF.cu:466-601).  T_co = pose^-1 * cam_pose.
+ * raylengths is in/out (non-zero = far clip); vertices/normals (float3) and mask (u8)
+ * are written at hit pixels only -- callers pre-clear, as in the reference.
+ * grads may be NULL (forward differences on the fly, bit-identical);
+ * fg_probs non-NULL applies ObjTSDF::raycast's weight masking
+ * (src/core/ObjTSDF.cpp:209-210: weights where fgProb > 0.5, else 0) inline.
+ * hit_voxel (optional, W x H x 3 int32, continuous): trunc(v*) at hit pixels. */
+EMF_API int emf_raycast_tsdf(const float* tsdf, const float* grads, const float* weights, const float* fg_probs,
+                     const emf_image* raylengths, const emf_image* vertices, const emf_image* normals,
+                     const emf_image* mask, const emf_pose* T_co, const float K[9], const int res[3],
+                     float voxel_size, float truncdist, int32_t* hit_voxel, emf_stream_t stream);
+
+/* emf::cuda::TSDF::getVolumeVals (1-channel), include/EMFusion/core/cuda/TSDF.cuh:204-210
+ * (src/core/cuda/TSDF.cu:662-726).  vals is fully overwritten (0 where not gathered). */
+EMF_API int emf_get_volume_vals(const float* vol, const emf_image* points, const emf_pose* T_co, const int res[3],
+                        float voxel_size, const emf_image* vals, emf_stream_t stream);
+
+/* emf::cuda::ObjTSDF::updateFgBgProbs, include/EMFusion/core/cuda/ObjTSDF.cuh:49-56
+ * (src/core/cuda/ObjTSDF.cu:29-107).  mask/occluded: W x H u8; fgbg: float2 per voxel. */
+EMF_API int emf_update_fgbg_probs(const emf_image* mask, const emf_image* occluded, const float* tsdf,
+                          const float* weights, float* fgbg, const emf_pose* T_oc, const float K[9],
+                          const int res[3], float voxel_size, emf_stream_t stream);
+
+/* emf::ObjTSDF::computeFgProbs, src/core/ObjTSDF.cpp:218-226 (6 OpenCV launches -> 1).
+ * fg_vol_mask (u8, 255 where fgProb > 0.5) may be NULL. */
+EMF_API int emf_compute_fg_probs(const float* fgbg, int64_t n_voxels, float* fg_probs, uint8_t* fg_vol_mask,
+                         emf_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Level 2: class-surface operations (one call = one reference method).
+ * ------------------------------------------------------------------------- */
+
+/* emf::TSDF::computeAssociation (src/core/TSDF.cpp:125-156) when vol->fg_probs == NULL,
+ * emf::ObjTSDF::computeAssociation (src/core/ObjTSDF.cpp:181-201) otherwise.
+ * assoc_out: W x H f32, fully overwritten, NOT normalised.
+ * assoc_mask_out (optional u8): associationMask (255 where the TSDF gather returned 0). */
+EMF_API int emf_compute_association(const emf_volume* vol, const emf_image* points, const emf_pose* T_co,
+                            const emf_tsdf_params* params, const emf_image* assoc_out,
+                            const emf_image* assoc_mask_out, emf_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Level 3: frame-level batched operations (one call = one EMFusion method).
+ * vols[0] is the background when has_background != 0; objects follow in the
+ * reference's iteration order (ascending id for the normaliser, list order for
+ * the composite -- identical in the reference because ids only grow).
+ * ------------------------------------------------------------------------- */
+
+/* emf::EMFusion::computeAssociationWeights, src/core/EMFusion.cpp:635-670.
+ * T_co[i] = pose_i^-1 * cam_pose.  assoc_out[i]: W x H f32 per volume.
+ * mode 0: compute + normalise across vols (single-GPU path; sum order = array order).
+ * mode 1: compute un-normalised weights and write their per-pixel sum to
+ *         norm_partial (multi-GPU: all-reduce norm_partial, then emf_assoc_normalise). */
+EMF_API int emf_assoc_weights(int n_vol, const emf_volume* vols, const emf_pose* T_co, const emf_image* points,
+                      const emf_tsdf_params* params, const emf_image* assoc_out, int mode,
+                      const emf_image* norm_partial, emf_stream_t stream);
+
+/* Divide every image by norm with x/0 -> 0 (src/core/EMFusion.cpp:659-665). */
+EMF_API int emf_assoc_normalise(int n_img, const emf_image* assoc_io, const emf_image* norm, emf_stream_t stream);
+
+/* Per-volume raycast of emf::EMFusion::raycast (src/core/EMFusion.cpp:745-754) for a whole
+ * batch in one launch.  Per volume i: ray_out[i] (f32, fully written inside rect, 0 = no hit),
+ * mask_out[i] (u8), vert_out[i]/norm_out[i] (float3, hit pixels only).  rects (n_vol x 4 ints:
+ * x0, y0, x1, y1, exclusive upper) bound the pixels each volume can cover; pixels outside a
+ * volume's rect are not touched and must be treated as "no hit" by the consumer. */
+EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
+                        const int* rects, const emf_image* ray_out, const emf_image* vert_out,
+                        const emf_image* norm_out, const emf_image* mask_out, emf_stream_t stream);
+
+/* Compositing of emf::EMFusion::raycast, src/core/EMFusion.cpp:760-794, in one launch.
+ * Objects i = 0..n_obj-1 in list order with ids[i]; background images bg_*.
+ * Outputs: ray/vert/norm/seg (seg u8) and vis_count[n_obj] (int32, device; zeroed by the call). */
+EMF_API int emf_raycast_composite(int n_obj, const int* ids, const int* rects, const emf_image* obj_ray,
+                          const emf_image* obj_vert, const emf_image* obj_norm, const emf_image* obj_mask,
+                          const emf_image* bg_ray, const emf_image* bg_vert, const emf_image* bg_norm,
+                          const emf_image* bg_mask, int boundary, const emf_image* ray, const emf_image* vert,
+                          const emf_image* norm, const emf_image* seg, int32_t* vis_count, emf_stream_t stream);
+
+/* emf::EMFusion::integrateDepth, src/core/EMFusion.cpp:865-889, one launch for all volumes.
+ * T_oc[i] = cam_pose^-1 * pose_i; assoc[i] = that volume's association image. */
+EMF_API int emf_integrate_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
+                          const emf_image* depth, const emf_image* assoc, float max_weight,
+                          emf_stream_t stream);
+
+/* Screen-space rectangle (x0,y0,x1,y1) that bounds every pixel whose ray can enter the
+ * volume's raycast box; full frame if a corner is behind the camera.  Host-side helper. */
+EMF_API int emf_volume_screen_rect(const int res[3], float voxel_size, const emf_pose* T_co, const float K[9],
+                           int width, int height, int rect_out[4]);
+
+/* Library identification: returns a static string "emf_b200 <version> sm_100a". */
+EMF_API const char* emf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMF_B200_H */

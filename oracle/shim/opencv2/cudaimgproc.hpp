@@ -1,0 +1,3 @@
+// see ../cvshim.hpp (type-only stand-in, test infrastructure)
+#pragma once
+#include <cvshim.hpp>
