@@ -17,6 +17,21 @@ from ._lib import Image, Pose, TsdfParams, Volume, check
 from .poses import Affine
 
 
+# kernels launched through this module, by C-ABI entry point (bench.py reports the sum as gpu_launches)
+LAUNCHES = {}
+_KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1, "raycastTSDF": 1, "getVolumeVals": 1,
+                     "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
+                     "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1}
+
+
+def _count(name: str) -> None:
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + _KERNELS_PER_CALL[name]
+
+
+def launches_total() -> int:
+    return sum(LAUNCHES.values())
+
+
 def _stream(stream=None) -> int:
     if stream is None:
         return torch.cuda.current_stream().cuda_stream
@@ -97,6 +112,7 @@ def tsdf_params(max_tsdf_weight=64.0, assoc_sigma=0.02, alpha=0.8, uni_prior=1.0
 # ---- level 1 --------------------------------------------------------------------------------
 def computePoints(depth, points, intr, stream=None):
     check(_lib.lib().emf_compute_points(image(depth), image(points), _f9(intr), _stream(stream)), "computePoints")
+    _count("computePoints")
 
 
 def updateTSDF(depth, assocWeights, tsdfVol, tsdfWeights, rel_pose_OC: Affine, intr, volumeRes, voxelSize,
@@ -104,11 +120,13 @@ def updateTSDF(depth, assocWeights, tsdfVol, tsdfWeights, rel_pose_OC: Affine, i
     check(_lib.lib().emf_update_tsdf(image(depth), image(assocWeights), _ptr(tsdfVol), _ptr(tsdfWeights),
                                      pose(rel_pose_OC), _f9(intr), _i3(volumeRes), voxelSize, truncdist, maxWeight,
                                      _stream(stream)), "updateTSDF")
+    _count("updateTSDF")
 
 
 def computeTSDFGrads(tsdfVol, tsdfGrads, volumeRes, stream=None):
     check(_lib.lib().emf_compute_tsdf_grads(_ptr(tsdfVol), _ptr(tsdfGrads), _i3(volumeRes), _stream(stream)),
           "computeTSDFGrads")
+    _count("computeTSDFGrads")
 
 
 def raycastTSDF(tsdfVol, tsdfGrads, tsdfWeights, raylengths, vertices, normals, mask, rel_pose_CO: Affine, intr,
@@ -117,11 +135,13 @@ def raycastTSDF(tsdfVol, tsdfGrads, tsdfWeights, raylengths, vertices, normals, 
                                       image(raylengths), image(vertices), image(normals), image(mask),
                                       pose(rel_pose_CO), _f9(intr), _i3(volumeRes), voxelSize, truncdist,
                                       _ptr(hit_voxel), _stream(stream)), "raycastTSDF")
+    _count("raycastTSDF")
 
 
 def getVolumeVals(vol, points, rel_pose_CO: Affine, volumeRes, voxelSize, vals, stream=None):
     check(_lib.lib().emf_get_volume_vals(_ptr(vol), image(points), pose(rel_pose_CO), _i3(volumeRes), voxelSize,
                                          image(vals), _stream(stream)), "getVolumeVals")
+    _count("getVolumeVals")
 
 
 def updateFgBgProbs(mask, occluded_mask, tsdfVol, tsdfWeights, fgBgProbs, rel_pose_OC: Affine, intr, volumeRes,
@@ -129,11 +149,13 @@ def updateFgBgProbs(mask, occluded_mask, tsdfVol, tsdfWeights, fgBgProbs, rel_po
     check(_lib.lib().emf_update_fgbg_probs(image(mask), image(occluded_mask), _ptr(tsdfVol), _ptr(tsdfWeights),
                                            _ptr(fgBgProbs), pose(rel_pose_OC), _f9(intr), _i3(volumeRes), voxelSize,
                                            _stream(stream)), "updateFgBgProbs")
+    _count("updateFgBgProbs")
 
 
 def computeFgProbs(fgBgProbs, fgProbs, fgVolMask=None, stream=None):
     check(_lib.lib().emf_compute_fg_probs(_ptr(fgBgProbs), fgProbs.numel(), _ptr(fgProbs), _ptr(fgVolMask),
                                           _stream(stream)), "computeFgProbs")
+    _count("computeFgProbs")
 
 
 # ---- level 2 / 3 ----------------------------------------------------------------------------
@@ -143,6 +165,7 @@ def computeAssociation(vol: Volume, points, rel_pose_CO: Affine, params: TsdfPar
                                              image(associationWeights),
                                              image(associationMask) if associationMask is not None else None,
                                              _stream(stream)), "computeAssociation")
+    _count("computeAssociation")
 
 
 def _vol_array(vols: Sequence[Volume]):
@@ -156,11 +179,13 @@ def assocWeights(vols, rel_poses_CO, points, params: TsdfParams, assoc_out, mode
     check(_lib.lib().emf_assoc_weights(len(vols), _vol_array(vols), poses(rel_poses_CO), image(points),
                                        C.byref(params), images(assoc_out), mode,
                                        image(norm) if norm is not None else None, _stream(stream)), "assocWeights")
+    _count("assocWeights")
 
 
 def assocNormalise(assoc_io, norm, stream=None):
     check(_lib.lib().emf_assoc_normalise(len(assoc_io), images(assoc_io), image(norm), _stream(stream)),
           "assocNormalise")
+    _count("assocNormalise")
 
 
 def volumeScreenRect(volumeRes, voxelSize, rel_pose_CO: Affine, intr, width, height):
@@ -175,6 +200,7 @@ def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out,
     check(_lib.lib().emf_raycast_volumes(len(vols), _vol_array(vols), poses(rel_poses_CO), _f9(intr), flat,
                                          images(ray_out), images(vert_out), images(norm_out), images(mask_out),
                                          _stream(stream)), "raycastVolumes")
+    _count("raycastVolumes")
 
 
 def raycastComposite(ids, rects, obj_ray, obj_vert, obj_norm, obj_mask, bg_ray, bg_vert, bg_norm, bg_mask, boundary,
@@ -188,8 +214,10 @@ def raycastComposite(ids, rects, obj_ray, obj_vert, obj_norm, obj_mask, bg_ray, 
                                            image(bg_norm), image(bg_mask), boundary, image(ray), image(vert),
                                            image(norm), image(seg), _ptr(vis_count), _stream(stream)),
           "raycastComposite")
+    _count("raycastComposite")
 
 
 def integrateVolumes(vols, rel_poses_OC, intr, depth, assoc, maxWeight, stream=None):
     check(_lib.lib().emf_integrate_volumes(len(vols), _vol_array(vols), poses(rel_poses_OC), _f9(intr), image(depth),
                                            images(assoc), maxWeight, _stream(stream)), "integrateVolumes")
+    _count("integrateVolumes")

@@ -392,7 +392,27 @@ REF_API int emfref_frame_fill_assoc(void* h, int i, float v) {
 // device-to-device copy out of frame-owned buffers (used by the Python test binding)
 REF_API int emfref_memcpy_d2d(void* dst, const void* src, size_t n) {
     cudaDeviceSynchronize();
-    const cudaError_t e = cudaMemcpy(dst, src, n, cudaMemcpyDeviceToDevice);
+    const cudaError_t e = cudaMemcpy(dst, src, n, cudaMemcpyDefault);   // any direction (UVA)
     cudaDeviceSynchronize();
     return e == cudaSuccess ? 0 : -2;
+}
+
+// emf::cuda::EMFusion::computePoints (src/core/cuda/EMFusion.cu:29-61).  That file does not compile
+// against CCCL 2.8 (thrust::sort at :87), so its ten lines of arithmetic are restated here, including the
+// launcher's setTo(0) and cudaDeviceSynchronize() (:57-60).
+__global__ void k_ref_points(const float* depth, float* points, int w, int h, float fx, float fy, float cx, float cy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float d = depth[(size_t)y * w + x];
+    float* p = points + 3 * ((size_t)y * w + x);
+    p[0] = __fdiv_rn(__fmul_rn(__fsub_rn((float)x, cx), d), fx);
+    p[1] = __fdiv_rn(__fmul_rn(__fsub_rn((float)y, cy), d), fy);
+    p[2] = d;
+}
+REF_API int emfref_compute_points(const float* depth, float* points, int w, int h, const float* K) {
+    cudaMemsetAsync(points, 0, (size_t)w * h * 12, nullptr);
+    dim3 threads(32, 32), blocks((w + 31) / 32, (h + 31) / 32);
+    k_ref_points<<<blocks, threads>>>(depth, points, w, h, K[0], K[4], K[2], K[5]);
+    cudaDeviceSynchronize();
+    return status();
 }

@@ -56,6 +56,7 @@ def lib():
         L.emfref_frame_set_visible.restype = None
         L.emfref_frame_fill_assoc.argtypes = [vp, ci, cf]
         L.emfref_memcpy_d2d.argtypes = [vp, vp, C.c_size_t]
+        L.emfref_compute_points.argtypes = [vp, vp, ci, ci, vp]
         _lib = L
     return _lib
 
@@ -73,6 +74,12 @@ def _s():
 def _chk(rc, what):
     if rc != 0:
         raise RuntimeError(f"reference {what} failed rc={rc}")
+
+
+def compute_points(depth, points, K):
+    h, w = depth.shape
+    kk, pk = _h(K)
+    _chk(lib().emfref_compute_points(depth.data_ptr(), points.data_ptr(), w, h, pk), "computePoints")
 
 
 def update_tsdf(depth, assoc, tsdf, weights, R, t, K, res, voxel, trunc, maxw):
@@ -171,6 +178,12 @@ class RefFrame:
                     vert=_from_ptr(L.emfref_frame_vert(self.hd), (self.h, self.w, 3), torch.float32),
                     norm=_from_ptr(L.emfref_frame_norm(self.hd), (self.h, self.w, 3), torch.float32),
                     seg=_from_ptr(L.emfref_frame_seg(self.hd), (self.h, self.w), torch.uint8))
+
+    def download_composite(self, seg_host, ray_host):
+        """blocking D2H copies of modelSegmentation / raylengths into (pinned) host tensors"""
+        L = lib()
+        _chk(L.emfref_memcpy_d2d(seg_host.data_ptr(), L.emfref_frame_seg(self.hd), seg_host.numel()), "memcpy")
+        _chk(L.emfref_memcpy_d2d(ray_host.data_ptr(), L.emfref_frame_ray(self.hd), ray_host.numel() * 4), "memcpy")
 
     def visible(self, i):
         return bool(lib().emfref_frame_visible(self.hd, i))
