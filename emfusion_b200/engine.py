@@ -36,8 +36,10 @@ class EMFusionEngine:
         dev = self.device
         self.background: Optional[TSDF] = None
         if rank == 0:
+            # float * float as in the reference (src/core/EMFusion.cpp:31)
             self.background = TSDF(params.globalVolumeDims, params.globalVoxelSize,
-                                   params.globalRelTruncDist * params.globalVoxelSize, params.volumePose,
+                                   float(np.float32(params.globalRelTruncDist) * np.float32(params.globalVoxelSize)),
+                                   params.volumePose,
                                    params.tsdfParams, params.frameSize, dev, materialize_grads)
         self.objects: List[ObjTSDF] = []          # local shard, list order
         self.all_ids: List[int] = []              # global list order (ids), identical on every rank
@@ -75,7 +77,8 @@ class EMFusionEngine:
         if self.owner_of(idx) != self.rank:
             ObjTSDF.nextID = new_id
             return None
-        obj = ObjTSDF(res, voxelSize, self.params.objRelTruncDist * voxelSize, obj_pose, self.params.tsdfParams,
+        obj = ObjTSDF(res, voxelSize, float(np.float32(self.params.objRelTruncDist) * np.float32(voxelSize)), obj_pose,
+                      self.params.tsdfParams,
                       self.params.frameSize, self.device, self.materialize_grads)
         assert obj.id == new_id
         self.objects.append(obj)
