@@ -236,7 +236,9 @@ EMFO_API void emfo_raycast(const float* tsdf, const float* grads, const float* w
                            float* raylengths, float* vertices, float* normals, uint8_t* mask,
                            int w, int h, const float* R, const float* t, const float* K,
                            const int* res, float voxel, float trunc,
-                           int32_t* hit_voxel, int64_t* steps) {
+                           int32_t* hit_voxel, int64_t* steps, int32_t* step_img) {
+    /* step_img (optional, w*h*3 int32): per pixel, in-bounds march samples taken with step == truncdist,
+     * == voxel, == voxel/2 (measurement only: the roofline numerator and the divergence statistics) */
     const int rx = res[0], ry = res[1], rz = res[2];
     const float frx = (float)rx, fry = (float)ry, frz = (float)rz;
     /* boxBounds = (volSize - 1) / 2 * voxelSize with INTEGER division
@@ -297,6 +299,7 @@ EMFO_API void emfo_raycast(const float* tsdf, const float* grads, const float* w
                 vz = hz + FMA(dz, tcur, oz) / voxel;
                 if (out_of(vx, vy, vz, 2.0f, frx, fry, frz)) continue;
                 ++n_steps;
+                if (step_img) ++step_img[3 * pix + (step == trunc ? 0 : (step == voxel ? 1 : 2))];
                 const float fn = trilinear(tsdf, rx, ry, vx, vy, vz);
                 const float wn = trilinear(weights, rx, ry, vx, vy, vz);
                 if (f < 0.0f && fn > 0.0f && wn > 0.0f) break; /* back face :532 */

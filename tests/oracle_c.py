@@ -27,7 +27,7 @@ class Oracle:
                                        C.c_float, C.c_void_p]
         L.emfo_compute_grads.argtypes = [_f, _f, _i32]
         L.emfo_raycast.argtypes = [_f, _f, _f, _f, _f, _f, _u8, C.c_int, C.c_int, _f, _f, _f, _i32, C.c_float,
-                                   C.c_float, C.c_void_p, C.c_void_p]
+                                   C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emfo_get_volume_vals.argtypes = [_f, _f, C.c_int, C.c_int, _f, _f, _i32, C.c_float, _f, C.c_void_p]
         L.emfo_assoc_volume.argtypes = [_f, C.c_void_p, _f, C.c_int, C.c_int, _f, _f, _i32, C.c_float, C.c_float,
                                         C.c_float, C.c_float, C.c_float, _f, C.c_void_p, _f]
@@ -71,16 +71,18 @@ class Oracle:
         self.L.emfo_compute_grads(tsdf, g, self._r(res))
         return g
 
-    def raycast(self, tsdf, grads, weights, R, t, K, res, voxel, trunc, w, h, raylengths=None):
+    def raycast(self, tsdf, grads, weights, R, t, K, res, voxel, trunc, w, h, raylengths=None, step_stats=False):
         ray = np.zeros((h, w), dtype=np.float32) if raylengths is None else np.ascontiguousarray(raylengths).copy()
         vert = np.zeros((h, w, 3), dtype=np.float32)
         norm = np.zeros((h, w, 3), dtype=np.float32)
         mask = np.zeros((h, w), dtype=np.uint8)
         hit = np.full((h, w, 3), -1, dtype=np.int32)
         steps = np.zeros(2, dtype=np.int64)
+        step_img = np.zeros((h, w, 3), dtype=np.int32) if step_stats else None
         self.L.emfo_raycast(tsdf, grads, weights, ray, vert, norm, mask, w, h, self._p(R), self._p(t), self._p(K),
-                            self._r(res), voxel, trunc, hit.ctypes.data, steps.ctypes.data)
-        return dict(ray=ray, vert=vert, norm=norm, mask=mask, hit=hit, steps=steps)
+                            self._r(res), voxel, trunc, hit.ctypes.data, steps.ctypes.data,
+                            step_img.ctypes.data if step_stats else None)
+        return dict(ray=ray, vert=vert, norm=norm, mask=mask, hit=hit, steps=steps, step_img=step_img)
 
     def get_volume_vals(self, vol, points, R, t, res, voxel):
         h, w = points.shape[:2]
