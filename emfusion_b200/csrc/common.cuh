@@ -7,6 +7,9 @@
 
 namespace emfb {
 
+// status codes of an 8-voxel x-segment (emf_volume::seg_status) / an 8^3 brick (emf_volume::brick_flags)
+enum : int { kMixed = 0, kAllOne = 1, kAllZero = 2, kAllMinusOne = 3 };
+
 // Pitched 2-D image view (device side).
 template <typename T>
 struct Img {

@@ -2,16 +2,29 @@
 //
 // Replaces emf::cuda::TSDF::updateTSDF (reference src/core/cuda/TSDF.cu:327-427),
 // called once per volume on its own stream by emf::EMFusion::integrateDepth
-// (src/core/EMFusion.cpp:865-889).  Here every volume of the frame is a row in a
-// kernel-parameter descriptor table and a CTA finds its volume with a short
-// search over the table's block prefix sums.
+// (src/core/EMFusion.cpp:865-889).  Every volume of the frame is a row in a
+// descriptor table (kernel parameter, constant bank).
 //
-// Traversal: a thread owns 4 consecutive x-voxels (one float4 of tsdf, one of
-// weights), a warp a contiguous 512-byte run, a CTA 512 voxels.  Voxels whose
-// projection misses the image are never read or written (as in the reference);
-// the others move 16 B (update), 8 B (occluded/unseen) or 4 B (occluded/seen).
-// All arithmetic is the canonical sequence of emf_math.cuh, so the result is
-// bit-identical to the reference build for any input.
+// k_integrate_rows (the hot kernel; x-resolution a multiple of 8, 16-byte aligned arrays):
+//  * persistent grid (a multiple of the SM count); a warp owns whole x-rows (y,z fixed) of a
+//    volume, rows are dealt round-robin so neighbouring rows -- which project to neighbouring
+//    image rows -- are in flight together;
+//  * per row, the x-interval whose voxels can project into the image is solved in closed form
+//    (four half-planes of the pinhole frustum, padded by kMarginPx pixels and one voxel), so the
+//    ~65 % of a room-sized grid that lies outside the frustum costs one warp-uniform test per row
+//    instead of a projection per voxel.  The reference never touches those voxels either;
+//  * inside the interval a thread owns 4 consecutive voxels (one float4 of tsdf, one of weights);
+//  * the result is bit-identical to the reference build: all arithmetic that reaches memory is the
+//    canonical sequence of emf_math.cuh.  The expensive IEEE divisions/square roots are only
+//    evaluated where their exact value matters: the pixel index comes from an approximate quotient
+//    whenever that quotient is provably on the same side of the rounding boundary, and voxels that
+//    an approximate signed distance places safely outside the truncation band take the free-space
+//    (value +1, weight +1) or occluded branch without the exact distance;
+//  * optionally maintains three bitmaps with one bit per 4-voxel x-segment (all +1 / all 0 /
+//    all -1), written with warp ballots, from which k_safe_bits (safe.cu) derives the maps the
+//    raycast uses to skip march samples whose outcome is known (raycast.cu).
+//
+// k_integrate_simple: one thread per voxel, any resolution/alignment (ragged volumes).
 #include "common.cuh"
 
 namespace emfb {
@@ -19,220 +32,430 @@ namespace emfb {
 struct IntVol {
     float* tsdf;
     float* weights;
+    uint32_t* const_bits; // nullable: three bitmaps (all +1 / all 0 / all -1), one bit per 4-voxel x-segment
+    int wpr;              // 32-bit words per row in a bitmap
+    size_t map_words;     // words per bitmap
     const float* assoc;   // this volume's association image
     size_t assoc_pitch;
     float R[9];           // T_OC
     float t[3];
     int rx, ry, rz;
     float voxel, trunc;
-    int first_block;      // prefix sum of CTAs
+    int first_item;       // prefix sum of work items (rows for k_integrate_rows, CTAs for k_integrate_simple)
+    int gate;             // index into IntParams::gate_counts, or -1: integrate unconditionally
 };
 
 struct IntParams {
     IntVol v[EMF_MAX_VOLUMES];
     int n_vol;
-    int total_blocks;
+    int total_items;
     const float* depth;
     size_t depth_pitch;
     int w, h;
     float K[9];
     float max_weight;
+    const int32_t* gate_counts;   // nullable: device-side visibility counters (raycast composite)
+    int gate_thresh;              // a gated volume is integrated iff gate_counts[gate] > gate_thresh
+    unsigned long long* stats;    // nullable: [0] updated [1] marked -1 [2] occluded-seen [3] check-only [4] skipped-in-interval
 };
 
-constexpr int kIntThreads = 128;
-constexpr int kVec = 4;
+constexpr int kIntThreads = 256;
+constexpr int kSimpleThreads = 128;
+constexpr float kMarginPx = 3.0f;    // frustum half-planes are pushed out by this many pixels
+constexpr float kMinDepthCull = 0.02f;   // rows that come closer than this to the camera plane are not culled
 
-// class of a voxel after projection
-enum : int { kSkip = 0, kCheckOnly = 1, kValid = 2 };
+__device__ __forceinline__ int value_code(float v) {
+    return v == 1.0f ? kAllOne : (v == -1.0f ? kAllMinusOne : (v == 0.0f ? kAllZero : kMixed));
+}
 
-template <bool PINHOLE, int VEC>
-__global__ void __launch_bounds__(kIntThreads) k_integrate(const __grid_constant__ IntParams P) {
-    // ---- which volume? (uniform per CTA; table lives in the constant bank)
-    int lo = 0, hi = P.n_vol - 1;
-    const int b = blockIdx.x;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (P.v[mid].first_block <= b) lo = mid; else hi = mid - 1;
+// __float2int_rn(fdiv(q, qz)) without the IEEE division whenever an approximate quotient is
+// provably on the same side of every rounding boundary (error of q * rcp.approx(qz) is below
+// 2^-22 |q/qz|; we keep 2^-20 |u| + 2^-20 away from the half-integers).
+__device__ __forceinline__ int round_quotient(float q, float qz, float rz) {
+    const float u = q * rz;
+    const float r = rintf(u);
+    const float tol = 0.5f - (fabsf(u) * 9.5367431640625e-7f + 9.5367431640625e-7f);
+    if (fabsf(u - r) < tol && fabsf(u) < 1.0e6f) return (int)r;
+    return __float2int_rn(fdiv(q, qz));
+}
+
+template <bool PINHOLE, bool TABLE, bool STATS>
+__global__ void __launch_bounds__(kIntThreads, 3) k_integrate_rows(const __grid_constant__ IntParams P) {
+    extern __shared__ float s_tab[];   // [0, w): (x - cx) / fx ; [w, w + h): (y - cy) / fy
+    if (TABLE) {
+        for (int i = threadIdx.x; i < P.w + P.h; i += kIntThreads)
+            s_tab[i] = i < P.w ? fdiv(fsub((float)i, P.K[2]), P.K[0]) : fdiv(fsub((float)(i - P.w), P.K[5]), P.K[4]);
+        __syncthreads();
     }
-    const IntVol& V = P.v[lo];
-    const int rx = V.rx, ry = V.ry;
-    const int64_t n_vox = (int64_t)rx * ry * V.rz;
-    const int64_t i0 = ((int64_t)(b - V.first_block) * kIntThreads + threadIdx.x) * VEC;
-    if (i0 >= n_vox) return;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = kIntThreads / 32;
+    const int gwarp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * warps_per_cta;
+    unsigned long long st[5] = {0, 0, 0, 0, 0};
 
-    const int64_t row = i0 / rx;            // z*Ry + y
-    const int x0 = (int)(i0 - row * rx);
-    const int z = (int)(row / ry);
-    const int y = (int)(row - (int64_t)z * ry);
+    int vi = 0;
+    for (int item = gwarp; item < P.total_items; item += n_warps) {
+        while (vi + 1 < P.n_vol && P.v[vi + 1].first_item <= item) ++vi;   // rows are dealt in ascending order
+        const IntVol& V = P.v[vi];
+        if (V.gate >= 0 && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh)) continue;   // not visible: not integrated
+        const int rx = V.rx, ry = V.ry;
+        const int row = item - V.first_item;          // z * Ry + y
+        const int z = row / ry;
+        const int y = row - z * ry;
+        const float s = V.voxel;
+        // (i - (R-1)/2.f) * voxelSize ; (R-1)*0.5 is exact
+        const float hx = fmul((float)(rx - 1), 0.5f);
+        const float cy = fmul(fsub((float)y, fmul((float)(ry - 1), 0.5f)), s);
+        const float cz = fmul(fsub((float)z, fmul((float)(V.rz - 1), 0.5f)), s);
+        const float my0 = fmul(V.R[1], cy), my1 = fmul(V.R[4], cy), my2 = fmul(V.R[7], cy);
 
-    const float s = V.voxel;
-    // (i - (R-1)/2.f) * voxelSize ; (R-1)*0.5 is exact
-    const float cy = fmul(fsub((float)y, fmul((float)(ry - 1), 0.5f)), s);
-    const float cz = fmul(fsub((float)z, fmul((float)(V.rz - 1), 0.5f)), s);
-    const float hx = fmul((float)(rx - 1), 0.5f);
-    const float my0 = fmul(V.R[1], cy), my1 = fmul(V.R[4], cy), my2 = fmul(V.R[7], cy);
-
-    int cls[VEC];
-    int pix_x[VEC], pix_y[VEC];
-    float dep[VEC], pcx[VEC], pcy[VEC], pcz[VEC];
-    int any = 0;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const float cx = fmul(fsub((float)(x0 + j), hx), s);
-        pcx[j] = fadd(V.t[0], ffma(V.R[2], cz, ffma(V.R[0], cx, my0)));
-        pcy[j] = fadd(V.t[1], ffma(V.R[5], cz, ffma(V.R[3], cx, my1)));
-        pcz[j] = fadd(V.t[2], ffma(V.R[8], cz, ffma(V.R[6], cx, my2)));
-        cls[j] = kCheckOnly;
-        dep[j] = 0.f; pix_x[j] = 0; pix_y[j] = 0;
-        if (pcz[j] > 0.0f) {
-            float qx, qy, qz;
+        // ---- conservative x-interval of voxels that can project into the image (plain float math;
+        //      the padding absorbs its rounding).  pc(x) = A + x * B.
+        int xa = 0, xb = rx - 1;
+        {
+            const float c0 = -hx * s;
+            const float ax = V.t[0] + (V.R[0] * c0 + my0 + V.R[2] * cz), bx = V.R[0] * s;
+            const float ay = V.t[1] + (V.R[3] * c0 + my1 + V.R[5] * cz), by = V.R[3] * s;
+            const float az = V.t[2] + (V.R[6] * c0 + my2 + V.R[8] * cz), bz = V.R[6] * s;
+            float qxa, qxb, qya, qyb, qza, qzb;
             if (PINHOLE) {
-                qx = ffma(P.K[2], pcz[j], fmul(P.K[0], pcx[j]));
-                qy = ffma(P.K[5], pcz[j], fmul(P.K[4], pcy[j]));
-                qz = pcz[j];
+                qxa = P.K[0] * ax + P.K[2] * az; qxb = P.K[0] * bx + P.K[2] * bz;
+                qya = P.K[4] * ay + P.K[5] * az; qyb = P.K[4] * by + P.K[5] * bz;
+                qza = az; qzb = bz;
             } else {
-                qx = dot_yxz(P.K[0], P.K[1], P.K[2], pcx[j], pcy[j], pcz[j]);
-                qy = dot_yxz(P.K[3], P.K[4], P.K[5], pcx[j], pcy[j], pcz[j]);
-                qz = dot_yxz(P.K[6], P.K[7], P.K[8], pcx[j], pcy[j], pcz[j]);
+                qxa = P.K[0] * ax + P.K[1] * ay + P.K[2] * az; qxb = P.K[0] * bx + P.K[1] * by + P.K[2] * bz;
+                qya = P.K[3] * ax + P.K[4] * ay + P.K[5] * az; qyb = P.K[3] * bx + P.K[4] * by + P.K[5] * bz;
+                qza = P.K[6] * ax + P.K[7] * ay + P.K[8] * az; qzb = P.K[6] * bx + P.K[7] * by + P.K[8] * bz;
             }
-            const int px = __float2int_rn(fdiv(qx, qz));
-            const int py = __float2int_rn(fdiv(qy, qz));
-            if (px < 0 || px >= P.w || py < 0 || py >= P.h) {
-                cls[j] = kSkip;
-            } else {
-                pix_x[j] = px; pix_y[j] = py;
-                const float d = __ldg((const float*)((const char*)P.depth + (size_t)py * P.depth_pitch) + px);
-                dep[j] = d;
-                if (d > 0.0f) cls[j] = kValid;
-            }
-        }
-        any |= cls[j];
-    }
-    if (!any) return;
-
-    float* wp = V.weights + i0;
-    float* tp = V.tsdf + i0;
-    float w[VEC], tv[VEC];
-    if (VEC == 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wp);
-        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
-    } else {
+            const float xe = (float)(rx - 1);
+            const float zmin = fminf(fminf(az, az + bz * xe), fminf(qza, qza + qzb * xe));
+            if (zmin > kMinDepthCull) {   // whole row safely in front of the camera: cull by the four image edges
+                float lo = 0.0f, hi = xe;
+                const float m0 = 0.5f + kMarginPx, mw = (float)P.w - 0.5f + kMarginPx, mh = (float)P.h - 0.5f + kMarginPx;
+                // alpha + beta * x >= 0 for: left, right, top, bottom
+                const float al[4] = {qxa + m0 * qza, mw * qza - qxa, qya + m0 * qza, mh * qza - qya};
+                const float be[4] = {qxb + m0 * qzb, mw * qzb - qxb, qyb + m0 * qzb, mh * qzb - qyb};
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) w[j] = wp[j];
-    }
-
-    float sdf[VEC];
-    int need_t = 0;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        sdf[j] = 0.f;
-        if (cls[j] == kValid) {
-            const float lx = fdiv(fsub((float)pix_x[j], P.K[2]), P.K[0]);
-            const float ly = fdiv(fsub((float)pix_y[j], P.K[5]), P.K[4]);
-            const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
-            const float inv_lambda = frcp(lambda);
-            const float nrm = norm3(pcx[j], pcy[j], pcz[j]);
-            sdf[j] = ffma(-nrm, inv_lambda, dep[j]);   // depth - (1/lambda)*|pc| as one FFMA (reference SASS)
-            if (sdf[j] >= -V.trunc) need_t |= 1 << j;
-        }
-    }
-    bool have_t = false;
-    if (need_t) {
-        have_t = true;
-        if (VEC == 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(tp);
-            tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) tv[j] = tp[j];
-        }
-    }
-
-    int wrote_t = 0, wrote_w = 0;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        if (cls[j] == kCheckOnly) {
-            // behind the camera or no depth: un-mark never-seen voxels (TSDF.cu:349-353, 369-374)
-            if (w[j] == 0.0f) { tv[j] = 0.0f; wrote_t |= 1 << j; }
-        } else if (cls[j] == kValid) {
-            if (need_t & (1 << j)) {
-                const float q = fdiv(sdf[j], V.trunc);
-                const float val = copysignf(fminf(1.0f, fabsf(q)), sdf[j]);
-                float a = 1.0f;
-                if (sdf[j] < V.trunc)
-                    a = __ldg((const float*)((const char*)V.assoc + (size_t)pix_y[j] * V.assoc_pitch) + pix_x[j]);
-                const float ws = fadd(w[j], a);
-                if (ws > 0.0f) {
-                    tv[j] = fdiv(ffma(w[j], tv[j], fmul(val, a)), ws);
-                    w[j] = fminf(ws, P.max_weight);
-                    wrote_t |= 1 << j; wrote_w |= 1 << j;
+                for (int k = 0; k < 4; ++k) {
+                    if (be[k] > 0.0f) lo = fmaxf(lo, -al[k] / be[k]);
+                    else if (be[k] < 0.0f) hi = fminf(hi, -al[k] / be[k]);
+                    else if (al[k] < 0.0f) hi = -1.0f;
                 }
-            } else if (w[j] == 0.0f) {
-                tv[j] = -1.0f; wrote_t |= 1 << j;   // occluded and never seen
+                if (!(lo <= hi)) continue;
+                xa = max(0, (int)floorf(lo) - 1);
+                xb = min(rx - 1, (int)ceilf(hi) + 1);
+                if (xa > xb) continue;
+            }
+        }
+        xa &= ~127;                     // whole 128-voxel chunks: one bitmap word per warp iteration
+        const int64_t row_off = (int64_t)row * rx;
+        const float* drow0 = P.depth;
+
+        for (int xbase = xa; xbase <= xb; xbase += 128) {   // warp-uniform trip count (shuffles below)
+            const int x0 = xbase + 4 * lane;
+            const bool active = x0 <= xb && x0 < rx;
+            int cls_skip = 0, cls_check = 0, cls_free = 0, cls_occ = 0, cls_exact = 0;   // bit j = voxel j
+            int pix_x[4], pix_y[4];
+            float dep[4], pcx[4], pcy[4], pcz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dep[j] = 0.f; pix_x[j] = 0; pix_y[j] = 0; pcx[j] = pcy[j] = pcz[j] = 0.f;
+                if (!active) continue;
+                const float cx = fmul(fsub((float)(x0 + j), hx), s);
+                pcx[j] = fadd(V.t[0], ffma(V.R[2], cz, ffma(V.R[0], cx, my0)));
+                pcy[j] = fadd(V.t[1], ffma(V.R[5], cz, ffma(V.R[3], cx, my1)));
+                pcz[j] = fadd(V.t[2], ffma(V.R[8], cz, ffma(V.R[6], cx, my2)));
+                if (!(pcz[j] > 0.0f)) { cls_check |= 1 << j; continue; }
+                float qx, qy, qz;
+                if (PINHOLE) {
+                    qx = ffma(P.K[2], pcz[j], fmul(P.K[0], pcx[j]));
+                    qy = ffma(P.K[5], pcz[j], fmul(P.K[4], pcy[j]));
+                    qz = pcz[j];
+                } else {
+                    qx = dot_yxz(P.K[0], P.K[1], P.K[2], pcx[j], pcy[j], pcz[j]);
+                    qy = dot_yxz(P.K[3], P.K[4], P.K[5], pcx[j], pcy[j], pcz[j]);
+                    qz = dot_yxz(P.K[6], P.K[7], P.K[8], pcx[j], pcy[j], pcz[j]);
+                }
+                const float rz = rcp_approx(qz);
+                const int px = round_quotient(qx, qz, rz);
+                const int py = round_quotient(qy, qz, rz);
+                if (px < 0 || px >= P.w || py < 0 || py >= P.h) { cls_skip |= 1 << j; continue; }
+                pix_x[j] = px; pix_y[j] = py;
+                const float d = __ldg((const float*)((const char*)drow0 + (size_t)py * P.depth_pitch) + px);
+                dep[j] = d;
+                if (!(d > 0.0f)) { cls_check |= 1 << j; continue; }
+                // approximate signed distance: decides free space / occluded when safely outside the band
+                float lx, ly;
+                if (TABLE) { lx = s_tab[px]; ly = s_tab[P.w + py]; }
+                else { lx = fdiv(fsub((float)px, P.K[2]), P.K[0]); ly = fdiv(fsub((float)py, P.K[5]), P.K[4]); }
+                const float l2 = fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f);
+                const float n2 = ffma(pcz[j], pcz[j], ffma(pcx[j], pcx[j], fmul(pcy[j], pcy[j])));
+                const float proj = n2 * rsqrt_approx(n2) * rsqrt_approx(l2);   // |pc| / lambda, ~2^-21 relative
+                const float sdf_a = d - proj;
+                const float eps = (fabsf(d) + proj) * 2.44140625e-4f;          // 2^-12 relative guard
+                if (sdf_a > V.trunc + eps) cls_free |= 1 << j;
+                else if (sdf_a < -V.trunc - eps) cls_occ |= 1 << j;
+                else cls_exact |= 1 << j;
+            }
+            const int touched = cls_check | cls_free | cls_occ | cls_exact;
+            int known = 0;                 // voxels whose final tsdf value this thread knows
+            float tv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (touched) {
+                float* wp = V.weights + row_off + x0;
+                float* tp = V.tsdf + row_off + x0;
+                float w[4];
+                {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wp);
+                    w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+                }
+                // exact signed distance where the band test needs it (canonical sequence)
+                float sdf[4];
+                int in_band = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sdf[j] = 0.f;
+                    if (cls_exact & (1 << j)) {
+                        const float lx = fdiv(fsub((float)pix_x[j], P.K[2]), P.K[0]);
+                        const float ly = fdiv(fsub((float)pix_y[j], P.K[5]), P.K[4]);
+                        const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
+                        const float inv_lambda = frcp(lambda);
+                        const float nrm = norm3(pcx[j], pcy[j], pcz[j]);
+                        sdf[j] = ffma(-nrm, inv_lambda, dep[j]);   // depth - (1/lambda)*|pc| as one FFMA (reference SASS)
+                        if (sdf[j] >= -V.trunc) in_band |= 1 << j;
+                    }
+                }
+                const int need_t = in_band | cls_free;
+                if (need_t) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(tp);
+                    tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+                    known = 0xF;
+                }
+                int wrote_t = 0, wrote_w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int bit = 1 << j;
+                    if (cls_check & bit) {
+                        // behind the camera or no depth: un-mark never-seen voxels (TSDF.cu:349-353, 369-374)
+                        if (w[j] == 0.0f) { tv[j] = 0.0f; wrote_t |= bit; known |= bit; }
+                        if (STATS) ++st[3];
+                    } else if (cls_free & bit) {
+                        // sdf >= trunc: value +1 with weight 1 (free space is never association-weighted)
+                        const float ws = fadd(w[j], 1.0f);
+                        if (ws > 0.0f) {
+                            const float num = ffma(w[j], tv[j], 1.0f);
+                            tv[j] = (num == ws && ws <= 3.0e38f) ? 1.0f : fdiv(num, ws);
+                            w[j] = fminf(ws, P.max_weight);
+                            wrote_t |= bit; wrote_w |= bit;
+                            if (STATS) ++st[0];
+                        }
+                    } else if (in_band & bit) {
+                        const float q = fdiv(sdf[j], V.trunc);
+                        const float val = copysignf(fminf(1.0f, fabsf(q)), sdf[j]);
+                        float a = 1.0f;
+                        if (sdf[j] < V.trunc)
+                            a = __ldg((const float*)((const char*)V.assoc + (size_t)pix_y[j] * V.assoc_pitch) + pix_x[j]);
+                        const float ws = fadd(w[j], a);
+                        if (ws > 0.0f) {
+                            tv[j] = fdiv(ffma(w[j], tv[j], fmul(val, a)), ws);
+                            w[j] = fminf(ws, P.max_weight);
+                            wrote_t |= bit; wrote_w |= bit;
+                            if (STATS) ++st[0];
+                        }
+                    } else if ((cls_occ | cls_exact) & bit) {
+                        // far behind the surface
+                        if (w[j] == 0.0f) { tv[j] = -1.0f; wrote_t |= bit; known |= bit; if (STATS) ++st[1]; }
+                        else if (STATS) ++st[2];
+                    }
+                }
+                if (wrote_w) *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
+                if (wrote_t) {
+                    if (known == 0xF) {
+                        *reinterpret_cast<float4*>(tp) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (wrote_t & (1 << j)) tp[j] = tv[j];
+                    }
+                }
+            }
+            if (STATS) st[4] += __popc(cls_skip);
+            // ---- constant-segment bitmaps: one bit per 4-voxel segment (this lane) in each of three maps
+            //      (all +1 / all 0 / all -1).  A word covers this warp's 128-voxel chunk, so it has one owner.
+            if (V.const_bits && __any_sync(0xffffffffu, known != 0)) {
+                int code = -1;    // common code of the values this lane knows; kMixed if they differ or are not constants
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (known & (1 << j)) {
+                        const int c = value_code(tv[j]);
+                        code = (code == -1 || code == c) ? c : kMixed;
+                    }
+                const bool full = (known == 0xF);
+                const size_t word = (size_t)row * V.wpr + (xbase >> 7);
+#pragma unroll
+                for (int m = 1; m <= 3; ++m) {
+                    const uint32_t set = __ballot_sync(0xffffffffu, full && code == m);
+                    // a partially known segment keeps its old bit only if what was seen agrees with it
+                    const uint32_t keep = __ballot_sync(0xffffffffu, !full && (code == -1 || code == m));
+                    if (lane == m - 1) {
+                        uint32_t* wp32 = V.const_bits + (size_t)(m - 1) * V.map_words + word;
+                        *wp32 = keep ? (set | (*wp32 & keep)) : set;
+                    }
+                }
             }
         }
     }
-
-    if (wrote_w) {
-        if (VEC == 4) *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
-        else {
+    if (STATS && P.stats) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) if (wrote_w & (1 << j)) wp[j] = w[j];
-        }
-    }
-    if (wrote_t) {
-        if (VEC == 4 && (have_t || wrote_t == 0xF)) {
-            *reinterpret_cast<float4*>(tp) = make_float4(tv[0], tv[1], tv[2], tv[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) if (wrote_t & (1 << j)) tp[j] = tv[j];
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long v = st[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicAdd(P.stats + k, v);
         }
     }
 }
 
-static int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float* K,
-                            const emf_image* depth, const emf_image* assoc, float max_weight,
-                            cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------
+// any resolution / alignment: one thread per voxel, straight canonical arithmetic
+// ---------------------------------------------------------------------------------------------
+template <bool PINHOLE>
+__global__ void __launch_bounds__(kSimpleThreads) k_integrate_simple(const __grid_constant__ IntParams P) {
+    int lo = 0, hi = P.n_vol - 1;
+    const int b = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.v[mid].first_item <= b) lo = mid; else hi = mid - 1;
+    }
+    const IntVol& V = P.v[lo];
+    if (V.gate >= 0 && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh)) return;
+    const int rx = V.rx, ry = V.ry;
+    const int64_t n_vox = (int64_t)rx * ry * V.rz;
+    const int64_t i = (int64_t)(b - V.first_item) * kSimpleThreads + threadIdx.x;
+    if (i >= n_vox) return;
+    const int64_t row = i / rx;
+    const int x = (int)(i - row * rx);
+    const int z = (int)(row / ry);
+    const int y = (int)(row - (int64_t)z * ry);
+    const float s = V.voxel;
+    const float cx = fmul(fsub((float)x, fmul((float)(rx - 1), 0.5f)), s);
+    const float cy = fmul(fsub((float)y, fmul((float)(ry - 1), 0.5f)), s);
+    const float cz = fmul(fsub((float)z, fmul((float)(V.rz - 1), 0.5f)), s);
+    const float pcx = fadd(V.t[0], dot_yxz(V.R[0], V.R[1], V.R[2], cx, cy, cz));
+    const float pcy = fadd(V.t[1], dot_yxz(V.R[3], V.R[4], V.R[5], cx, cy, cz));
+    const float pcz = fadd(V.t[2], dot_yxz(V.R[6], V.R[7], V.R[8], cx, cy, cz));
+    float* wp = V.weights + i;
+    float* tp = V.tsdf + i;
+    if (!(pcz > 0.0f)) { if (*wp == 0.0f) *tp = 0.0f; return; }
+    float qx, qy, qz;
+    if (PINHOLE) {
+        qx = ffma(P.K[2], pcz, fmul(P.K[0], pcx)); qy = ffma(P.K[5], pcz, fmul(P.K[4], pcy)); qz = pcz;
+    } else {
+        qx = dot_yxz(P.K[0], P.K[1], P.K[2], pcx, pcy, pcz);
+        qy = dot_yxz(P.K[3], P.K[4], P.K[5], pcx, pcy, pcz);
+        qz = dot_yxz(P.K[6], P.K[7], P.K[8], pcx, pcy, pcz);
+    }
+    const int px = __float2int_rn(fdiv(qx, qz)), py = __float2int_rn(fdiv(qy, qz));
+    if (px < 0 || px >= P.w || py < 0 || py >= P.h) return;
+    const float d = __ldg((const float*)((const char*)P.depth + (size_t)py * P.depth_pitch) + px);
+    if (!(d > 0.0f)) { if (*wp == 0.0f) *tp = 0.0f; return; }
+    const float lx = fdiv(fsub((float)px, P.K[2]), P.K[0]);
+    const float ly = fdiv(fsub((float)py, P.K[5]), P.K[4]);
+    const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
+    const float sdf = ffma(-norm3(pcx, pcy, pcz), frcp(lambda), d);
+    const float w = *wp;
+    if (sdf >= -V.trunc) {
+        const float val = copysignf(fminf(1.0f, fabsf(fdiv(sdf, V.trunc))), sdf);
+        float a = 1.0f;
+        if (sdf < V.trunc) a = __ldg((const float*)((const char*)V.assoc + (size_t)py * V.assoc_pitch) + px);
+        const float ws = fadd(w, a);
+        if (ws > 0.0f) {
+            *tp = fdiv(ffma(w, *tp, fmul(val, a)), ws);
+            *wp = fminf(ws, P.max_weight);
+        }
+    } else if (w == 0.0f) {
+        *tp = -1.0f;
+    }
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        g_sm_count = n;
+    }
+    return g_sm_count;
+}
+
+int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float* K, const emf_image* depth,
+                     const emf_image* assoc, float max_weight, const int32_t* gate_counts, const int* gates,
+                     int gate_thresh, unsigned long long* stats, cudaStream_t stream) {
     if (n_vol <= 0 || !vols || !T_oc || !K || !assoc) return EMF_ERR_INVALID;
     if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
     if (!image_ok(depth, 4)) return EMF_ERR_INVALID;
-    IntParams P;  // ~10 KB descriptor table, passed by value as the kernel parameter
-    bool vec_ok = true;
-    int64_t blocks = 0;
+    IntParams P;  // ~11 KB descriptor table, passed by value as the kernel parameter
+    bool rows_ok = true;
     for (int i = 0; i < n_vol; ++i) {
         const emf_volume& v = vols[i];
         if (!v.tsdf || !v.weights || !res_ok(v.res) || !image_ok(&assoc[i], 4) || !same_size(&assoc[i], depth))
             return EMF_ERR_INVALID;
-        vec_ok = vec_ok && (v.res[0] % kVec == 0) && aligned16(v.tsdf) && aligned16(v.weights);
+        rows_ok = rows_ok && (v.res[0] % 4 == 0) && aligned16(v.tsdf) && aligned16(v.weights);
+        if (v.const_bits && (v.res[0] % 4 != 0 || !aligned16(v.tsdf) || !aligned16(v.weights))) return EMF_ERR_INVALID;
     }
-    const int vec = vec_ok ? kVec : 1;
+    int64_t items = 0;
     for (int i = 0; i < n_vol; ++i) {
         const emf_volume& v = vols[i];
         IntVol& d = P.v[i];
         d.tsdf = v.tsdf; d.weights = v.weights;
+        d.const_bits = rows_ok ? v.const_bits : nullptr;   // (the one-thread-per-voxel path keeps no maps: callers pass NULL)
+        d.wpr = emf_bitmap_words_per_row(v.res[0]);
+        d.map_words = (size_t)d.wpr * v.res[1] * v.res[2];
         d.assoc = (const float*)assoc[i].ptr; d.assoc_pitch = assoc[i].pitch;
         for (int k = 0; k < 9; ++k) d.R[k] = T_oc[i].R[k];
         for (int k = 0; k < 3; ++k) d.t[k] = T_oc[i].t[k];
         d.rx = v.res[0]; d.ry = v.res[1]; d.rz = v.res[2];
         d.voxel = v.voxel_size; d.trunc = v.truncdist;
-        d.first_block = (int)blocks;
+        d.first_item = (int)items;
+        d.gate = (gates && gate_counts) ? gates[i] : -1;
         const int64_t n_vox = (int64_t)v.res[0] * v.res[1] * v.res[2];
-        blocks += (n_vox + (int64_t)kIntThreads * vec - 1) / ((int64_t)kIntThreads * vec);
-        if (blocks > 0x7fffffff) return EMF_ERR_UNSUPPORTED;
+        items += rows_ok ? (int64_t)v.res[1] * v.res[2] : (n_vox + kSimpleThreads - 1) / kSimpleThreads;
+        if (items > 0x7fffffff) return EMF_ERR_UNSUPPORTED;
     }
-    P.n_vol = n_vol; P.total_blocks = (int)blocks;
+    P.n_vol = n_vol; P.total_items = (int)items;
     P.depth = (const float*)depth->ptr; P.depth_pitch = depth->pitch; P.w = depth->width; P.h = depth->height;
     for (int k = 0; k < 9; ++k) P.K[k] = K[k];
     P.max_weight = max_weight;
+    P.gate_counts = gate_counts; P.gate_thresh = gate_thresh;
+    P.stats = stats;
     const bool pin = is_pinhole(K);
-    const dim3 grid((unsigned)blocks), block(kIntThreads);
-    if (vec == 4) {
-        if (pin) k_integrate<true, 4><<<grid, block, 0, stream>>>(P);
-        else k_integrate<false, 4><<<grid, block, 0, stream>>>(P);
-    } else {
-        if (pin) k_integrate<true, 1><<<grid, block, 0, stream>>>(P);
-        else k_integrate<false, 1><<<grid, block, 0, stream>>>(P);
+    if (!rows_ok) {
+        if (pin) k_integrate_simple<true><<<(unsigned)items, kSimpleThreads, 0, stream>>>(P);
+        else k_integrate_simple<false><<<(unsigned)items, kSimpleThreads, 0, stream>>>(P);
+        return launch_status();
     }
+    const size_t tab_bytes = (size_t)(P.w + P.h) * sizeof(float);
+    const bool table = tab_bytes <= 40 * 1024;
+    const size_t smem = table ? tab_bytes : 0;
+    const dim3 block(kIntThreads);
+    // persistent grid: every SM filled to the kernel's occupancy, rows dealt round-robin to warps
+#define EMF_LAUNCH_ROWS(PIN, TAB)                                                                          \
+    do {                                                                                                   \
+        static int occ_s = 0, occ_n = 0;                                                                   \
+        int& occ = stats ? occ_s : occ_n;                                                                  \
+        if (occ == 0) {                                                                                    \
+            if (stats) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_rows<PIN, TAB, true>, kIntThreads, smem); \
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_rows<PIN, TAB, false>, kIntThreads, smem);     \
+            if (occ <= 0) occ = 2;                                                                         \
+        }                                                                                                  \
+        int64_t blocks = (int64_t)sm_count() * occ;                                                        \
+        const int64_t min_blocks = (items + kIntThreads / 32 - 1) / (kIntThreads / 32);                    \
+        if (blocks > min_blocks) blocks = min_blocks;                                                      \
+        const dim3 grid((unsigned)blocks);                                                                 \
+        if (stats) k_integrate_rows<PIN, TAB, true><<<grid, block, smem, stream>>>(P);                     \
+        else k_integrate_rows<PIN, TAB, false><<<grid, block, smem, stream>>>(P);                          \
+    } while (0)
+    if (pin) { if (table) EMF_LAUNCH_ROWS(true, true); else EMF_LAUNCH_ROWS(true, false); }
+    else { if (table) EMF_LAUNCH_ROWS(false, true); else EMF_LAUNCH_ROWS(false, false); }
+#undef EMF_LAUNCH_ROWS
     return launch_status();
 }
 
@@ -241,16 +464,26 @@ static int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T
 extern "C" EMF_API int emf_integrate_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
                                      const emf_image* depth, const emf_image* assoc, float max_weight,
                                      emf_stream_t stream) {
-    return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, (cudaStream_t)stream);
+    return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, nullptr, nullptr, 0, nullptr,
+                                  (cudaStream_t)stream);
+}
+
+extern "C" EMF_API int emf_integrate_volumes_gated(int n_vol, const emf_volume* vols, const emf_pose* T_oc,
+                                           const float K[9], const emf_image* depth, const emf_image* assoc,
+                                           float max_weight, const int32_t* gate_counts, const int* gates,
+                                           int gate_thresh, uint64_t* stats, emf_stream_t stream) {
+    return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, gate_counts, gates, gate_thresh,
+                                  (unsigned long long*)stats, (cudaStream_t)stream);
 }
 
 extern "C" EMF_API int emf_update_tsdf(const emf_image* depth, const emf_image* assoc_weights, float* tsdf, float* weights,
                                const emf_pose* T_oc, const float K[9], const int res[3], float voxel_size,
                                float truncdist, float max_weight, emf_stream_t stream) {
     if (!res || !assoc_weights || !T_oc) return EMF_ERR_INVALID;
-    emf_volume v;
-    v.tsdf = tsdf; v.weights = weights; v.grads = nullptr; v.fg_probs = nullptr;
+    emf_volume v = {};
+    v.tsdf = tsdf; v.weights = weights;
     v.res[0] = res[0]; v.res[1] = res[1]; v.res[2] = res[2];
     v.voxel_size = voxel_size; v.truncdist = truncdist; v.id = 0;
-    return emfb::launch_integrate(1, &v, T_oc, K, depth, assoc_weights, max_weight, (cudaStream_t)stream);
+    return emfb::launch_integrate(1, &v, T_oc, K, depth, assoc_weights, max_weight, nullptr, nullptr, 0, nullptr,
+                                  (cudaStream_t)stream);
 }

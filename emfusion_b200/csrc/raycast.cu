@@ -14,7 +14,13 @@
 //    weight gather instead of materialising raycastWeights per frame;
 //  * normals come from on-the-fly forward differences when no gradient volume
 //    is supplied (same single fp32 subtraction per component => same bits);
-//  * a volume is only traced inside the screen rectangle of its box.
+//  * a volume is only traced inside the screen rectangle of its box;
+//  * the three IEEE divisions by the voxel size per march sample reuse one refined reciprocal
+//    (ConstDiv, emf_math.cuh) -- the same instruction sequence the reference build executes;
+//  * with the "safe sample" bitmaps (emf_volume::safe_bits, safe.cu) a fine-stepping ray whose last
+//    sample was exactly +1, 0 or -1 "crawls": it advances its ray parameter by the same sequence of
+//    fp32 additions, but while the bitmap certifies that the next sample would return that same
+//    value again it does not take it -- such a sample changes nothing of the march state.
 #include "common.cuh"
 
 namespace emfb {
@@ -24,6 +30,9 @@ struct RayVol {
     const float* weights;
     const float* fg_probs;   // nullable
     const float* grads;      // nullable (float3 per voxel)
+    const uint32_t* safe;    // nullable: three "safe sample" bitmaps (safe.cu), one bit per 4-voxel x-segment
+    int wpr;                 // words per row of a bitmap
+    unsigned map_words;      // words per bitmap
     float* ray; size_t ray_pitch;
     float* vert; size_t vert_pitch;
     float* norm; size_t norm_pitch;
@@ -44,10 +53,28 @@ struct RayParams {
     float K[9];
     int32_t* hit_voxel;      // optional (single-volume API)
     int write_all;           // 1: batched semantics (ray/mask written for every pixel of the rect)
+    unsigned long long* stats;   // optional: [0] tsdf samples taken [1] samples skipped while crawling
+                                 //           [2] crawl attempts [3] weight samples
 };
 
 constexpr int kTileW = 16, kTileH = 8;   // CTA tile; warp = 8 x 4 pixels
 constexpr int kRayThreads = kTileW * kTileH;
+
+// trilinear TSDF sample with 32-bit element offsets (volumes are < 2^31 voxels: res_ok)
+__device__ __forceinline__ float trilinear32(const float* __restrict__ vol, int rx, int plane, int lx, int ly, int lz,
+                                             float vx, float vy, float vz) {
+    const float ax = fsub(vx, (float)lx), ay = fsub(vy, (float)ly), az = fsub(vz, (float)lz);
+    const float bx = fsub(1.0f, ax), by = fsub(1.0f, ay), bz = fsub(1.0f, az);
+    const float* r00 = vol + (uint32_t)(lz * plane + ly * rx + lx);
+    const float* r01 = r00 + rx;
+    const float* r10 = r00 + plane;
+    const float* r11 = r10 + rx;
+    const float c00 = lerp1(bx, __ldg(r00), ax, __ldg(r00 + 1));
+    const float c01 = lerp1(bx, __ldg(r01), ax, __ldg(r01 + 1));
+    const float c10 = lerp1(bx, __ldg(r10), ax, __ldg(r10 + 1));
+    const float c11 = lerp1(bx, __ldg(r11), ax, __ldg(r11 + 1));
+    return lerp1(bz, lerp1(by, c00, ay, c01), az, lerp1(by, c10, ay, c11));
+}
 
 __device__ __forceinline__ float weight_at(const RayVol& V, int64_t idx) {
     float w = __ldg(V.weights + idx);
@@ -89,7 +116,9 @@ __device__ __forceinline__ void trilinear_grad(const RayVol& V, float vx, float 
         out[k] = s.combine(g[0][k], g[1][k], g[2][k], g[3][k], g[4][k], g[5][k], g[6][k], g[7][k]);
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__ RayParams P) {
+    unsigned long long st[4] = {0, 0, 0, 0};
     int lo = 0, hi = P.n_vol - 1;
     const int b = blockIdx.x;
     while (lo < hi) {
@@ -103,7 +132,7 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = V.x0 + tx * kTileW + (warp & 1) * 8 + (lane & 7);
     const int y = V.y0 + ty * kTileH + (warp >> 1) * 4 + (lane >> 3);
-    if (x >= V.x1 || y >= V.y1) return;
+    if (x >= V.x1 || y >= V.y1) return;   // (STATS: no warp-collective below)
 
     float* ray_px = (float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x;
     uint8_t* mask_px = V.mask + (size_t)y * V.mask_pitch + x;
@@ -139,12 +168,16 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
         const float hxh = fmul((float)(V.rx - 1), 0.5f), hyh = fmul((float)(V.ry - 1), 0.5f),
                     hzh = fmul((float)(V.rz - 1), 0.5f);
         const float half_s = fmul(s, 0.5f);
+        const ConstDiv div_s(s);
+        const int rx = V.rx, plane = V.rx * V.ry;
+        const uint32_t* __restrict__ safe = V.safe;
+        const int wpr = V.wpr, ry_ = V.ry, rz_ = V.rz;
         float step = V.trunc;
         float vx, vy, vz;
         for (;;) {   // coarse skip (TSDF.cu:509-515)
-            vx = fadd(hxh, fdiv(ffma(dx, tcur, ox), s));
-            vy = fadd(hyh, fdiv(ffma(dy, tcur, oy), s));
-            vz = fadd(hzh, fdiv(ffma(dz, tcur, oz), s));
+            vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
+            vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
+            vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
             if (out_of(vx, vy, vz, 1.0f, frx, fry, frz) && tcur < tmax) tcur = fadd(step, tcur);
             else break;
         }
@@ -153,34 +186,102 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
             float f = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
             if (fabsf(f) < 1.0f) step = s;
             if (fabsf(f) < 0.8f) step = half_s;
+            // One loop, two kinds of iteration per lane (no nested per-lane loop: the lanes of a warp advance
+            // together).  CRAWL: up to four march steps whose samples are certified to return f again, looked up
+            // speculatively (four independent bitmap loads) and accepted as the longest certified prefix.
+            // SAMPLE: one march step of the reference algorithm.
+            int backoff = 0, wait = 0;   // crawl attempts that certify nothing are retried less often
+            bool crawling = false;
+            const uint32_t* __restrict__ map = safe;
+            float px = 0.f, py = 0.f, pz = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            int since_sync = 0;
             for (;;) {
-                tcur = fadd(tcur, step);
-                if (!(tcur <= tmax)) break;
-                vx = fadd(hxh, fdiv(ffma(dx, tcur, ox), s));
-                vy = fadd(hyh, fdiv(ffma(dy, tcur, oy), s));
-                vz = fadd(hzh, fdiv(ffma(dz, tcur, oz), s));
-                if (out_of(vx, vy, vz, 2.0f, frx, fry, frz)) continue;
-                const float fn = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
-                // back face (TSDF.cu:532): the weight sample is only needed for this test
-                if (f < 0.0f && fn > 0.0f) {
-                    if (trilinear_weight(V, vx, vy, vz) > 0.0f) break;
-                }
-                if (fabsf(fn) < 1.0f) step = s;
-                if (fabsf(fn) < 0.8f) step = half_s;
-                if (f > 0.0f && fn < 0.0f) {   // front face (TSDF.cu:540)
-                    const float ts = fsub(tcur, fdiv(fmul(f, step), fsub(fn, f)));
-                    const float mx = fmul(dx, ts), my = fmul(dy, ts), mz = fmul(dz, ts);
-                    const float sx = fadd(hxh, fdiv(fadd(ox, mx), s));
-                    const float sy = fadd(hyh, fdiv(fadd(oy, my), s));
-                    const float sz = fadd(hzh, fdiv(fadd(oz, mz), s));
-                    if (out_of(sx, sy, sz, 2.0f, frx, fry, frz)) continue;   // f keeps its old value
-                    if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
-                        hit = true; out_t = ts;
-                        hvx = sx; hvy = sy; hvz = sz; hmx = mx; hmy = my; hmz = mz;
-                        break;
+                if (!crawling && safe && step <= s && (f == 1.0f || f == 0.0f || f == -1.0f)) {
+                    if (wait > 0) {
+                        --wait;
+                    } else {
+                        // (vx, vy, vz) is the exact sample position of tcur here
+                        crawling = true;
+                        map = safe + (f == 1.0f ? 0u : (f == 0.0f ? V.map_words : 2u * V.map_words));
+                        const float sc = (step == s) ? 1.0f : 0.5f;      // voxels per step along the ray
+                        ddx = dx * sc; ddy = dy * sc; ddz = dz * sc;
+                        px = vx; py = vy; pz = vz;
+                        since_sync = 0;
+                        if (STATS) ++st[2];
                     }
                 }
-                f = fn;
+                bool sample = true;
+                if (crawling) {
+                    float tn[4];
+                    uint32_t ok = 0;
+                    tn[0] = fadd(tcur, step); tn[1] = fadd(tn[0], step); tn[2] = fadd(tn[1], step); tn[3] = fadd(tn[2], step);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float qx = px + ddx * (float)(k + 1), qy = py + ddy * (float)(k + 1), qz = pz + ddz * (float)(k + 1);
+                        const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
+                        const bool in = tn[k] <= tmax && qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && ix < rx && iy < ry_ && iz < rz_;
+                        uint32_t wd = 0;
+                        if (in) wd = __ldg(map + (unsigned)((iz * ry_ + iy) * wpr + (ix >> 7)));
+                        ok |= ((wd >> ((ix >> 2) & 31)) & 1u) << k;
+                    }
+                    const int n = __ffs(~ok) - 1;          // certified prefix, 0..4
+                    if (n > 0) {
+                        tcur = n == 1 ? tn[0] : (n == 2 ? tn[1] : (n == 3 ? tn[2] : tn[3]));
+                        px += ddx * (float)n; py += ddy * (float)n; pz += ddz * (float)n;
+                        if (STATS) st[1] += n;
+                        since_sync += n;
+                        if (since_sync >= 64) {              // keep the running position within 1e-2 voxels
+                            px = fadd(hxh, div_s(ffma(dx, tcur, ox)));
+                            py = fadd(hyh, div_s(ffma(dy, tcur, oy)));
+                            pz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
+                            since_sync = 0;
+                        }
+                        backoff = 0;
+                    }
+                    if (n == 4) {
+                        sample = false;                      // keep crawling
+                    } else {
+                        crawling = false;                    // the next step is not certified (or ends the ray): sample it
+                        if (n == 0) { backoff = min(2 * backoff + 1, 15); wait = backoff; }
+                    }
+                }
+                // (structured control flow from here on -- flags instead of `continue` -- so that the lanes leaving
+                //  the crawl and the lanes that were sampling anyway execute the sample together)
+                if (sample) {
+                    tcur = fadd(tcur, step);
+                    if (!(tcur <= tmax)) break;
+                    vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
+                    vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
+                    vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
+                    if (!out_of(vx, vy, vz, 2.0f, frx, fry, frz)) {
+                        const int lx = __float2int_rz(vx), ly = __float2int_rz(vy), lz = __float2int_rz(vz);
+                        const float fn = trilinear32(V.tsdf, rx, plane, lx, ly, lz, vx, vy, vz);
+                        if (STATS) ++st[0];
+                        // back face (TSDF.cu:532): the weight sample is only needed for this test
+                        if (f < 0.0f && fn > 0.0f) {
+                            if (STATS) ++st[3];
+                            if (trilinear_weight(V, vx, vy, vz) > 0.0f) break;
+                        }
+                        if (fabsf(fn) < 1.0f) step = s;
+                        if (fabsf(fn) < 0.8f) step = half_s;
+                        bool keep_f = false;
+                        if (f > 0.0f && fn < 0.0f) {   // front face (TSDF.cu:540)
+                            const float ts = fsub(tcur, fdiv(fmul(f, step), fsub(fn, f)));
+                            const float mx = fmul(dx, ts), my = fmul(dy, ts), mz = fmul(dz, ts);
+                            const float sx = fadd(hxh, div_s(fadd(ox, mx)));
+                            const float sy = fadd(hyh, div_s(fadd(oy, my)));
+                            const float sz = fadd(hzh, div_s(fadd(oz, mz)));
+                            if (out_of(sx, sy, sz, 2.0f, frx, fry, frz)) {
+                                keep_f = true;             // reference `continue`: f keeps its old value
+                            } else if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
+                                hit = true; out_t = ts;
+                                hvx = sx; hvy = sy; hvz = sz; hmx = mx; hmy = my; hmz = mz;
+                                break;
+                            }
+                        }
+                        if (!keep_f) f = fn;
+                    }
+                }
             }
         }
     }
@@ -209,6 +310,10 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
         *ray_px = 0.0f;
         *mask_px = 0;
     }
+    if (STATS && P.stats) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (st[k]) atomicAdd(P.stats + k, st[k]);
+    }
 }
 
 static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const emf_image* ray,
@@ -219,6 +324,9 @@ static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const
     if (ray->width != w || ray->height != h || !same_size(ray, vert) || !same_size(ray, norm) || !same_size(ray, mask))
         return EMF_ERR_INVALID;
     d.tsdf = v.tsdf; d.weights = v.weights; d.fg_probs = v.fg_probs; d.grads = v.grads;
+    d.safe = (v.safe_bits && v.res[0] % 4 == 0) ? v.safe_bits : nullptr;
+    d.wpr = emf_bitmap_words_per_row(v.res[0]);
+    d.map_words = (unsigned)((size_t)d.wpr * v.res[1] * v.res[2]);
     d.ray = (float*)ray->ptr; d.ray_pitch = ray->pitch;
     d.vert = (float*)vert->ptr; d.vert_pitch = vert->pitch;
     d.norm = (float*)norm->ptr; d.norm_pitch = norm->pitch;
@@ -346,7 +454,7 @@ extern "C" EMF_API int emf_raycast_tsdf(const float* tsdf, const float* grads, c
                                 const emf_image* mask, const emf_pose* T_co, const float K[9], const int res[3],
                                 float voxel_size, float truncdist, int32_t* hit_voxel, emf_stream_t stream) {
     if (!T_co || !K || !res || !raylengths) return EMF_ERR_INVALID;
-    emf_volume v;
+    emf_volume v = {};
     v.tsdf = (float*)tsdf; v.weights = (float*)weights; v.grads = grads; v.fg_probs = fg_probs;
     v.res[0] = res[0]; v.res[1] = res[1]; v.res[2] = res[2];
     v.voxel_size = voxel_size; v.truncdist = truncdist; v.id = 0;
@@ -357,15 +465,16 @@ extern "C" EMF_API int emf_raycast_tsdf(const float* tsdf, const float* grads, c
     P.v[0].first_block = 0;
     P.n_vol = 1; P.w = w; P.h = h;
     for (int k = 0; k < 9; ++k) P.K[k] = K[k];
-    P.hit_voxel = hit_voxel; P.write_all = 0;
+    P.hit_voxel = hit_voxel; P.write_all = 0; P.stats = nullptr;
     const int blocks = P.v[0].tiles_x * ((h + kTileH - 1) / kTileH);
-    k_raycast<<<blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    k_raycast<false><<<blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
 }
 
 extern "C" EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
                                    const int* rects, const emf_image* ray_out, const emf_image* vert_out,
-                                   const emf_image* norm_out, const emf_image* mask_out, emf_stream_t stream) {
+                                   const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
+                                   emf_stream_t stream) {
     if (n_vol <= 0 || !vols || !T_co || !K || !ray_out || !vert_out || !norm_out || !mask_out) return EMF_ERR_INVALID;
     if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
     RayParams P;
@@ -381,8 +490,9 @@ extern "C" EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, co
     if (blocks == 0) return EMF_OK;
     P.n_vol = n_vol; P.w = w; P.h = h;
     for (int k = 0; k < 9; ++k) P.K[k] = K[k];
-    P.hit_voxel = nullptr; P.write_all = 1;
-    k_raycast<<<(unsigned)blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    P.hit_voxel = nullptr; P.write_all = 1; P.stats = (unsigned long long*)stats;
+    if (stats) k_raycast<true><<<(unsigned)blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    else k_raycast<false><<<(unsigned)blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
 }
 

@@ -22,8 +22,9 @@ from .volume import ObjTSDF, Params, TSDF
 
 class EMFusionEngine:
     def __init__(self, params: Params, device="cuda", rank: int = 0, world_size: int = 1, group=None,
-                 materialize_grads: bool = False):
+                 materialize_grads: bool = False, accelerate: bool = False):
         self.params = params
+        self.accelerate = accelerate
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
         self.group = group
@@ -40,7 +41,7 @@ class EMFusionEngine:
             self.background = TSDF(params.globalVolumeDims, params.globalVoxelSize,
                                    float(np.float32(params.globalRelTruncDist) * np.float32(params.globalVoxelSize)),
                                    params.volumePose,
-                                   params.tsdfParams, params.frameSize, dev, materialize_grads)
+                                   params.tsdfParams, params.frameSize, dev, materialize_grads, accelerate)
         self.objects: List[ObjTSDF] = []          # local shard, list order
         self.all_ids: List[int] = []              # global list order (ids), identical on every rank
         self.depth = torch.zeros((h, w), dtype=f32, device=dev)
@@ -79,7 +80,7 @@ class EMFusionEngine:
             return None
         obj = ObjTSDF(res, voxelSize, float(np.float32(self.params.objRelTruncDist) * np.float32(voxelSize)), obj_pose,
                       self.params.tsdfParams,
-                      self.params.frameSize, self.device, self.materialize_grads)
+                      self.params.frameSize, self.device, self.materialize_grads, self.accelerate)
         assert obj.id == new_id
         self.objects.append(obj)
         h, w, dev = self.h, self.w, self.device
@@ -252,9 +253,11 @@ class EMFusionEngine:
         vols = [v for v in self.local_volumes() if v.id == 0 or not only_visible or v.id in self.vis_objs]
         if not vols:
             return
-        ops.integrateVolumes([v.c_volume() for v in vols], [rel_pose_OC(self.pose, v.pose) for v in vols],
+        cv = [v.c_volume() for v in vols]
+        ops.integrateVolumes(cv, [rel_pose_OC(self.pose, v.pose) for v in vols],
                              self.params.intr, self.depth, self._assoc_images(vols),
                              self.params.tsdfParams.maxTSDFWeight)
+        ops.updateSafeBits(cv)
         for v in vols:
             v._grads_dirty = True
             v.updateGradients()

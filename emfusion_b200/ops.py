@@ -21,7 +21,8 @@ from .poses import Affine
 LAUNCHES = {}
 _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1, "raycastTSDF": 1, "getVolumeVals": 1,
                      "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
-                     "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1}
+                     "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
+                     "updateSafeBits": 1}
 
 
 def _count(name: str) -> None:
@@ -92,12 +93,15 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
-def volume(tsdf, weights, res, voxel_size, truncdist, grads=None, fg_probs=None, vid=0) -> Volume:
+def volume(tsdf, weights, res, voxel_size, truncdist, grads=None, fg_probs=None, vid=0, const_bits=None,
+           safe_bits=None) -> Volume:
     v = Volume()
     v.tsdf = _ptr(tsdf)
     v.weights = _ptr(weights)
     v.grads = _ptr(grads)
     v.fg_probs = _ptr(fg_probs)
+    v.const_bits = _ptr(const_bits)
+    v.safe_bits = _ptr(safe_bits)
     v.res[:] = [int(r) for r in res]
     v.voxel_size = float(voxel_size)
     v.truncdist = float(truncdist)
@@ -195,11 +199,11 @@ def volumeScreenRect(volumeRes, voxelSize, rel_pose_CO: Affine, intr, width, hei
     return list(out)
 
 
-def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out, mask_out, stream=None):
+def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out, mask_out, stream=None, stats=None):
     flat = (C.c_int * (4 * len(vols)))(*[int(v) for r in rects for v in r]) if rects is not None else None
     check(_lib.lib().emf_raycast_volumes(len(vols), _vol_array(vols), poses(rel_poses_CO), _f9(intr), flat,
                                          images(ray_out), images(vert_out), images(norm_out), images(mask_out),
-                                         _stream(stream)), "raycastVolumes")
+                                         _ptr(stats), _stream(stream)), "raycastVolumes")
     _count("raycastVolumes")
 
 
@@ -217,7 +221,34 @@ def raycastComposite(ids, rects, obj_ray, obj_vert, obj_norm, obj_mask, bg_ray, 
     _count("raycastComposite")
 
 
-def integrateVolumes(vols, rel_poses_OC, intr, depth, assoc, maxWeight, stream=None):
-    check(_lib.lib().emf_integrate_volumes(len(vols), _vol_array(vols), poses(rel_poses_OC), _f9(intr), image(depth),
-                                           images(assoc), maxWeight, _stream(stream)), "integrateVolumes")
+def integrateVolumes(vols, rel_poses_OC, intr, depth, assoc, maxWeight, stream=None, gate_counts=None, gates=None,
+                     gate_thresh=0, stats=None):
+    """gate_counts (int32 CUDA tensor) + gates (per-volume index or -1): device-side visibility filter;
+    stats: optional uint64/int64 CUDA tensor of 5 counters (accumulated)."""
+    if gate_counts is None and stats is None:
+        check(_lib.lib().emf_integrate_volumes(len(vols), _vol_array(vols), poses(rel_poses_OC), _f9(intr),
+                                               image(depth), images(assoc), maxWeight, _stream(stream)),
+              "integrateVolumes")
+    else:
+        g = (C.c_int * len(vols))(*[int(x) for x in gates]) if gates is not None else None
+        check(_lib.lib().emf_integrate_volumes_gated(len(vols), _vol_array(vols), poses(rel_poses_OC), _f9(intr),
+                                                     image(depth), images(assoc), maxWeight, _ptr(gate_counts), g,
+                                                     int(gate_thresh), _ptr(stats), _stream(stream)),
+              "integrateVolumes")
     _count("integrateVolumes")
+
+
+def updateSafeBits(vols, stream=None):
+    """safe_bits <- erosion of const_bits for every volume that carries both (one launch)."""
+    check(_lib.lib().emf_update_safe_bits(len(vols), _vol_array(vols), _stream(stream)), "updateSafeBits")
+    if any(v.const_bits and v.safe_bits for v in vols):
+        _count("updateSafeBits")
+
+
+def resetBitmaps(vol: Volume, stream=None):
+    check(_lib.lib().emf_reset_bitmaps(C.byref(vol), _stream(stream)), "resetBitmaps")
+
+
+def bitmapWords(res) -> int:
+    """32-bit words of ONE segment bitmap of a volume (emf_bitmap_words_per_row(Rx) * Ry * Rz)."""
+    return ((int(res[0]) // 4 + 31) // 32) * int(res[1]) * int(res[2])

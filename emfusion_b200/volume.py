@@ -66,7 +66,7 @@ class Params:
 
 class TSDF:
     def __init__(self, volumeRes, voxelSize: float, truncdist: float, pose: Affine, params: TSDFParams,
-                 frameSize, device="cuda", materialize_grads: bool = False):
+                 frameSize, device="cuda", materialize_grads: bool = False, accelerate: bool = False):
         self.params = params
         self.volumeRes = tuple(int(r) for r in volumeRes)
         self.voxelSize = float(np.float32(voxelSize))
@@ -76,6 +76,13 @@ class TSDF:
         rx, ry, rz = self.volumeRes
         self.tsdfVol = torch.empty((ry * rz, rx), dtype=torch.float32, device=self.device)
         self.tsdfWeights = torch.empty((ry * rz, rx), dtype=torch.float32, device=self.device)
+        # acceleration state (no reference counterpart; results are unchanged): constant-segment bitmaps
+        # maintained by the integrate kernel and the "safe sample" bitmaps the raycast crawls through
+        self.constBits = self.safeBits = None
+        if accelerate and rx % 4 == 0:
+            words = ops.bitmapWords(self.volumeRes)
+            self.constBits = torch.empty((3 * words,), dtype=torch.int32, device=self.device)
+            self.safeBits = torch.empty((3 * words,), dtype=torch.int32, device=self.device)
         self.materialize_grads = materialize_grads
         self._grads: Optional[torch.Tensor] = None
         self._grads_dirty = True
@@ -86,6 +93,8 @@ class TSDF:
     def reset(self, pose: Affine):
         self.tsdfVol.zero_()
         self.tsdfWeights.zero_()
+        if self.constBits is not None:
+            ops.resetBitmaps(self.c_volume())   # every segment is "all 0"; nothing certified safe yet
         if self._grads is not None:
             self._grads.zero_()
         self._grads_dirty = False if self._grads is not None else True
@@ -115,8 +124,10 @@ class TSDF:
 
     # -- src/core/TSDF.cpp:108-118
     def integrate(self, depth, weights, cam_pose: Affine, intr, stream=None):
-        ops.updateTSDF(depth, weights, self.tsdfVol, self.tsdfWeights, rel_pose_OC(cam_pose, self.pose), intr,
-                       self.volumeRes, self.voxelSize, self.truncdist, self.params.maxTSDFWeight, stream)
+        v = [self.c_volume()]
+        ops.integrateVolumes(v, [rel_pose_OC(cam_pose, self.pose)], intr, depth, [weights],
+                             self.params.maxTSDFWeight, stream)
+        ops.updateSafeBits(v, stream)
         self._grads_dirty = True
 
     # -- src/core/TSDF.cpp:120-123
@@ -142,7 +153,8 @@ class TSDF:
 
     def c_volume(self, with_grads: bool = False):
         return ops.volume(self.tsdfVol, self.tsdfWeights, self.volumeRes, self.voxelSize, self.truncdist,
-                          grads=self._raycast_grads() if with_grads else None, fg_probs=self._fg(), vid=self.id)
+                          grads=self._raycast_grads() if with_grads else None, fg_probs=self._fg(), vid=self.id,
+                          const_bits=self.constBits, safe_bits=self.safeBits)
 
     def _fg(self):
         return None
@@ -170,7 +182,7 @@ class ObjTSDF(TSDF):
     nextID = 0   # static counter, incremented only by the constructor (src/core/ObjTSDF.cpp:28,34)
 
     def __init__(self, volumeRes, voxelSize, truncdist, pose, params, frameSize, device="cuda",
-                 materialize_grads: bool = False):
+                 materialize_grads: bool = False, accelerate: bool = False):
         rx, ry, rz = (int(r) for r in volumeRes)
         dev = torch.device(device)
         self.fgBgProbs = torch.empty((ry * rz, rx, 2), dtype=torch.float32, device=dev)
@@ -178,7 +190,8 @@ class ObjTSDF(TSDF):
         self.classProbs = []
         self.exCount = 1
         self.nonExCount = 0
-        super().__init__(volumeRes, voxelSize, truncdist, pose, params, frameSize, device, materialize_grads)
+        super().__init__(volumeRes, voxelSize, truncdist, pose, params, frameSize, device, materialize_grads,
+                         accelerate)
         ObjTSDF.nextID += 1
         self.id = ObjTSDF.nextID
 

@@ -73,6 +73,18 @@ typedef struct emf_volume {
     float* weights;        /* tsdfWeights  Rx*Ry*Rz floats */
     const float* grads;    /* tsdfGrads (float3 per voxel) or NULL: gradients are then taken on the fly */
     const float* fg_probs; /* fgProbs (objects) or NULL (background) */
+    /* Optional acceleration state (no reference counterpart; results are unchanged).  NULL = off.
+     * A "map" has one bit per 4-voxel x-segment, rows padded to whole 32-bit words:
+     *   words per map = emf_bitmap_words_per_row(Rx) * Ry * Rz.
+     * const_bits: three consecutive maps -- segment is all +1 / all 0 / all -1.  Maintained by
+     *   emf_integrate_volumes*; whoever zeroes the volume must set map 1 (all 0) to ones and the others to
+     *   zero (emf_reset_bitmaps); anyone else writing tsdf must clear all three.
+     * safe_bits: three consecutive maps derived by emf_update_safe_bits: bit set = every voxel within one
+     *   segment in x and [-1, +2] voxels in y and z of the segment holds that constant, i.e. any trilinear
+     *   sample whose base voxel is within one voxel of the segment returns exactly that constant.  The raycast
+     *   skips such samples (raycast.cu). */
+    uint32_t* const_bits;
+    uint32_t* safe_bits;
     int res[3];            /* volumeRes (x, y, z) */
     float voxel_size;
     float truncdist;
@@ -162,10 +174,13 @@ EMF_API int emf_assoc_normalise(int n_img, const emf_image* assoc_io, const emf_
  * batch in one launch.  Per volume i: ray_out[i] (f32, fully written inside rect, 0 = no hit),
  * mask_out[i] (u8), vert_out[i]/norm_out[i] (float3, hit pixels only).  rects (n_vol x 4 ints:
  * x0, y0, x1, y1, exclusive upper) bound the pixels each volume can cover; pixels outside a
- * volume's rect are not touched and must be treated as "no hit" by the consumer. */
+ * volume's rect are not touched and must be treated as "no hit" by the consumer.
+ * stats (optional, 4 x uint64 on the device, accumulated): TSDF samples taken, march samples skipped inside
+ * constant bricks, brick look-ups that skipped, weight samples -- the raycast's roofline numerator. */
 EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
                         const int* rects, const emf_image* ray_out, const emf_image* vert_out,
-                        const emf_image* norm_out, const emf_image* mask_out, emf_stream_t stream);
+                        const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
+                        emf_stream_t stream);
 
 /* Compositing of emf::EMFusion::raycast, src/core/EMFusion.cpp:760-794, in one launch.
  * Objects i = 0..n_obj-1 in list order with ids[i]; background images bg_*.
@@ -181,6 +196,29 @@ EMF_API int emf_raycast_composite(int n_obj, const int* ids, const int* rects, c
 EMF_API int emf_integrate_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
                           const emf_image* depth, const emf_image* assoc, float max_weight,
                           emf_stream_t stream);
+
+/* emf_integrate_volumes with device-side visibility gating and optional counters.
+ * gates[i] < 0: volume i is always integrated (background); otherwise it is integrated iff
+ * gate_counts[gates[i]] > gate_thresh, read ON THE DEVICE -- gate_counts is the vis_count array that
+ * emf_raycast_composite wrote earlier on the same stream, so the visibility filter of
+ * emf::EMFusion::integrateDepth (src/core/EMFusion.cpp:869-872) needs no device->host round trip.
+ * stats (optional, 5 x uint64 on the device, accumulated): voxels updated, marked occluded-unseen (-1),
+ * occluded but already seen, check-only (behind camera / invalid depth), projected outside the image inside
+ * the culling interval -- the exact-bytes roofline numerator. */
+EMF_API int emf_integrate_volumes_gated(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
+                                const emf_image* depth, const emf_image* assoc, float max_weight,
+                                const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,
+                                emf_stream_t stream);
+
+/* Derives safe_bits from const_bits for every volume that carries both (others are skipped).
+ * Call after integrating and before raycasting. */
+EMF_API int emf_update_safe_bits(int n_vol, const emf_volume* vols, emf_stream_t stream);
+
+/* Bitmap state of a freshly zeroed volume: const map "all 0" = ones, everything else = zero. */
+EMF_API int emf_reset_bitmaps(const emf_volume* vol, emf_stream_t stream);
+
+/* 32-bit words per volume row in a segment bitmap. */
+static inline int emf_bitmap_words_per_row(int rx) { return (rx / 4 + 31) / 32; }
 
 /* Screen-space rectangle (x0,y0,x1,y1) that bounds every pixel whose ray can enter the
  * volume's raycast box; full frame if a corner is behind the camera.  Host-side helper. */

@@ -76,7 +76,7 @@ def test_invalid_arguments_are_rejected_without_a_device(lib):
     assert lib.emf_compute_fg_probs(None, 10, None, None, None) == _lib.EMF_ERR_INVALID
     assert lib.emf_assoc_weights(0, None, None, img, None, None, 0, None, None) == _lib.EMF_ERR_INVALID
     assert lib.emf_integrate_volumes(0, None, None, K, img, None, 64.0, None) == _lib.EMF_ERR_INVALID
-    assert lib.emf_raycast_volumes(0, None, None, K, None, None, None, None, None, None) == _lib.EMF_ERR_INVALID
+    assert lib.emf_raycast_volumes(0, None, None, K, None, None, None, None, None, None, None) == _lib.EMF_ERR_INVALID
     vols = (_lib.Volume * 1)()
     poses = (_lib.Pose * 1)()
     imgs = (_lib.Image * 1)()
