@@ -38,7 +38,7 @@ class TsdfParams(C.Structure):
 
 class Volume(C.Structure):
     _fields_ = [("tsdf", C.c_void_p), ("weights", C.c_void_p), ("grads", C.c_void_p), ("fg_probs", C.c_void_p),
-                ("const_bits", C.c_void_p), ("safe_bits", C.c_void_p), ("res", C.c_int * 3), ("voxel_size", C.c_float), ("truncdist", C.c_float), ("id", C.c_int)]
+                ("const_bits", C.c_void_p), ("brick_map", C.c_void_p), ("res", C.c_int * 3), ("voxel_size", C.c_float), ("truncdist", C.c_float), ("id", C.c_int)]
 
 
 _P = C.POINTER
@@ -66,11 +66,11 @@ _SIGS = {
                               C.c_void_p],
     "emf_integrate_volumes_gated": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(Image), _P(Image), C.c_float,
                                     C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p],
-    "emf_update_safe_bits": [C.c_int, _P(Volume), C.c_void_p],
+    "emf_update_brick_maps": [C.c_int, _P(Volume), C.c_void_p],
     "emf_reset_bitmaps": [_P(Volume), C.c_void_p],
     "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],
 }
-EXPORTED = sorted(list(_SIGS) + ["emf_version"])
+EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes"])
 
 _lib = None
 
@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        L.emf_brick_map_bytes.argtypes = [_P(C.c_int)]
+        L.emf_brick_map_bytes.restype = C.c_size_t
         L.emf_version.restype = C.c_char_p
         L.emf_version.argtypes = []
         _lib = L

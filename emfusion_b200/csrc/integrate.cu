@@ -21,7 +21,7 @@
 //    an approximate signed distance places safely outside the truncation band take the free-space
 //    (value +1, weight +1) or occluded branch without the exact distance;
 //  * optionally maintains three bitmaps with one bit per 4-voxel x-segment (all +1 / all 0 /
-//    all -1), written with warp ballots, from which k_safe_bits (safe.cu) derives the maps the
+//    all -1), written with warp ballots, from which bricks.cu derives the brick map the
 //    raycast uses to skip march samples whose outcome is known (raycast.cu).
 //
 // k_integrate_simple: one thread per voxel, any resolution/alignment (ragged volumes).
@@ -57,6 +57,7 @@ struct IntParams {
     const int32_t* gate_counts;   // nullable: device-side visibility counters (raycast composite)
     int gate_thresh;              // a gated volume is integrated iff gate_counts[gate] > gate_thresh
     unsigned long long* stats;    // nullable: [0] updated [1] marked -1 [2] occluded-seen [3] check-only [4] skipped-in-interval
+    float g_rel, g_abs;           // |(|pc| / lambda(pixel)) - pc.z| <= g_rel * pc.z + g_abs (classification guard)
 };
 
 constexpr int kIntThreads = 256;
@@ -74,14 +75,17 @@ __device__ __forceinline__ int value_code(float v) {
 __device__ __forceinline__ int round_quotient(float q, float qz, float rz) {
     const float u = q * rz;
     const float r = rintf(u);
-    const float tol = 0.5f - (fabsf(u) * 9.5367431640625e-7f + 9.5367431640625e-7f);
-    if (fabsf(u - r) < tol && fabsf(u) < 1.0e6f) return (int)r;
+    const float slack = fmaf(fabsf(u), 9.5367431640625e-7f, 9.5367431640625e-7f);
+    if (fabsf(u - r) + slack < 0.5f && fabsf(u) < 1.0e6f) return (int)r;
     return __float2int_rn(fdiv(q, qz));
 }
 
+// voxel classes of one lane's 4-voxel segment, one bit per voxel in each mask
+struct SegClass { int check, free_, occ, exact, skip; };
+
 template <bool PINHOLE, bool TABLE, bool STATS>
-__global__ void __launch_bounds__(kIntThreads, 3) k_integrate_rows(const __grid_constant__ IntParams P) {
-    extern __shared__ float s_tab[];   // [0, w): (x - cx) / fx ; [w, w + h): (y - cy) / fy
+__global__ void __launch_bounds__(kIntThreads, 4) k_integrate_rows(const __grid_constant__ IntParams P) {
+    extern __shared__ float s_tab[];   // [0, w): (x - cx) / fx ; [w, w + h): (y - cy) / fy   (exact IEEE quotients)
     if (TABLE) {
         for (int i = threadIdx.x; i < P.w + P.h; i += kIntThreads)
             s_tab[i] = i < P.w ? fdiv(fsub((float)i, P.K[2]), P.K[0]) : fdiv(fsub((float)(i - P.w), P.K[5]), P.K[4]);
@@ -149,52 +153,49 @@ __global__ void __launch_bounds__(kIntThreads, 3) k_integrate_rows(const __grid_
         }
         xa &= ~127;                     // whole 128-voxel chunks: one bitmap word per warp iteration
         const int64_t row_off = (int64_t)row * rx;
-        const float* drow0 = P.depth;
+        const ConstDiv div_trunc(V.trunc);
+        const float ntrunc = -V.trunc;
 
-        for (int xbase = xa; xbase <= xb; xbase += 128) {   // warp-uniform trip count (shuffles below)
+        for (int xbase = xa; xbase <= xb; xbase += 128) {   // warp-uniform trip count (ballots below)
             const int x0 = xbase + 4 * lane;
             const bool active = x0 <= xb && x0 < rx;
             int cls_skip = 0, cls_check = 0, cls_free = 0, cls_occ = 0, cls_exact = 0;   // bit j = voxel j
-            int pix_x[4], pix_y[4];
-            float dep[4], pcx[4], pcy[4], pcz[4];
+            int pix[4];        // py << 16 | px of the voxels that are looked at
+            float dep[4];
+            // ---- phase 1: projection (canonical), depth look-up, classification by an approximate signed distance
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                dep[j] = 0.f; pix_x[j] = 0; pix_y[j] = 0; pcx[j] = pcy[j] = pcz[j] = 0.f;
+                dep[j] = 0.f; pix[j] = 0;
                 if (!active) continue;
                 const float cx = fmul(fsub((float)(x0 + j), hx), s);
-                pcx[j] = fadd(V.t[0], ffma(V.R[2], cz, ffma(V.R[0], cx, my0)));
-                pcy[j] = fadd(V.t[1], ffma(V.R[5], cz, ffma(V.R[3], cx, my1)));
-                pcz[j] = fadd(V.t[2], ffma(V.R[8], cz, ffma(V.R[6], cx, my2)));
-                if (!(pcz[j] > 0.0f)) { cls_check |= 1 << j; continue; }
+                const float pcx = fadd(V.t[0], ffma(V.R[2], cz, ffma(V.R[0], cx, my0)));
+                const float pcy = fadd(V.t[1], ffma(V.R[5], cz, ffma(V.R[3], cx, my1)));
+                const float pcz = fadd(V.t[2], ffma(V.R[8], cz, ffma(V.R[6], cx, my2)));
+                if (!(pcz > 0.0f)) { cls_check |= 1 << j; continue; }
                 float qx, qy, qz;
                 if (PINHOLE) {
-                    qx = ffma(P.K[2], pcz[j], fmul(P.K[0], pcx[j]));
-                    qy = ffma(P.K[5], pcz[j], fmul(P.K[4], pcy[j]));
-                    qz = pcz[j];
+                    qx = ffma(P.K[2], pcz, fmul(P.K[0], pcx));
+                    qy = ffma(P.K[5], pcz, fmul(P.K[4], pcy));
+                    qz = pcz;
                 } else {
-                    qx = dot_yxz(P.K[0], P.K[1], P.K[2], pcx[j], pcy[j], pcz[j]);
-                    qy = dot_yxz(P.K[3], P.K[4], P.K[5], pcx[j], pcy[j], pcz[j]);
-                    qz = dot_yxz(P.K[6], P.K[7], P.K[8], pcx[j], pcy[j], pcz[j]);
+                    qx = dot_yxz(P.K[0], P.K[1], P.K[2], pcx, pcy, pcz);
+                    qy = dot_yxz(P.K[3], P.K[4], P.K[5], pcx, pcy, pcz);
+                    qz = dot_yxz(P.K[6], P.K[7], P.K[8], pcx, pcy, pcz);
                 }
                 const float rz = rcp_approx(qz);
                 const int px = round_quotient(qx, qz, rz);
                 const int py = round_quotient(qy, qz, rz);
-                if (px < 0 || px >= P.w || py < 0 || py >= P.h) { cls_skip |= 1 << j; continue; }
-                pix_x[j] = px; pix_y[j] = py;
-                const float d = __ldg((const float*)((const char*)drow0 + (size_t)py * P.depth_pitch) + px);
+                if ((unsigned)px >= (unsigned)P.w || (unsigned)py >= (unsigned)P.h) { cls_skip |= 1 << j; continue; }
+                pix[j] = (py << 16) | px;
+                const float d = __ldg((const float*)((const char*)P.depth + (size_t)py * P.depth_pitch) + px);
                 dep[j] = d;
                 if (!(d > 0.0f)) { cls_check |= 1 << j; continue; }
-                // approximate signed distance: decides free space / occluded when safely outside the band
-                float lx, ly;
-                if (TABLE) { lx = s_tab[px]; ly = s_tab[P.w + py]; }
-                else { lx = fdiv(fsub((float)px, P.K[2]), P.K[0]); ly = fdiv(fsub((float)py, P.K[5]), P.K[4]); }
-                const float l2 = fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f);
-                const float n2 = ffma(pcz[j], pcz[j], ffma(pcx[j], pcx[j], fmul(pcy[j], pcy[j])));
-                const float proj = n2 * rsqrt_approx(n2) * rsqrt_approx(l2);   // |pc| / lambda, ~2^-21 relative
-                const float sdf_a = d - proj;
-                const float eps = (fabsf(d) + proj) * 2.44140625e-4f;          // 2^-12 relative guard
-                if (sdf_a > V.trunc + eps) cls_free |= 1 << j;
-                else if (sdf_a < -V.trunc - eps) cls_occ |= 1 << j;
+                // |pc| / lambda(pixel) lies within g_rel * pcz of pcz (the pixel ray and the voxel ray differ by at most
+                // half a pixel); outside the truncation band by more than that, the exact distance is not needed
+                const float sdf_a = d - pcz;
+                const float lim = fmaf(pcz, P.g_rel, V.trunc + P.g_abs);
+                if (sdf_a > lim) cls_free |= 1 << j;
+                else if (sdf_a < -lim) cls_occ |= 1 << j;
                 else cls_exact |= 1 << j;
             }
             const int touched = cls_check | cls_free | cls_occ | cls_exact;
@@ -208,29 +209,13 @@ __global__ void __launch_bounds__(kIntThreads, 3) k_integrate_rows(const __grid_
                     const float4 w4 = *reinterpret_cast<const float4*>(wp);
                     w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
                 }
-                // exact signed distance where the band test needs it (canonical sequence)
-                float sdf[4];
-                int in_band = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    sdf[j] = 0.f;
-                    if (cls_exact & (1 << j)) {
-                        const float lx = fdiv(fsub((float)pix_x[j], P.K[2]), P.K[0]);
-                        const float ly = fdiv(fsub((float)pix_y[j], P.K[5]), P.K[4]);
-                        const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
-                        const float inv_lambda = frcp(lambda);
-                        const float nrm = norm3(pcx[j], pcy[j], pcz[j]);
-                        sdf[j] = ffma(-nrm, inv_lambda, dep[j]);   // depth - (1/lambda)*|pc| as one FFMA (reference SASS)
-                        if (sdf[j] >= -V.trunc) in_band |= 1 << j;
-                    }
-                }
-                const int need_t = in_band | cls_free;
-                if (need_t) {
+                if (cls_free | cls_exact) {
                     const float4 t4 = *reinterpret_cast<const float4*>(tp);
                     tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
                     known = 0xF;
                 }
                 int wrote_t = 0, wrote_w = 0;
+                // ---- phase 2a: the classes that need no distance
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int bit = 1 << j;
@@ -248,23 +233,46 @@ __global__ void __launch_bounds__(kIntThreads, 3) k_integrate_rows(const __grid_
                             wrote_t |= bit; wrote_w |= bit;
                             if (STATS) ++st[0];
                         }
-                    } else if (in_band & bit) {
-                        const float q = fdiv(sdf[j], V.trunc);
-                        const float val = copysignf(fminf(1.0f, fabsf(q)), sdf[j]);
-                        float a = 1.0f;
-                        if (sdf[j] < V.trunc)
-                            a = __ldg((const float*)((const char*)V.assoc + (size_t)pix_y[j] * V.assoc_pitch) + pix_x[j]);
-                        const float ws = fadd(w[j], a);
-                        if (ws > 0.0f) {
-                            tv[j] = fdiv(ffma(w[j], tv[j], fmul(val, a)), ws);
-                            w[j] = fminf(ws, P.max_weight);
-                            wrote_t |= bit; wrote_w |= bit;
-                            if (STATS) ++st[0];
-                        }
-                    } else if ((cls_occ | cls_exact) & bit) {
+                    } else if (cls_occ & bit) {
                         // far behind the surface
                         if (w[j] == 0.0f) { tv[j] = -1.0f; wrote_t |= bit; known |= bit; if (STATS) ++st[1]; }
                         else if (STATS) ++st[2];
+                    }
+                }
+                // ---- phase 2b: voxels near the truncation band: exact signed distance (canonical sequence)
+                if (cls_exact) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int bit = 1 << j;
+                        if (!(cls_exact & bit)) continue;
+                        const int px = pix[j] & 0xffff, py = pix[j] >> 16;
+                        const float cx = fmul(fsub((float)(x0 + j), hx), s);
+                        const float pcx = fadd(V.t[0], ffma(V.R[2], cz, ffma(V.R[0], cx, my0)));
+                        const float pcy = fadd(V.t[1], ffma(V.R[5], cz, ffma(V.R[3], cx, my1)));
+                        const float pcz = fadd(V.t[2], ffma(V.R[8], cz, ffma(V.R[6], cx, my2)));
+                        float lx, ly;
+                        if (TABLE) { lx = s_tab[px]; ly = s_tab[P.w + py]; }
+                        else { lx = fdiv(fsub((float)px, P.K[2]), P.K[0]); ly = fdiv(fsub((float)py, P.K[5]), P.K[4]); }
+                        const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
+                        const float inv_lambda = frcp(lambda);
+                        const float nrm = norm3(pcx, pcy, pcz);
+                        const float sdf = ffma(-nrm, inv_lambda, dep[j]);   // depth - (1/lambda)*|pc| as one FFMA (reference SASS)
+                        if (sdf >= ntrunc) {
+                            const float q = div_trunc(sdf);
+                            const float val = copysignf(fminf(1.0f, fabsf(q)), sdf);
+                            float a = 1.0f;
+                            if (sdf < V.trunc)
+                                a = __ldg((const float*)((const char*)V.assoc + (size_t)py * V.assoc_pitch) + px);
+                            const float ws = fadd(w[j], a);
+                            if (ws > 0.0f) {
+                                tv[j] = fdiv(ffma(w[j], tv[j], fmul(val, a)), ws);
+                                w[j] = fminf(ws, P.max_weight);
+                                wrote_t |= bit; wrote_w |= bit;
+                                if (STATS) ++st[0];
+                            }
+                        } else if (w[j] == 0.0f) {
+                            tv[j] = -1.0f; wrote_t |= bit; if (STATS) ++st[1];
+                        } else if (STATS) ++st[2];
                     }
                 }
                 if (wrote_w) *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
@@ -427,6 +435,11 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
     P.gate_counts = gate_counts; P.gate_thresh = gate_thresh;
     P.stats = stats;
     const bool pin = is_pinhole(K);
+    // lambda(pixel) vs the voxel's own ray: the two differ by at most half a pixel in each direction, and
+    // d ln(lambda) / da = a / lambda^2 <= 1/2, so | ln(lambda_voxel / lambda_pixel) | <= (1/|fx| + 1/|fy|) / 4.
+    // A camera matrix that is not a plain pinhole gets an infinite guard: every voxel takes the exact path.
+    P.g_rel = pin ? 1.25f * 0.25f * (1.0f / fabsf(K[0]) + 1.0f / fabsf(K[4])) + 4.0e-6f : INFINITY;
+    P.g_abs = 1.0e-4f;
     if (!rows_ok) {
         if (pin) k_integrate_simple<true><<<(unsigned)items, kSimpleThreads, 0, stream>>>(P);
         else k_integrate_simple<false><<<(unsigned)items, kSimpleThreads, 0, stream>>>(P);

@@ -17,11 +17,12 @@
 //  * a volume is only traced inside the screen rectangle of its box;
 //  * the three IEEE divisions by the voxel size per march sample reuse one refined reciprocal
 //    (ConstDiv, emf_math.cuh) -- the same instruction sequence the reference build executes;
-//  * with the "safe sample" bitmaps (emf_volume::safe_bits, safe.cu) a fine-stepping ray whose last
-//    sample was exactly +1, 0 or -1 "crawls": it advances its ray parameter by the same sequence of
-//    fp32 additions, but while the bitmap certifies that the next sample would return that same
-//    value again it does not take it -- such a sample changes nothing of the march state.
+//  * with a brick map (emf_volume::brick_map, bricks.cu) a warp whose rays all carry exactly +1, 0 or -1
+//    "jumps": where the map certifies that the next n samples of every ray would return that same value
+//    again -- such a sample changes nothing of the march state -- they are not taken, and every ray advances
+//    its ray parameter by the same n fp32 additions in closed form (seq_add.h).
 #include "common.cuh"
+#include "seq_add.h"
 
 namespace emfb {
 
@@ -30,9 +31,8 @@ struct RayVol {
     const float* weights;
     const float* fg_probs;   // nullable
     const float* grads;      // nullable (float3 per voxel)
-    const uint32_t* safe;    // nullable: three "safe sample" bitmaps (safe.cu), one bit per 4-voxel x-segment
-    int wpr;                 // words per row of a bitmap
-    unsigned map_words;      // words per bitmap
+    const uint8_t* bmap;     // nullable: brick map (bricks.cu), one byte per 8^3 brick
+    int nbx, nby;            // bricks per row / rows per slice
     float* ray; size_t ray_pitch;
     float* vert; size_t vert_pitch;
     float* norm; size_t norm_pitch;
@@ -53,8 +53,8 @@ struct RayParams {
     float K[9];
     int32_t* hit_voxel;      // optional (single-volume API)
     int write_all;           // 1: batched semantics (ray/mask written for every pixel of the rect)
-    unsigned long long* stats;   // optional: [0] tsdf samples taken [1] samples skipped while crawling
-                                 //           [2] crawl attempts [3] weight samples
+    unsigned long long* stats;   // optional: [0] tsdf samples taken [1] samples skipped by jumps
+                                 //           [2] jumps [3] weight samples
 };
 
 constexpr int kTileW = 16, kTileH = 8;   // CTA tile; warp = 8 x 4 pixels
@@ -128,11 +128,14 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
     const RayVol& V = P.v[lo];
     const int lb = b - V.first_block;
     const int ty = lb / V.tiles_x, tx = lb - ty * V.tiles_x;
-    // warp = 8x4 pixel patch inside the 16x8 CTA tile
+    // warp = 8x4 pixel patch inside the 16x8 CTA tile.  Every lane of a warp stays in the march loop until the whole
+    // warp is done (lanes outside the rectangle idle), so that jumps can be agreed on with warp collectives.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = V.x0 + tx * kTileW + (warp & 1) * 8 + (lane & 7);
-    const int y = V.y0 + ty * kTileH + (warp >> 1) * 4 + (lane >> 3);
-    if (x >= V.x1 || y >= V.y1) return;   // (STATS: no warp-collective below)
+    const int xr = V.x0 + tx * kTileW + (warp & 1) * 8 + (lane & 7);
+    const int yr = V.y0 + ty * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    const bool valid = xr < V.x1 && yr < V.y1;
+    const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);
+    constexpr unsigned kFull = 0xffffffffu;
 
     float* ray_px = (float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x;
     uint8_t* mask_px = V.mask + (size_t)y * V.mask_pitch + x;
@@ -161,19 +164,18 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
                              fdiv(fsub(dz > 0.f ? bz : -bz, oz), dz));
     float tcur = fadd(s, tin);
     float tmax = fsub(tout, s);
-    const float old = P.write_all ? 0.0f : *ray_px;   // in/out far clip (TSDF.cu:496-500)
+    const float old = (P.write_all || !valid) ? 0.0f : *ray_px;   // in/out far clip (TSDF.cu:496-500)
     if (old != 0.0f) tmax = fminf(old, tmax);
 
-    if (!(tcur >= tmax)) {
-        const float hxh = fmul((float)(V.rx - 1), 0.5f), hyh = fmul((float)(V.ry - 1), 0.5f),
-                    hzh = fmul((float)(V.rz - 1), 0.5f);
-        const float half_s = fmul(s, 0.5f);
-        const ConstDiv div_s(s);
-        const int rx = V.rx, plane = V.rx * V.ry;
-        const uint32_t* __restrict__ safe = V.safe;
-        const int wpr = V.wpr, ry_ = V.ry, rz_ = V.rz;
-        float step = V.trunc;
-        float vx, vy, vz;
+    const float hxh = fmul((float)(V.rx - 1), 0.5f), hyh = fmul((float)(V.ry - 1), 0.5f), hzh = fmul((float)(V.rz - 1), 0.5f);
+    const float half_s = fmul(s, 0.5f);
+    const ConstDiv div_s(s);
+    const int rx = V.rx, plane = V.rx * V.ry;
+    const uint8_t* __restrict__ bmap = V.bmap;
+    float step = V.trunc;
+    float vx = 0.f, vy = 0.f, vz = 0.f, f = 0.f;
+    bool done = !valid || tcur >= tmax;
+    if (!done) {
         for (;;) {   // coarse skip (TSDF.cu:509-515)
             vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
             vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
@@ -183,108 +185,110 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
         }
         // still outside => the reference's march loop cannot run (tcur >= tmax): defined as no hit
         if (!out_of(vx, vy, vz, 1.0f, frx, fry, frz) && vx == vx && vy == vy && vz == vz) {
-            float f = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
+            f = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
             if (fabsf(f) < 1.0f) step = s;
             if (fabsf(f) < 0.8f) step = half_s;
-            // One loop, two kinds of iteration per lane (no nested per-lane loop: the lanes of a warp advance
-            // together).  CRAWL: up to four march steps whose samples are certified to return f again, looked up
-            // speculatively (four independent bitmap loads) and accepted as the longest certified prefix.
-            // SAMPLE: one march step of the reference algorithm.
-            int backoff = 0, wait = 0;   // crawl attempts that certify nothing are retried less often
-            bool crawling = false;
-            const uint32_t* __restrict__ map = safe;
-            float px = 0.f, py = 0.f, pz = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f;
-            int since_sync = 0;
-            for (;;) {
-                if (!crawling && safe && step <= s && (f == 1.0f || f == 0.0f || f == -1.0f)) {
-                    if (wait > 0) {
-                        --wait;
-                    } else {
-                        // (vx, vy, vz) is the exact sample position of tcur here
-                        crawling = true;
-                        map = safe + (f == 1.0f ? 0u : (f == 0.0f ? V.map_words : 2u * V.map_words));
-                        const float sc = (step == s) ? 1.0f : 0.5f;      // voxels per step along the ray
-                        ddx = dx * sc; ddy = dy * sc; ddz = dz * sc;
-                        px = vx; py = vy; pz = vz;
-                        since_sync = 0;
-                        if (STATS) ++st[2];
-                    }
-                }
-                bool sample = true;
-                if (crawling) {
-                    float tn[4];
-                    uint32_t ok = 0;
-                    tn[0] = fadd(tcur, step); tn[1] = fadd(tn[0], step); tn[2] = fadd(tn[1], step); tn[3] = fadd(tn[2], step);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float qx = px + ddx * (float)(k + 1), qy = py + ddy * (float)(k + 1), qz = pz + ddz * (float)(k + 1);
-                        const int ix = __float2int_rz(qx), iy = __float2int_rz(qy), iz = __float2int_rz(qz);
-                        const bool in = tn[k] <= tmax && qx >= 0.0f && qy >= 0.0f && qz >= 0.0f && ix < rx && iy < ry_ && iz < rz_;
-                        uint32_t wd = 0;
-                        if (in) wd = __ldg(map + (unsigned)((iz * ry_ + iy) * wpr + (ix >> 7)));
-                        ok |= ((wd >> ((ix >> 2) & 31)) & 1u) << k;
-                    }
-                    const int n = __ffs(~ok) - 1;          // certified prefix, 0..4
-                    if (n > 0) {
-                        tcur = n == 1 ? tn[0] : (n == 2 ? tn[1] : (n == 3 ? tn[2] : tn[3]));
-                        px += ddx * (float)n; py += ddy * (float)n; pz += ddz * (float)n;
-                        if (STATS) st[1] += n;
-                        since_sync += n;
-                        if (since_sync >= 64) {              // keep the running position within 1e-2 voxels
-                            px = fadd(hxh, div_s(ffma(dx, tcur, ox)));
-                            py = fadd(hyh, div_s(ffma(dy, tcur, oy)));
-                            pz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
-                            since_sync = 0;
-                        }
-                        backoff = 0;
-                    }
-                    if (n == 4) {
-                        sample = false;                      // keep crawling
-                    } else {
-                        crawling = false;                    // the next step is not certified (or ends the ray): sample it
-                        if (n == 0) { backoff = min(2 * backoff + 1, 15); wait = backoff; }
-                    }
-                }
-                // (structured control flow from here on -- flags instead of `continue` -- so that the lanes leaving
-                //  the crawl and the lanes that were sampling anyway execute the sample together)
-                if (sample) {
-                    tcur = fadd(tcur, step);
-                    if (!(tcur <= tmax)) break;
-                    vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
-                    vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
-                    vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
-                    if (!out_of(vx, vy, vz, 2.0f, frx, fry, frz)) {
-                        const int lx = __float2int_rz(vx), ly = __float2int_rz(vy), lz = __float2int_rz(vz);
-                        const float fn = trilinear32(V.tsdf, rx, plane, lx, ly, lz, vx, vy, vz);
-                        if (STATS) ++st[0];
-                        // back face (TSDF.cu:532): the weight sample is only needed for this test
-                        if (f < 0.0f && fn > 0.0f) {
-                            if (STATS) ++st[3];
-                            if (trilinear_weight(V, vx, vy, vz) > 0.0f) break;
-                        }
-                        if (fabsf(fn) < 1.0f) step = s;
-                        if (fabsf(fn) < 0.8f) step = half_s;
-                        bool keep_f = false;
-                        if (f > 0.0f && fn < 0.0f) {   // front face (TSDF.cu:540)
-                            const float ts = fsub(tcur, fdiv(fmul(f, step), fsub(fn, f)));
-                            const float mx = fmul(dx, ts), my = fmul(dy, ts), mz = fmul(dz, ts);
-                            const float sx = fadd(hxh, div_s(fadd(ox, mx)));
-                            const float sy = fadd(hyh, div_s(fadd(oy, my)));
-                            const float sz = fadd(hzh, div_s(fadd(oz, mz)));
-                            if (out_of(sx, sy, sz, 2.0f, frx, fry, frz)) {
-                                keep_f = true;             // reference `continue`: f keeps its old value
-                            } else if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
-                                hit = true; out_t = ts;
-                                hvx = sx; hvy = sy; hvz = sz; hmx = mx; hmy = my; hmz = mz;
-                                break;
+        } else {
+            done = true;
+        }
+    }
+    // jump geometry: voxels advanced per metre of ray parameter along each axis (and the largest of them)
+    const float ax_m = fdiv(fabsf(dx), s), ay_m = fdiv(fabsf(dy), s), az_m = fdiv(fabsf(dz), s);
+    const float vox_per_m = fmaxf(ax_m, fmaxf(ay_m, az_m));
+    int wait = 0;   // (warp-uniform) march steps to take before the brick map is consulted again after a failed attempt
+    while (!__all_sync(kFull, done)) {
+        // ---- jump: (vx, vy, vz) is the sample position of tcur.  Where the brick map certifies that every sample the next
+        //      n march steps would take returns exactly f, those steps change nothing but tcur.  The warp jumps together
+        //      (n = the smallest count any of its marching rays is certified for) and so stays in lockstep.
+        if (bmap) {
+            const bool isconst = done || f == 1.0f || f == 0.0f || f == -1.0f;
+            if (__all_sync(kFull, isconst)) {
+                if (wait == 0) {
+                    int n = 0x7fffffff;
+                    if (!done) {
+                        n = 0;
+                        if (vx >= 0.0f && vy >= 0.0f && vz >= 0.0f && vx < frx && vy < fry && vz < frz) {
+                            const int bxi = __float2int_rz(vx) >> 3, byi = __float2int_rz(vy) >> 3, bzi = __float2int_rz(vz) >> 3;
+                            const unsigned e = __ldg(bmap + (unsigned)((bzi * V.nby + byi) * V.nbx + bxi));
+                            const unsigned want = f == 1.0f ? 1u : (f == 0.0f ? 2u : 3u);
+                            if ((e >> 4) == want) {
+                                const unsigned D = e & 7u;
+                                const float inv_step = __fdividef(0.999f, step);
+                                float nf = 0.0f;
+                                if (D >= 2u) {
+                                    // every brick within D - 1 bricks holds the constant: any sample whose base voxel moves less
+                                    // than 8 (D - 1) - 1 voxels (Chebyshev) from here is certified
+                                    nf = ((float)((D - 1u) * 8u) - 1.25f) * __fdividef(inv_step, vox_per_m);
+                                } else if (e & 8u) {
+                                    // the 2 x 2 x 2 block of bricks starting at this one holds the constant: certified while the
+                                    // base voxel stays in [8 b, 8 b + 14] on every axis
+                                    const float lox = vx - (float)(bxi << 3), loy = vy - (float)(byi << 3), loz = vz - (float)(bzi << 3);
+                                    const float rx_ = (dx > 0.0f ? 15.0f - lox : lox) - 0.05f;
+                                    const float ry_ = (dy > 0.0f ? 15.0f - loy : loy) - 0.05f;
+                                    const float rz_ = (dz > 0.0f ? 15.0f - loz : loz) - 0.05f;
+                                    nf = fminf(fminf(__fdividef(rx_, fmaxf(ax_m, 1e-12f)), __fdividef(ry_, fmaxf(ay_m, 1e-12f))),
+                                               __fdividef(rz_, fmaxf(az_m, 1e-12f))) * inv_step;
+                                }
+                                n = nf >= 1.0f ? (nf < 4096.0f ? (int)nf : 4096) : 0;
                             }
                         }
-                        if (!keep_f) f = fn;
                     }
+                    n = __reduce_min_sync(kFull, n);
+                    if (n >= 1) {
+                        if (!done) {
+                            tcur = emf_seq_add(tcur, step, n);
+                            if (STATS) { st[1] += n; ++st[2]; }
+                            if (!(tcur <= tmax)) {
+                                done = true;                 // the ray ends inside the certified region: no hit
+                            } else {
+                                vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
+                                vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
+                                vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
+                            }
+                        }
+                        continue;
+                    }
+                    wait = 1;
+                } else {
+                    --wait;
                 }
             }
         }
+        if (done) continue;
+        // ---- one march step of the reference algorithm (TSDF.cu:523-572)
+        tcur = fadd(tcur, step);
+        if (!(tcur <= tmax)) { done = true; continue; }
+        vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
+        vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
+        vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
+        if (out_of(vx, vy, vz, 2.0f, frx, fry, frz)) continue;
+        const int lx = __float2int_rz(vx), ly = __float2int_rz(vy), lz = __float2int_rz(vz);
+        const float fn = trilinear32(V.tsdf, rx, plane, lx, ly, lz, vx, vy, vz);
+        if (STATS) ++st[0];
+        // back face (TSDF.cu:532): the weight sample is only needed for this test
+        if (f < 0.0f && fn > 0.0f) {
+            if (STATS) ++st[3];
+            if (trilinear_weight(V, vx, vy, vz) > 0.0f) { done = true; continue; }
+        }
+        if (fabsf(fn) < 1.0f) step = s;
+        if (fabsf(fn) < 0.8f) step = half_s;
+        if (f > 0.0f && fn < 0.0f) {   // front face (TSDF.cu:540)
+            const float ts = fsub(tcur, fdiv(fmul(f, step), fsub(fn, f)));
+            const float mx = fmul(dx, ts), my = fmul(dy, ts), mz = fmul(dz, ts);
+            const float sx = fadd(hxh, div_s(fadd(ox, mx)));
+            const float sy = fadd(hyh, div_s(fadd(oy, my)));
+            const float sz = fadd(hzh, div_s(fadd(oz, mz)));
+            if (out_of(sx, sy, sz, 2.0f, frx, fry, frz)) continue;   // reference `continue`: f keeps its old value
+            if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
+                hit = true; out_t = ts;
+                hvx = sx; hvy = sy; hvz = sz; hmx = mx; hmy = my; hmz = mz;
+                done = true;
+                continue;
+            }
+        }
+        f = fn;
     }
+    if (!valid) return;
 
     if (hit) {
         float g[3];
@@ -324,9 +328,8 @@ static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const
     if (ray->width != w || ray->height != h || !same_size(ray, vert) || !same_size(ray, norm) || !same_size(ray, mask))
         return EMF_ERR_INVALID;
     d.tsdf = v.tsdf; d.weights = v.weights; d.fg_probs = v.fg_probs; d.grads = v.grads;
-    d.safe = (v.safe_bits && v.res[0] % 4 == 0) ? v.safe_bits : nullptr;
-    d.wpr = emf_bitmap_words_per_row(v.res[0]);
-    d.map_words = (unsigned)((size_t)d.wpr * v.res[1] * v.res[2]);
+    d.bmap = (v.brick_map && v.const_bits && v.res[0] % 4 == 0) ? v.brick_map : nullptr;
+    d.nbx = (v.res[0] + 7) / 8; d.nby = (v.res[1] + 7) / 8;
     d.ray = (float*)ray->ptr; d.ray_pitch = ray->pitch;
     d.vert = (float*)vert->ptr; d.vert_pitch = vert->pitch;
     d.norm = (float*)norm->ptr; d.norm_pitch = norm->pitch;

@@ -22,7 +22,7 @@ from .volume import ObjTSDF, Params, TSDF
 
 class EMFusionEngine:
     def __init__(self, params: Params, device="cuda", rank: int = 0, world_size: int = 1, group=None,
-                 materialize_grads: bool = False, accelerate: bool = False):
+                 materialize_grads: bool = False, accelerate: bool = True):
         self.params = params
         self.accelerate = accelerate
         self.device = torch.device(device)
@@ -257,7 +257,7 @@ class EMFusionEngine:
         ops.integrateVolumes(cv, [rel_pose_OC(self.pose, v.pose) for v in vols],
                              self.params.intr, self.depth, self._assoc_images(vols),
                              self.params.tsdfParams.maxTSDFWeight)
-        ops.updateSafeBits(cv)
+        ops.updateBrickMaps(cv)
         for v in vols:
             v._grads_dirty = True
             v.updateGradients()

@@ -22,7 +22,7 @@ LAUNCHES = {}
 _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1, "raycastTSDF": 1, "getVolumeVals": 1,
                      "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
                      "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
-                     "updateSafeBits": 1}
+                     "updateBrickMaps": 2}
 
 
 def _count(name: str) -> None:
@@ -94,14 +94,14 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def volume(tsdf, weights, res, voxel_size, truncdist, grads=None, fg_probs=None, vid=0, const_bits=None,
-           safe_bits=None) -> Volume:
+           brick_map=None) -> Volume:
     v = Volume()
     v.tsdf = _ptr(tsdf)
     v.weights = _ptr(weights)
     v.grads = _ptr(grads)
     v.fg_probs = _ptr(fg_probs)
     v.const_bits = _ptr(const_bits)
-    v.safe_bits = _ptr(safe_bits)
+    v.brick_map = _ptr(brick_map)
     v.res[:] = [int(r) for r in res]
     v.voxel_size = float(voxel_size)
     v.truncdist = float(truncdist)
@@ -238,11 +238,15 @@ def integrateVolumes(vols, rel_poses_OC, intr, depth, assoc, maxWeight, stream=N
     _count("integrateVolumes")
 
 
-def updateSafeBits(vols, stream=None):
-    """safe_bits <- erosion of const_bits for every volume that carries both (one launch)."""
-    check(_lib.lib().emf_update_safe_bits(len(vols), _vol_array(vols), _stream(stream)), "updateSafeBits")
-    if any(v.const_bits and v.safe_bits for v in vols):
-        _count("updateSafeBits")
+def updateBrickMaps(vols, stream=None):
+    """brick_map <- const_bits for every volume that carries both (two launches)."""
+    check(_lib.lib().emf_update_brick_maps(len(vols), _vol_array(vols), _stream(stream)), "updateBrickMaps")
+    if any(v.const_bits and v.brick_map for v in vols):
+        _count("updateBrickMaps")
+
+
+def brickMapBytes(res) -> int:
+    return int(_lib.lib().emf_brick_map_bytes(_i3(res)))
 
 
 def resetBitmaps(vol: Volume, stream=None):

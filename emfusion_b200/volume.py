@@ -66,7 +66,7 @@ class Params:
 
 class TSDF:
     def __init__(self, volumeRes, voxelSize: float, truncdist: float, pose: Affine, params: TSDFParams,
-                 frameSize, device="cuda", materialize_grads: bool = False, accelerate: bool = False):
+                 frameSize, device="cuda", materialize_grads: bool = False, accelerate: bool = True):
         self.params = params
         self.volumeRes = tuple(int(r) for r in volumeRes)
         self.voxelSize = float(np.float32(voxelSize))
@@ -77,12 +77,12 @@ class TSDF:
         self.tsdfVol = torch.empty((ry * rz, rx), dtype=torch.float32, device=self.device)
         self.tsdfWeights = torch.empty((ry * rz, rx), dtype=torch.float32, device=self.device)
         # acceleration state (no reference counterpart; results are unchanged): constant-segment bitmaps
-        # maintained by the integrate kernel and the "safe sample" bitmaps the raycast crawls through
-        self.constBits = self.safeBits = None
+        # maintained by the integrate kernel and the brick map the raycast jumps through
+        self.constBits = self.brickMap = None
         if accelerate and rx % 4 == 0:
             words = ops.bitmapWords(self.volumeRes)
             self.constBits = torch.empty((3 * words,), dtype=torch.int32, device=self.device)
-            self.safeBits = torch.empty((3 * words,), dtype=torch.int32, device=self.device)
+            self.brickMap = torch.empty((ops.brickMapBytes(self.volumeRes),), dtype=torch.uint8, device=self.device)
         self.materialize_grads = materialize_grads
         self._grads: Optional[torch.Tensor] = None
         self._grads_dirty = True
@@ -94,7 +94,7 @@ class TSDF:
         self.tsdfVol.zero_()
         self.tsdfWeights.zero_()
         if self.constBits is not None:
-            ops.resetBitmaps(self.c_volume())   # every segment is "all 0"; nothing certified safe yet
+            ops.resetBitmaps(self.c_volume())   # every segment is "all 0"; the brick map is rebuilt
         if self._grads is not None:
             self._grads.zero_()
         self._grads_dirty = False if self._grads is not None else True
@@ -127,7 +127,7 @@ class TSDF:
         v = [self.c_volume()]
         ops.integrateVolumes(v, [rel_pose_OC(cam_pose, self.pose)], intr, depth, [weights],
                              self.params.maxTSDFWeight, stream)
-        ops.updateSafeBits(v, stream)
+        ops.updateBrickMaps(v, stream)
         self._grads_dirty = True
 
     # -- src/core/TSDF.cpp:120-123
@@ -154,7 +154,7 @@ class TSDF:
     def c_volume(self, with_grads: bool = False):
         return ops.volume(self.tsdfVol, self.tsdfWeights, self.volumeRes, self.voxelSize, self.truncdist,
                           grads=self._raycast_grads() if with_grads else None, fg_probs=self._fg(), vid=self.id,
-                          const_bits=self.constBits, safe_bits=self.safeBits)
+                          const_bits=self.constBits, brick_map=self.brickMap)
 
     def _fg(self):
         return None
@@ -182,7 +182,7 @@ class ObjTSDF(TSDF):
     nextID = 0   # static counter, incremented only by the constructor (src/core/ObjTSDF.cpp:28,34)
 
     def __init__(self, volumeRes, voxelSize, truncdist, pose, params, frameSize, device="cuda",
-                 materialize_grads: bool = False, accelerate: bool = False):
+                 materialize_grads: bool = False, accelerate: bool = True):
         rx, ry, rz = (int(r) for r in volumeRes)
         dev = torch.device(device)
         self.fgBgProbs = torch.empty((ry * rz, rx, 2), dtype=torch.float32, device=dev)

@@ -74,17 +74,16 @@ typedef struct emf_volume {
     const float* grads;    /* tsdfGrads (float3 per voxel) or NULL: gradients are then taken on the fly */
     const float* fg_probs; /* fgProbs (objects) or NULL (background) */
     /* Optional acceleration state (no reference counterpart; results are unchanged).  NULL = off.
-     * A "map" has one bit per 4-voxel x-segment, rows padded to whole 32-bit words:
-     *   words per map = emf_bitmap_words_per_row(Rx) * Ry * Rz.
-     * const_bits: three consecutive maps -- segment is all +1 / all 0 / all -1.  Maintained by
-     *   emf_integrate_volumes*; whoever zeroes the volume must set map 1 (all 0) to ones and the others to
-     *   zero (emf_reset_bitmaps); anyone else writing tsdf must clear all three.
-     * safe_bits: three consecutive maps derived by emf_update_safe_bits: bit set = every voxel within one
-     *   segment in x and [-1, +2] voxels in y and z of the segment holds that constant, i.e. any trilinear
-     *   sample whose base voxel is within one voxel of the segment returns exactly that constant.  The raycast
-     *   skips such samples (raycast.cu). */
+     * const_bits: three consecutive bitmaps -- a 4-voxel x-segment is all +1 / all 0 / all -1 -- one bit per
+     *   segment, rows padded to whole 32-bit words: words per map = emf_bitmap_words_per_row(Rx) * Ry * Rz.
+     *   Maintained by emf_integrate_volumes*; whoever zeroes the volume calls emf_reset_bitmaps; anyone else
+     *   writing tsdf must clear all three maps.  Requires Rx % 4 == 0 and 16-byte aligned arrays.
+     * brick_map: emf_brick_map_bytes(res) bytes, derived from const_bits by emf_update_brick_maps: one byte per
+     *   8^3 brick, (m << 4) | (P << 3) | D -- the whole brick holds constant m (1: +1, 2: 0, 3: -1; 0 = mixed), so
+     *   does every brick within D - 1 bricks of it, and (P) so does the 2x2x2 block of bricks starting at it.
+     *   The raycast skips the march samples these certify (raycast.cu). */
     uint32_t* const_bits;
-    uint32_t* safe_bits;
+    uint8_t* brick_map;
     int res[3];            /* volumeRes (x, y, z) */
     float voxel_size;
     float truncdist;
@@ -175,8 +174,8 @@ EMF_API int emf_assoc_normalise(int n_img, const emf_image* assoc_io, const emf_
  * mask_out[i] (u8), vert_out[i]/norm_out[i] (float3, hit pixels only).  rects (n_vol x 4 ints:
  * x0, y0, x1, y1, exclusive upper) bound the pixels each volume can cover; pixels outside a
  * volume's rect are not touched and must be treated as "no hit" by the consumer.
- * stats (optional, 4 x uint64 on the device, accumulated): TSDF samples taken, march samples skipped inside
- * constant bricks, brick look-ups that skipped, weight samples -- the raycast's roofline numerator. */
+ * stats (optional, 4 x uint64 on the device, accumulated): TSDF samples taken, march samples skipped by jumps
+ * through constant bricks, jumps, weight samples -- the raycast's roofline numerator. */
 EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
                         const int* rects, const emf_image* ray_out, const emf_image* vert_out,
                         const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
@@ -210,11 +209,14 @@ EMF_API int emf_integrate_volumes_gated(int n_vol, const emf_volume* vols, const
                                 const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,
                                 emf_stream_t stream);
 
-/* Derives safe_bits from const_bits for every volume that carries both (others are skipped).
+/* Derives brick_map from const_bits for every volume that carries both (others are skipped); two launches.
  * Call after integrating and before raycasting. */
-EMF_API int emf_update_safe_bits(int n_vol, const emf_volume* vols, emf_stream_t stream);
+EMF_API int emf_update_brick_maps(int n_vol, const emf_volume* vols, emf_stream_t stream);
 
-/* Bitmap state of a freshly zeroed volume: const map "all 0" = ones, everything else = zero. */
+/* Bytes of emf_volume::brick_map for a volume of this resolution (0 if the resolution is invalid). */
+EMF_API size_t emf_brick_map_bytes(const int res[3]);
+
+/* Acceleration state of a freshly zeroed volume: every segment / brick is "all 0". */
 EMF_API int emf_reset_bitmaps(const emf_volume* vol, emf_stream_t stream);
 
 /* 32-bit words per volume row in a segment bitmap. */

@@ -69,6 +69,15 @@ for name, sl in (("bg", slice(0, 1)), ("objs", slice(1, None))):
     px = sum((r[2] - r[0]) * (r[3] - r[1]) for r in rects[sl])
     hits = sum(int(m.sum()) for m in mask[sl])
     print(f"raycast {name}: rect px {px} hits {hits} stats {st.cpu().numpy().tolist()}")
+cv_nb = [ops.volume(v.tsdfVol, v.tsdfWeights, v.volumeRes, v.voxelSize, v.truncdist, fg_probs=v._fg(), vid=v.id) for v in vols]
+rc()
+keep = [x.clone() for x in ray + vert + norm + mask]
+ops.raycastVolumes(cv_nb, T, prm.intr, rects, ray, vert, norm, mask)
+same = all(bool((a.view(torch.int32) == b.view(torch.int32)).all()) if a.dtype == torch.float32 else bool((a == b).all())
+           for a, b in zip(keep, ray + vert + norm + mask))
+print("raycast with brick maps == without (bitwise, all volumes):", same)
+print("raycast all, no brick maps ms", timeit(lambda: ops.raycastVolumes(cv_nb, T, prm.intr, rects, ray, vert, norm, mask)))
+print("brick maps update ms", timeit(lambda: ops.updateBrickMaps(cv)))
 print("raycast all ms", timeit(rc))
 print("raycast bg  ms", timeit(lambda: rc(slice(0, 1))))
 print("raycast obj ms", timeit(lambda: rc(slice(1, None))))
@@ -85,3 +94,16 @@ for name, sl in (("all", slice(None)), ("bg", slice(0, 1)), ("objs", slice(1, No
     print(f"integrate {name} ms", timeit(lambda: ops.integrateVolumes(cvi[sl], Toc[sl], prm.intr, eng.depth, assoc[sl], 64.0)))
 print("assoc ms", timeit(eng.computeAssociationWeights))
 print("points ms", timeit(lambda: eng.set_depth(d_dev[i])))
+
+# ---- brick map coverage vs ground truth (background)
+b = eng.background
+if b.brickMap is not None:
+    R = b.volumeRes[0]; nb = R // 8
+    t = b.tsdfVol.reshape(nb, 8, nb, 8, nb, 8)
+    m = b.brickMap[: nb ** 3].reshape(nb, nb, nb).to(torch.int64)
+    code, Pf, D = m >> 4, (m >> 3) & 1, m & 7
+    for k, c in enumerate((1.0, 0.0, -1.0)):
+        truth = (t == c).all(dim=5).all(dim=3).all(dim=1)
+        print(f"bg bricks constant {c:+.0f}: truth {float(truth.float().mean()):.4f} flagged {float((code == k + 1).float().mean()):.4f} "
+              f"P {float(((code == k + 1) & (Pf == 1)).float().mean()):.4f} D>=2 {float(((code == k + 1) & (D >= 2)).float().mean()):.4f}")
+    print("bg voxels == 1:", float((b.tsdfVol == 1).float().mean()), " == 0:", float((b.tsdfVol == 0).float().mean()), " == -1:", float((b.tsdfVol == -1).float().mean()))

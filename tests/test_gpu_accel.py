@@ -1,7 +1,7 @@
 """-m gpu: the acceleration state (segment status, constant-brick map, frustum culling, approximate-then-exact
 arithmetic) must never change a result.
  * integrate under random camera poses (rotated, inside the volume, looking away, grazing) == C oracle, bit-exact;
- * the constant-segment and safe-sample bitmaps are sound (a set bit certifies the voxel values it claims) and tight;
+ * the constant-segment and brick maps are sound (an entry certifies the voxel values it claims);
  * the engine with acceleration on == the engine with acceleration off, bit for bit, over a moving stream;
  * ConstDiv (hoisted-reciprocal IEEE division) is exercised through the raycast against the reference kernels in
    tests/test_gpu_vs_reference.py; here additionally at larger volumes where rays cross many bricks."""
@@ -89,25 +89,45 @@ def check_const_bits(tsdf, bits, res):
     return [float(m[k].float().mean()) for k in range(3)]
 
 
-def check_safe_bits(tsdf, bits, res):
-    """a set bit certifies x in [4xs-4, 4xs+7], y in [y-1, y+2], z in [z-1, z+2] all equal the constant"""
+def brick_view(bmap, res):
+    """brick_map bytes -> (code, D) int tensors of shape (nbz, nby, nbx)"""
+    nb = [(r + 7) // 8 for r in res]
+    n = nb[0] * nb[1] * nb[2]
+    m = bmap[:n].reshape(nb[2], nb[1], nb[0]).to(torch.int64)
+    return m >> 4, m & 7, (m >> 3) & 1
+
+
+def check_brick_map(tsdf, bmap, res, tight=False):
+    """(m << 4) | D certifies: every voxel of every brick within D - 1 bricks (Chebyshev) of this one, as far as it lies
+    inside the volume, holds constant VALS[m - 1]."""
     import torch.nn.functional as F
     rx, ry, rz = res
-    t = tsdf.reshape(1, 1, rz, ry, rx)
-    m = unpack_maps(bits, res)
-    out = []
+    code, D, Pf = brick_view(bmap, res)
+    nbz, nby, nbx = code.shape
+    t = tsdf.reshape(rz, ry, rx)
+    pad = (0, nbx * 8 - rx, 0, nby * 8 - ry, 0, nbz * 8 - rz)
+    fr = []
+    assert int(D.max()) <= 7 and bool(((code == 0) == (D == 0)).all())
     for k, c in enumerate(VALS):
-        bad = (t != c).float()
-        bad = F.pad(bad, (4, 7, 1, 2, 1, 2), value=1.0)
-        pooled = F.max_pool3d(bad, kernel_size=(4, 4, 12), stride=(1, 1, 4))[0, 0]
-        assert pooled.shape == m[k].shape, (pooled.shape, m[k].shape)
-        wrong = m[k] & (pooled > 0)
-        assert not bool(wrong.any()), f"{int(wrong.sum())} segments are certified safe for {c} but are not"
-        # and the map is tight: everything certifiable is certified
-        missed = (~m[k]) & (pooled == 0)
-        assert not bool(missed.any()), f"{int(missed.sum())} safe segments for {c} are not certified"
-        out.append(float(m[k].float().mean()))
-    return out
+        bad = F.pad((t != c).float(), pad, value=0.0)[None, None]          # outside the volume: never "bad"
+        brick_bad = F.max_pool3d(bad, kernel_size=8, stride=8)[0, 0] > 0   # (nbz, nby, nbx)
+        for d in range(1, 8):
+            sel = (code == k + 1) & (D >= d)
+            if not bool(sel.any()):
+                continue
+            r = d - 1
+            nb_bad = F.max_pool3d(brick_bad[None, None].float(), kernel_size=2 * r + 1, stride=1, padding=r)[0, 0] > 0
+            wrong = sel & nb_bad
+            assert not bool(wrong.any()), f"{int(wrong.sum())} bricks certify constant {c} with D >= {d} but are not"
+            if tight:   # whatever the segment bitmaps allow is certified
+                miss = (~nb_bad) & ~((code == k + 1) & (D >= d))
+                assert not bool(miss.any()), f"{int(miss.sum())} bricks could certify {c} with D >= {d} but do not"
+        # P: the 2x2x2 block of bricks starting here (as far as inside the volume) holds the constant
+        blk_bad = F.max_pool3d(F.pad(brick_bad[None, None].float(), (0, 1, 0, 1, 0, 1), value=0.0), kernel_size=2, stride=1)[0, 0] > 0
+        wrong = (code == k + 1) & (Pf == 1) & blk_bad
+        assert not bool(wrong.any()), f"{int(wrong.sum())} bricks flag a constant-{c} 2x2x2 block that is not"
+        fr.append(float(((code == k + 1) & ((D >= 2) | (Pf == 1))).float().mean()))
+    return fr
 
 
 def build(accel, w=320, h=240, bg=128, n_obj=3, obj=64, seed=5):
@@ -148,9 +168,9 @@ def test_acceleration_changes_nothing(cuda_dev):
     fr = []
     for v in fast.local_volumes():
         fr.append((check_const_bits(v.tsdfVol.reshape(-1), v.constBits, v.volumeRes),
-                   check_safe_bits(v.tsdfVol.reshape(-1), v.safeBits, v.volumeRes)))
-    # the maps are not vacuous: free space (+1) of the background is certified
-    assert fr[0][0][0] > 0.03 and fr[0][1][0] > 0.01, fr
+                   check_brick_map(v.tsdfVol.reshape(-1), v.brickMap, v.volumeRes)))
+    # the maps are not vacuous: free space (+1) and never-seen space (0) of the background are certified
+    assert fr[0][0][0] > 0.03 and fr[0][1][0] + fr[0][1][1] > 0.01, fr
     assert int(fast.bg_mask.sum()) > 0.8 * fast.w * fast.h
 
 
@@ -166,16 +186,18 @@ def test_raycast_with_bricks_vs_oracle(oracle, cuda_dev):
     pose = Affine.translation([0, 0, 2.56])
     t_g, w_g = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
     cbits = torch.zeros((3 * ops.bitmapWords(res),), dtype=torch.int32, device=DEV)
-    sbits = torch.zeros_like(cbits)
-    v = ops.volume(t_g, w_g, res, voxel, trunc, const_bits=cbits, safe_bits=sbits)
+    bmap = torch.zeros((ops.brickMapBytes(res),), dtype=torch.uint8, device=DEV)
+    v = ops.volume(t_g, w_g, res, voxel, trunc, const_bits=cbits, brick_map=bmap)
     ops.resetBitmaps(v)
+    code, D, Pf = brick_view(bmap, res)
+    assert bool((code == 2).all()) and bool((D == 7).all()) and bool((Pf == 1).all())     # a zeroed volume: every brick "all 0", full radius
     ones = torch.ones((h, w), device=DEV)
     for f in range(4):
         depth, _ = scene.render(f)
         ops.integrateVolumes([v], [rel_pose_OC(scene.cam_pose(f), pose)], scene.K, cu(depth), [ones], 64.0)
-    ops.updateSafeBits([v])
+    ops.updateBrickMaps([v])
     check_const_bits(t_g, cbits, res)
-    assert check_safe_bits(t_g, sbits, res)[0] > 0.005
+    assert sum(check_brick_map(t_g, bmap, res)) > 0.005
     t_np, w_np = t_g.cpu().numpy(), w_g.cpu().numpy()
     for f in (4, 9):
         T = rel_pose_CO(scene.cam_pose(f), pose)
