@@ -37,7 +37,7 @@ class TsdfParams(C.Structure):
 
 
 class Volume(C.Structure):
-    _fields_ = [("tsdf", C.c_void_p), ("weights", C.c_void_p), ("grads", C.c_void_p), ("fg_probs", C.c_void_p),
+    _fields_ = [("tsdf", C.c_void_p), ("weights", C.c_void_p), ("grads", C.c_void_p), ("fg_probs", C.c_void_p), ("fg_box", C.c_void_p),
                 ("const_bits", C.c_void_p), ("brick_map", C.c_void_p), ("res", C.c_int * 3), ("voxel_size", C.c_float), ("truncdist", C.c_float), ("id", C.c_int)]
 
 
@@ -53,6 +53,7 @@ _SIGS = {
     "emf_update_fgbg_probs": [_P(Image), _P(Image), C.c_void_p, C.c_void_p, C.c_void_p, _P(Pose), _P(C.c_float),
                               _P(C.c_int), C.c_float, C.c_void_p],
     "emf_compute_fg_probs": [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    "emf_compute_fg_probs_box": [C.c_void_p, _P(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "emf_compute_association": [_P(Volume), _P(Image), _P(Pose), _P(TsdfParams), _P(Image), _P(Image), C.c_void_p],
     "emf_assoc_weights": [C.c_int, _P(Volume), _P(Pose), _P(Image), _P(TsdfParams), _P(Image), C.c_int, _P(Image),
                           C.c_void_p],

@@ -54,6 +54,41 @@ __global__ void __launch_bounds__(256) k_fg_probs(const float2* __restrict__ fgb
     }
 }
 
+// computeFgProbs + inclusive voxel bounds of {fgProb > 0.5} (emf_volume::fg_box).  box must hold
+// (INT_MAX, INT_MAX, INT_MAX, -1, -1, -1) on entry (k_fg_box_init on the same stream).
+__global__ void k_fg_box_init(int32_t* box) {
+    if (threadIdx.x < 3) box[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) box[threadIdx.x] = -1;
+}
+__global__ void __launch_bounds__(256) k_fg_probs_box(const float2* __restrict__ fgbg, int rx, int ry, int rz, float* __restrict__ fg,
+                                                      uint8_t* __restrict__ vol_mask, int32_t* __restrict__ box) {
+    const int64_t n = (int64_t)rx * ry * rz;
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-1, -1, -1};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 p = fgbg[i];
+        const float s = fadd(p.x, p.y);
+        float v = (s != 0.0f) ? fdiv(p.x, s) : 0.0f;   // guarded cv::cuda::divide
+        if (v != v) v = 0.0f;                            // NaN patch (ObjTSDF.cpp:223-224)
+        fg[i] = v;
+        if (vol_mask) vol_mask[i] = (v > 0.5f) ? 255 : 0;
+        if (v > 0.5f) {
+            const int64_t row = i / rx;
+            const int x = (int)(i - row * rx), z = (int)(row / ry), y = (int)(row - (int64_t)z * ry);
+            lo[0] = min(lo[0], x); lo[1] = min(lo[1], y); lo[2] = min(lo[2], z);
+            hi[0] = max(hi[0], x); hi[1] = max(hi[1], y); hi[2] = max(hi[2], z);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+        hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+    }
+    if ((threadIdx.x & 31) == 0 && hi[0] >= 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(box + k, lo[k]); atomicMax(box + 3 + k, hi[k]); }
+    }
+}
+
 }  // namespace emfb
 
 using namespace emfb;
@@ -81,5 +116,15 @@ extern "C" EMF_API int emf_compute_fg_probs(const float* fgbg, int64_t n_voxels,
                                     emf_stream_t stream) {
     if (!fgbg || !fg_probs || n_voxels <= 0) return EMF_ERR_INVALID;
     k_fg_probs<<<grid_for(n_voxels), 256, 0, (cudaStream_t)stream>>>((const float2*)fgbg, n_voxels, fg_probs, fg_vol_mask);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_compute_fg_probs_box(const float* fgbg, const int res[3], float* fg_probs, uint8_t* fg_vol_mask,
+                                        int32_t* fg_box, emf_stream_t stream) {
+    if (!fgbg || !fg_probs || !fg_box || !res_ok(res)) return EMF_ERR_INVALID;
+    const int64_t n = (int64_t)res[0] * res[1] * res[2];
+    k_fg_box_init<<<1, 32, 0, (cudaStream_t)stream>>>(fg_box);
+    k_fg_probs_box<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float2*)fgbg, res[0], res[1], res[2], fg_probs,
+                                                                fg_vol_mask, fg_box);
     return launch_status();
 }

@@ -23,6 +23,7 @@
 //    its ray parameter by the same n fp32 additions in closed form (seq_add.h).
 #include "common.cuh"
 #include "seq_add.h"
+#include <math.h>
 
 namespace emfb {
 
@@ -30,6 +31,7 @@ struct RayVol {
     const float* tsdf;
     const float* weights;
     const float* fg_probs;   // nullable
+    const int32_t* fg_box;   // nullable: inclusive voxel bounds of {fgProb > 0.5} (device memory)
     const float* grads;      // nullable (float3 per voxel)
     const uint8_t* bmap;     // nullable: brick map (bricks.cu), one byte per 8^3 brick
     int nbx, nby;            // bricks per row / rows per slice
@@ -41,6 +43,7 @@ struct RayVol {
     float t[3];
     int rx, ry, rz;
     float voxel, trunc;
+    float thr1[3], thr2[3];  // smallest v with fadd(v, pad) >= R per axis, pad = 1 / 2 (bounds tests without the addition)
     int x0, y0, x1, y1;      // screen rect (exclusive upper)
     int tiles_x;             // tiles per rect row
     int first_block;
@@ -116,8 +119,68 @@ __device__ __forceinline__ void trilinear_grad(const RayVol& V, float vx, float 
         out[k] = s.combine(g[0][k], g[1][k], g[2][k], g[3][k], g[4][k], g[5][k], g[6][k], g[7][k]);
 }
 
+// v < 0 || v + pad >= R on every axis, with the rounded additions folded into per-volume thresholds
+__device__ __forceinline__ bool out_of_thr(float vx, float vy, float vz, const float* thr) {
+    return vx < 0.0f || vx >= thr[0] || vy < 0.0f || vy >= thr[1] || vz < 0.0f || vz >= thr[2];
+}
+
+// march state of one ray
+struct Ray {
+    float tcur, step, f;        // ray parameter, current step, previous sample
+    float vx, vy, vz;           // sample position (voxel coordinates) of tcur
+    float out_t, hvx, hvy, hvz, hmx, hmy, hmz;
+    bool hit;
+};
+struct RayConst {
+    float dx, dy, dz, ox, oy, oz, hxh, hyh, hzh, s, half_s, tmax;
+};
+
+__device__ __forceinline__ void ray_position(Ray& r, const RayConst& c, const ConstDiv& div_s) {
+    r.vx = fadd(c.hxh, div_s(ffma(c.dx, r.tcur, c.ox)));
+    r.vy = fadd(c.hyh, div_s(ffma(c.dy, r.tcur, c.oy)));
+    r.vz = fadd(c.hzh, div_s(ffma(c.dz, r.tcur, c.oz)));
+}
+
+// one march step of the reference algorithm (TSDF.cu:523-572); returns true when the ray is finished
 template <bool STATS>
-__global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__ RayParams P) {
+__device__ __forceinline__ bool march_step(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
+                                           unsigned long long* st) {
+    r.tcur = fadd(r.tcur, r.step);
+    if (!(r.tcur <= c.tmax)) return true;
+    ray_position(r, c, div_s);
+    if (out_of_thr(r.vx, r.vy, r.vz, V.thr2)) return false;
+    const int lx = __float2int_rz(r.vx), ly = __float2int_rz(r.vy), lz = __float2int_rz(r.vz);
+    const float fn = trilinear32(V.tsdf, rx, plane, lx, ly, lz, r.vx, r.vy, r.vz);
+    if (STATS) ++st[0];
+    // back face (TSDF.cu:532): the weight sample is only needed for this test
+    if (r.f < 0.0f && fn > 0.0f) {
+        if (STATS) ++st[3];
+        if (trilinear_weight(V, r.vx, r.vy, r.vz) > 0.0f) return true;
+    }
+    if (fabsf(fn) < 1.0f) r.step = c.s;
+    if (fabsf(fn) < 0.8f) r.step = c.half_s;
+    if (r.f > 0.0f && fn < 0.0f) {   // front face (TSDF.cu:540)
+        const float ts = fsub(r.tcur, fdiv(fmul(r.f, r.step), fsub(fn, r.f)));
+        const float mx = fmul(c.dx, ts), my = fmul(c.dy, ts), mz = fmul(c.dz, ts);
+        const float sx = fadd(c.hxh, div_s(fadd(c.ox, mx)));
+        const float sy = fadd(c.hyh, div_s(fadd(c.oy, my)));
+        const float sz = fadd(c.hzh, div_s(fadd(c.oz, mz)));
+        if (out_of_thr(sx, sy, sz, V.thr2)) return false;   // reference `continue`: f keeps its old value
+        if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
+            r.hit = true; r.out_t = ts;
+            r.hvx = sx; r.hvy = sy; r.hvz = sz; r.hmx = mx; r.hmy = my; r.hmz = mz;
+            return true;
+        }
+    }
+    r.f = fn;
+    return false;
+}
+
+// JUMP = false: every lane marches its own ray (the lean default).
+// JUMP = true : the warp stays in lockstep so that jumps through certified constant regions can be agreed on with warp
+//               collectives (needs emf_volume::brick_map on at least one volume of the launch).
+template <bool STATS, bool JUMP>
+__global__ void __launch_bounds__(kRayThreads, 8) k_raycast(const __grid_constant__ RayParams P) {
     unsigned long long st[4] = {0, 0, 0, 0};
     int lo = 0, hi = P.n_vol - 1;
     const int b = blockIdx.x;
@@ -128,23 +191,22 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
     const RayVol& V = P.v[lo];
     const int lb = b - V.first_block;
     const int ty = lb / V.tiles_x, tx = lb - ty * V.tiles_x;
-    // warp = 8x4 pixel patch inside the 16x8 CTA tile.  Every lane of a warp stays in the march loop until the whole
-    // warp is done (lanes outside the rectangle idle), so that jumps can be agreed on with warp collectives.
+    // warp = 8x4 pixel patch inside the 16x8 CTA tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int xr = V.x0 + tx * kTileW + (warp & 1) * 8 + (lane & 7);
     const int yr = V.y0 + ty * kTileH + (warp >> 1) * 4 + (lane >> 3);
     const bool valid = xr < V.x1 && yr < V.y1;
-    const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);
-    constexpr unsigned kFull = 0xffffffffu;
+    if (!JUMP && !valid) return;
+    const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);   // (JUMP: lanes outside the rectangle idle in the loop)
 
     float* ray_px = (float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x;
     uint8_t* mask_px = V.mask + (size_t)y * V.mask_pitch + x;
-    float out_t = 0.0f;
-    bool hit = false;
-    float hvx = 0.f, hvy = 0.f, hvz = 0.f, hmx = 0.f, hmy = 0.f, hmz = 0.f;
-
-    const float s = V.voxel;
-    const float frx = (float)V.rx, fry = (float)V.ry, frz = (float)V.rz;
+    Ray r;
+    r.out_t = 0.0f; r.hit = false;
+    r.hvx = r.hvy = r.hvz = r.hmx = r.hmy = r.hmz = 0.f;
+    RayConst c;
+    c.s = V.voxel;
+    const float s = c.s;
     const float ux = fdiv(fsub((float)x, P.K[2]), P.K[0]);
     const float uy = fdiv(fsub((float)y, P.K[5]), P.K[4]);
     // rot_CO * (ux, uy, 1)
@@ -152,143 +214,135 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
     const float rayy = fadd(V.R[5], ffma(V.R[3], ux, fmul(V.R[4], uy)));
     const float rayz = fadd(V.R[8], ffma(V.R[6], ux, fmul(V.R[7], uy)));
     const float rn = norm3(rayx, rayy, rayz);
-    const float dx = fdiv(rayx, rn), dy = fdiv(rayy, rn), dz = fdiv(rayz, rn);
+    c.dx = fdiv(rayx, rn); c.dy = fdiv(rayy, rn); c.dz = fdiv(rayz, rn);
     // boxBounds = (volSize - 1) / 2 * voxelSize with INTEGER division (TSDF.cu:490)
     const float bx = fmul((float)((V.rx - 1) / 2), s);
     const float by = fmul((float)((V.ry - 1) / 2), s);
     const float bz = fmul((float)((V.rz - 1) / 2), s);
-    const float ox = V.t[0], oy = V.t[1], oz = V.t[2];
-    const float tin = fmaxf(fmaxf(fdiv(fsub(dx > 0.f ? -bx : bx, ox), dx), fdiv(fsub(dy > 0.f ? -by : by, oy), dy)),
-                            fdiv(fsub(dz > 0.f ? -bz : bz, oz), dz));
-    const float tout = fminf(fminf(fdiv(fsub(dx > 0.f ? bx : -bx, ox), dx), fdiv(fsub(dy > 0.f ? by : -by, oy), dy)),
-                             fdiv(fsub(dz > 0.f ? bz : -bz, oz), dz));
-    float tcur = fadd(s, tin);
-    float tmax = fsub(tout, s);
+    c.ox = V.t[0]; c.oy = V.t[1]; c.oz = V.t[2];
+    const float tin = fmaxf(fmaxf(fdiv(fsub(c.dx > 0.f ? -bx : bx, c.ox), c.dx), fdiv(fsub(c.dy > 0.f ? -by : by, c.oy), c.dy)),
+                            fdiv(fsub(c.dz > 0.f ? -bz : bz, c.oz), c.dz));
+    const float tout = fminf(fminf(fdiv(fsub(c.dx > 0.f ? bx : -bx, c.ox), c.dx), fdiv(fsub(c.dy > 0.f ? by : -by, c.oy), c.dy)),
+                             fdiv(fsub(c.dz > 0.f ? bz : -bz, c.oz), c.dz));
+    r.tcur = fadd(s, tin);
+    c.tmax = fsub(tout, s);
     const float old = (P.write_all || !valid) ? 0.0f : *ray_px;   // in/out far clip (TSDF.cu:496-500)
-    if (old != 0.0f) tmax = fminf(old, tmax);
+    if (old != 0.0f) c.tmax = fminf(old, c.tmax);
 
-    const float hxh = fmul((float)(V.rx - 1), 0.5f), hyh = fmul((float)(V.ry - 1), 0.5f), hzh = fmul((float)(V.rz - 1), 0.5f);
-    const float half_s = fmul(s, 0.5f);
+    c.hxh = fmul((float)(V.rx - 1), 0.5f); c.hyh = fmul((float)(V.ry - 1), 0.5f); c.hzh = fmul((float)(V.rz - 1), 0.5f);
+    c.half_s = fmul(s, 0.5f);
+    bool culled = false;
+    if (V.fg_box) {
+        // ObjTSDF::raycast: a hit needs a positive masked weight, i.e. a corner voxel with fgProb > 0.5.  Both the march
+        // sample and the refined crossing lie on the ray, so a ray can only hit while it is inside the box of those voxels
+        // (padded by 3 voxels against rounding): clip the march there; a ray that misses the box is not marched at all.
+        const float inv_s = 1.0f / s;
+        const float p0[3] = {c.hxh + c.ox * inv_s, c.hyh + c.oy * inv_s, c.hzh + c.oz * inv_s};
+        const float dv[3] = {c.dx * inv_s, c.dy * inv_s, c.dz * inv_s};
+        float ta = -INFINITY, tb = INFINITY;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float lo_k = (float)__ldg(V.fg_box + k) - 4.0f, hi_k = (float)__ldg(V.fg_box + 3 + k) + 4.0f;
+            if (fabsf(dv[k]) > 1e-12f) {
+                const float t0 = (lo_k - p0[k]) / dv[k], t1 = (hi_k - p0[k]) / dv[k];
+                ta = fmaxf(ta, fminf(t0, t1)); tb = fminf(tb, fmaxf(t0, t1));
+            } else if (p0[k] < lo_k || p0[k] > hi_k) {
+                tb = -INFINITY;
+            }
+        }
+        if (__ldg(V.fg_box) > __ldg(V.fg_box + 3) || !(ta <= tb)) culled = true;
+        else c.tmax = fminf(c.tmax, tb);
+    }
     const ConstDiv div_s(s);
     const int rx = V.rx, plane = V.rx * V.ry;
-    const uint8_t* __restrict__ bmap = V.bmap;
-    float step = V.trunc;
-    float vx = 0.f, vy = 0.f, vz = 0.f, f = 0.f;
-    bool done = !valid || tcur >= tmax;
+    r.step = V.trunc;
+    r.vx = r.vy = r.vz = r.f = 0.f;
+    bool done = !valid || culled || r.tcur >= c.tmax;
     if (!done) {
         for (;;) {   // coarse skip (TSDF.cu:509-515)
-            vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
-            vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
-            vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
-            if (out_of(vx, vy, vz, 1.0f, frx, fry, frz) && tcur < tmax) tcur = fadd(step, tcur);
+            ray_position(r, c, div_s);
+            if (out_of_thr(r.vx, r.vy, r.vz, V.thr1) && r.tcur < c.tmax) r.tcur = fadd(r.step, r.tcur);
             else break;
         }
         // still outside => the reference's march loop cannot run (tcur >= tmax): defined as no hit
-        if (!out_of(vx, vy, vz, 1.0f, frx, fry, frz) && vx == vx && vy == vy && vz == vz) {
-            f = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
-            if (fabsf(f) < 1.0f) step = s;
-            if (fabsf(f) < 0.8f) step = half_s;
+        if (!out_of_thr(r.vx, r.vy, r.vz, V.thr1) && r.vx == r.vx && r.vy == r.vy && r.vz == r.vz) {
+            r.f = trilinear(V.tsdf, V.rx, V.ry, r.vx, r.vy, r.vz);
+            if (fabsf(r.f) < 1.0f) r.step = s;
+            if (fabsf(r.f) < 0.8f) r.step = c.half_s;
         } else {
             done = true;
         }
     }
-    // jump geometry: voxels advanced per metre of ray parameter along each axis (and the largest of them)
-    const float ax_m = fdiv(fabsf(dx), s), ay_m = fdiv(fabsf(dy), s), az_m = fdiv(fabsf(dz), s);
-    const float vox_per_m = fmaxf(ax_m, fmaxf(ay_m, az_m));
-    int wait = 0;   // (warp-uniform) march steps to take before the brick map is consulted again after a failed attempt
-    while (!__all_sync(kFull, done)) {
-        // ---- jump: (vx, vy, vz) is the sample position of tcur.  Where the brick map certifies that every sample the next
-        //      n march steps would take returns exactly f, those steps change nothing but tcur.  The warp jumps together
-        //      (n = the smallest count any of its marching rays is certified for) and so stays in lockstep.
-        if (bmap) {
-            const bool isconst = done || f == 1.0f || f == 0.0f || f == -1.0f;
-            if (__all_sync(kFull, isconst)) {
-                if (wait == 0) {
-                    int n = 0x7fffffff;
-                    if (!done) {
-                        n = 0;
-                        if (vx >= 0.0f && vy >= 0.0f && vz >= 0.0f && vx < frx && vy < fry && vz < frz) {
-                            const int bxi = __float2int_rz(vx) >> 3, byi = __float2int_rz(vy) >> 3, bzi = __float2int_rz(vz) >> 3;
-                            const unsigned e = __ldg(bmap + (unsigned)((bzi * V.nby + byi) * V.nbx + bxi));
-                            const unsigned want = f == 1.0f ? 1u : (f == 0.0f ? 2u : 3u);
-                            if ((e >> 4) == want) {
-                                const unsigned D = e & 7u;
-                                const float inv_step = __fdividef(0.999f, step);
-                                float nf = 0.0f;
-                                if (D >= 2u) {
-                                    // every brick within D - 1 bricks holds the constant: any sample whose base voxel moves less
-                                    // than 8 (D - 1) - 1 voxels (Chebyshev) from here is certified
-                                    nf = ((float)((D - 1u) * 8u) - 1.25f) * __fdividef(inv_step, vox_per_m);
-                                } else if (e & 8u) {
-                                    // the 2 x 2 x 2 block of bricks starting at this one holds the constant: certified while the
-                                    // base voxel stays in [8 b, 8 b + 14] on every axis
-                                    const float lox = vx - (float)(bxi << 3), loy = vy - (float)(byi << 3), loz = vz - (float)(bzi << 3);
-                                    const float rx_ = (dx > 0.0f ? 15.0f - lox : lox) - 0.05f;
-                                    const float ry_ = (dy > 0.0f ? 15.0f - loy : loy) - 0.05f;
-                                    const float rz_ = (dz > 0.0f ? 15.0f - loz : loz) - 0.05f;
-                                    nf = fminf(fminf(__fdividef(rx_, fmaxf(ax_m, 1e-12f)), __fdividef(ry_, fmaxf(ay_m, 1e-12f))),
-                                               __fdividef(rz_, fmaxf(az_m, 1e-12f))) * inv_step;
-                                }
-                                n = nf >= 1.0f ? (nf < 4096.0f ? (int)nf : 4096) : 0;
-                            }
-                        }
-                    }
-                    n = __reduce_min_sync(kFull, n);
-                    if (n >= 1) {
+    if (!JUMP) {
+        if (!done)
+            while (!march_step<STATS>(r, c, div_s, V, rx, plane, st)) {}
+    } else {
+        constexpr unsigned kFull = 0xffffffffu;
+        const uint8_t* __restrict__ bmap = V.bmap;
+        const float frx = (float)V.rx, fry = (float)V.ry, frz = (float)V.rz;
+        // jump geometry: voxels advanced per metre of ray parameter along each axis (and the largest of them)
+        const float ax_m = fdiv(fabsf(c.dx), s), ay_m = fdiv(fabsf(c.dy), s), az_m = fdiv(fabsf(c.dz), s);
+        const float vox_per_m = fmaxf(ax_m, fmaxf(ay_m, az_m));
+        int wait = 0;   // (warp-uniform) march steps to take before the brick map is consulted again after a failed attempt
+        while (!__all_sync(kFull, done)) {
+            // ---- jump: (vx, vy, vz) is the sample position of tcur.  Where the brick map certifies that every sample the
+            //      next n march steps would take returns exactly f, those steps change nothing but tcur.  The warp jumps
+            //      together (n = the smallest count any of its marching rays is certified for) and so stays in lockstep.
+            if (bmap) {
+                const bool isconst = done || r.f == 1.0f || r.f == 0.0f || r.f == -1.0f;
+                if (__all_sync(kFull, isconst)) {
+                    if (wait == 0) {
+                        int n = 0x7fffffff;
                         if (!done) {
-                            tcur = emf_seq_add(tcur, step, n);
-                            if (STATS) { st[1] += n; ++st[2]; }
-                            if (!(tcur <= tmax)) {
-                                done = true;                 // the ray ends inside the certified region: no hit
-                            } else {
-                                vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
-                                vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
-                                vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
+                            n = 0;
+                            if (r.vx >= 0.0f && r.vy >= 0.0f && r.vz >= 0.0f && r.vx < frx && r.vy < fry && r.vz < frz) {
+                                const int bxi = __float2int_rz(r.vx) >> 3, byi = __float2int_rz(r.vy) >> 3, bzi = __float2int_rz(r.vz) >> 3;
+                                const unsigned e = __ldg(bmap + (unsigned)((bzi * V.nby + byi) * V.nbx + bxi));
+                                const unsigned want = r.f == 1.0f ? 1u : (r.f == 0.0f ? 2u : 3u);
+                                if ((e >> 4) == want) {
+                                    const unsigned D = e & 7u;
+                                    const float inv_step = __fdividef(0.999f, r.step);
+                                    float nf = 0.0f;
+                                    if (D >= 2u) {
+                                        // every brick within D - 1 bricks holds the constant: any sample whose base voxel moves
+                                        // less than 8 (D - 1) - 1 voxels (Chebyshev) from here is certified
+                                        nf = ((float)((D - 1u) * 8u) - 1.25f) * __fdividef(inv_step, vox_per_m);
+                                    } else if (e & 8u) {
+                                        // the 2 x 2 x 2 block of bricks starting at this one holds the constant: certified while
+                                        // the base voxel stays in [8 b, 8 b + 14] on every axis
+                                        const float lox = r.vx - (float)(bxi << 3), loy = r.vy - (float)(byi << 3), loz = r.vz - (float)(bzi << 3);
+                                        const float rx_ = (c.dx > 0.0f ? 15.0f - lox : lox) - 0.05f;
+                                        const float ry_ = (c.dy > 0.0f ? 15.0f - loy : loy) - 0.05f;
+                                        const float rz_ = (c.dz > 0.0f ? 15.0f - loz : loz) - 0.05f;
+                                        nf = fminf(fminf(__fdividef(rx_, fmaxf(ax_m, 1e-12f)), __fdividef(ry_, fmaxf(ay_m, 1e-12f))),
+                                                   __fdividef(rz_, fmaxf(az_m, 1e-12f))) * inv_step;
+                                    }
+                                    n = nf >= 1.0f ? (nf < 4096.0f ? (int)nf : 4096) : 0;
+                                }
                             }
                         }
-                        continue;
+                        n = __reduce_min_sync(kFull, n);
+                        if (n >= 1) {
+                            if (!done) {
+                                r.tcur = emf_seq_add(r.tcur, r.step, n);
+                                if (STATS) { st[1] += n; ++st[2]; }
+                                if (!(r.tcur <= c.tmax)) done = true;    // the ray ends inside the certified region: no hit
+                                else ray_position(r, c, div_s);
+                            }
+                            continue;
+                        }
+                        wait = 1;
+                    } else {
+                        --wait;
                     }
-                    wait = 1;
-                } else {
-                    --wait;
                 }
             }
+            if (!done) done = march_step<STATS>(r, c, div_s, V, rx, plane, st);
         }
-        if (done) continue;
-        // ---- one march step of the reference algorithm (TSDF.cu:523-572)
-        tcur = fadd(tcur, step);
-        if (!(tcur <= tmax)) { done = true; continue; }
-        vx = fadd(hxh, div_s(ffma(dx, tcur, ox)));
-        vy = fadd(hyh, div_s(ffma(dy, tcur, oy)));
-        vz = fadd(hzh, div_s(ffma(dz, tcur, oz)));
-        if (out_of(vx, vy, vz, 2.0f, frx, fry, frz)) continue;
-        const int lx = __float2int_rz(vx), ly = __float2int_rz(vy), lz = __float2int_rz(vz);
-        const float fn = trilinear32(V.tsdf, rx, plane, lx, ly, lz, vx, vy, vz);
-        if (STATS) ++st[0];
-        // back face (TSDF.cu:532): the weight sample is only needed for this test
-        if (f < 0.0f && fn > 0.0f) {
-            if (STATS) ++st[3];
-            if (trilinear_weight(V, vx, vy, vz) > 0.0f) { done = true; continue; }
-        }
-        if (fabsf(fn) < 1.0f) step = s;
-        if (fabsf(fn) < 0.8f) step = half_s;
-        if (f > 0.0f && fn < 0.0f) {   // front face (TSDF.cu:540)
-            const float ts = fsub(tcur, fdiv(fmul(f, step), fsub(fn, f)));
-            const float mx = fmul(dx, ts), my = fmul(dy, ts), mz = fmul(dz, ts);
-            const float sx = fadd(hxh, div_s(fadd(ox, mx)));
-            const float sy = fadd(hyh, div_s(fadd(oy, my)));
-            const float sz = fadd(hzh, div_s(fadd(oz, mz)));
-            if (out_of(sx, sy, sz, 2.0f, frx, fry, frz)) continue;   // reference `continue`: f keeps its old value
-            if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
-                hit = true; out_t = ts;
-                hvx = sx; hvy = sy; hvz = sz; hmx = mx; hmy = my; hmz = mz;
-                done = true;
-                continue;
-            }
-        }
-        f = fn;
+        if (!valid) return;
     }
-    if (!valid) return;
+    const bool hit = r.hit;
+    const float out_t = r.out_t, hvx = r.hvx, hvy = r.hvy, hvz = r.hvz, hmx = r.hmx, hmy = r.hmy, hmz = r.hmz;
 
     if (hit) {
         float g[3];
@@ -320,6 +374,24 @@ __global__ void __launch_bounds__(kRayThreads) k_raycast(const __grid_constant__
     }
 }
 
+// smallest float v with fl(v + pad) >= R: `v + pad >= R` (reference bounds tests, TSDF.cu:510,526,547) <=> v >= threshold,
+// because rounding is monotone
+static float pad_threshold(int R, float pad) {
+    const float fr = (float)R;
+    float v = fr - pad;
+    for (;;) {
+        const float p = nextafterf(v, -INFINITY);
+        volatile float sum = p + pad;
+        if (sum >= fr) v = p; else break;
+    }
+    for (;;) {   // (and never too low)
+        volatile float sum = v + pad;
+        if (sum >= fr) break;
+        v = nextafterf(v, INFINITY);
+    }
+    return v;
+}
+
 static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const emf_image* ray,
                         const emf_image* vert, const emf_image* norm, const emf_image* mask, const int* rect,
                         int w, int h) {
@@ -328,6 +400,7 @@ static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const
     if (ray->width != w || ray->height != h || !same_size(ray, vert) || !same_size(ray, norm) || !same_size(ray, mask))
         return EMF_ERR_INVALID;
     d.tsdf = v.tsdf; d.weights = v.weights; d.fg_probs = v.fg_probs; d.grads = v.grads;
+    d.fg_box = v.fg_probs ? v.fg_box : nullptr;
     d.bmap = (v.brick_map && v.const_bits && v.res[0] % 4 == 0) ? v.brick_map : nullptr;
     d.nbx = (v.res[0] + 7) / 8; d.nby = (v.res[1] + 7) / 8;
     d.ray = (float*)ray->ptr; d.ray_pitch = ray->pitch;
@@ -338,6 +411,7 @@ static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const
     for (int k = 0; k < 3; ++k) d.t[k] = T.t[k];
     d.rx = v.res[0]; d.ry = v.res[1]; d.rz = v.res[2];
     d.voxel = v.voxel_size; d.trunc = v.truncdist;
+    for (int k = 0; k < 3; ++k) { d.thr1[k] = pad_threshold(v.res[k], 1.0f); d.thr2[k] = pad_threshold(v.res[k], 2.0f); }
     int x0 = 0, y0 = 0, x1 = w, y1 = h;
     if (rect) {
         x0 = rect[0] < 0 ? 0 : rect[0]; y0 = rect[1] < 0 ? 0 : rect[1];
@@ -470,7 +544,7 @@ extern "C" EMF_API int emf_raycast_tsdf(const float* tsdf, const float* grads, c
     for (int k = 0; k < 9; ++k) P.K[k] = K[k];
     P.hit_voxel = hit_voxel; P.write_all = 0; P.stats = nullptr;
     const int blocks = P.v[0].tiles_x * ((h + kTileH - 1) / kTileH);
-    k_raycast<false><<<blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    k_raycast<false, false><<<blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
 }
 
@@ -494,8 +568,16 @@ extern "C" EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, co
     P.n_vol = n_vol; P.w = w; P.h = h;
     for (int k = 0; k < 9; ++k) P.K[k] = K[k];
     P.hit_voxel = nullptr; P.write_all = 1; P.stats = (unsigned long long*)stats;
-    if (stats) k_raycast<true><<<(unsigned)blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
-    else k_raycast<false><<<(unsigned)blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    bool jump = false;
+    for (int i = 0; i < n_vol; ++i) jump = jump || P.v[i].bmap != nullptr;
+    const cudaStream_t cs = (cudaStream_t)stream;
+    if (jump) {
+        if (stats) k_raycast<true, true><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+        else k_raycast<false, true><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+    } else {
+        if (stats) k_raycast<true, false><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+        else k_raycast<false, false><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+    }
     return launch_status();
 }
 

@@ -22,7 +22,7 @@ from .volume import ObjTSDF, Params, TSDF
 
 class EMFusionEngine:
     def __init__(self, params: Params, device="cuda", rank: int = 0, world_size: int = 1, group=None,
-                 materialize_grads: bool = False, accelerate: bool = True):
+                 materialize_grads: bool = False, accelerate: bool = False):
         self.params = params
         self.accelerate = accelerate
         self.device = torch.device(device)

@@ -94,12 +94,13 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def volume(tsdf, weights, res, voxel_size, truncdist, grads=None, fg_probs=None, vid=0, const_bits=None,
-           brick_map=None) -> Volume:
+           brick_map=None, fg_box=None) -> Volume:
     v = Volume()
     v.tsdf = _ptr(tsdf)
     v.weights = _ptr(weights)
     v.grads = _ptr(grads)
     v.fg_probs = _ptr(fg_probs)
+    v.fg_box = _ptr(fg_box)
     v.const_bits = _ptr(const_bits)
     v.brick_map = _ptr(brick_map)
     v.res[:] = [int(r) for r in res]
@@ -156,10 +157,17 @@ def updateFgBgProbs(mask, occluded_mask, tsdfVol, tsdfWeights, fgBgProbs, rel_po
     _count("updateFgBgProbs")
 
 
-def computeFgProbs(fgBgProbs, fgProbs, fgVolMask=None, stream=None):
-    check(_lib.lib().emf_compute_fg_probs(_ptr(fgBgProbs), fgProbs.numel(), _ptr(fgProbs), _ptr(fgVolMask),
-                                          _stream(stream)), "computeFgProbs")
-    _count("computeFgProbs")
+def computeFgProbs(fgBgProbs, fgProbs, fgVolMask=None, stream=None, fgBox=None, volumeRes=None):
+    """fgBox (6 x int32 CUDA tensor, needs volumeRes): also the voxel bounds of {fgProb > 0.5} (raycast cull)."""
+    if fgBox is None:
+        check(_lib.lib().emf_compute_fg_probs(_ptr(fgBgProbs), fgProbs.numel(), _ptr(fgProbs), _ptr(fgVolMask),
+                                              _stream(stream)), "computeFgProbs")
+        _count("computeFgProbs")
+    else:
+        check(_lib.lib().emf_compute_fg_probs_box(_ptr(fgBgProbs), _i3(volumeRes), _ptr(fgProbs), _ptr(fgVolMask),
+                                                  _ptr(fgBox), _stream(stream)), "computeFgProbs")
+        _count("computeFgProbs")
+        _count("computeFgProbs")
 
 
 # ---- level 2 / 3 ----------------------------------------------------------------------------

@@ -66,7 +66,7 @@ class Params:
 
 class TSDF:
     def __init__(self, volumeRes, voxelSize: float, truncdist: float, pose: Affine, params: TSDFParams,
-                 frameSize, device="cuda", materialize_grads: bool = False, accelerate: bool = True):
+                 frameSize, device="cuda", materialize_grads: bool = False, accelerate: bool = False):
         self.params = params
         self.volumeRes = tuple(int(r) for r in volumeRes)
         self.voxelSize = float(np.float32(voxelSize))
@@ -154,9 +154,12 @@ class TSDF:
     def c_volume(self, with_grads: bool = False):
         return ops.volume(self.tsdfVol, self.tsdfWeights, self.volumeRes, self.voxelSize, self.truncdist,
                           grads=self._raycast_grads() if with_grads else None, fg_probs=self._fg(), vid=self.id,
-                          const_bits=self.constBits, brick_map=self.brickMap)
+                          const_bits=self.constBits, brick_map=self.brickMap, fg_box=self._fg_box())
 
     def _fg(self):
+        return None
+
+    def _fg_box(self):
         return None
 
     # -- src/core/TSDF.cpp:125-156
@@ -182,11 +185,13 @@ class ObjTSDF(TSDF):
     nextID = 0   # static counter, incremented only by the constructor (src/core/ObjTSDF.cpp:28,34)
 
     def __init__(self, volumeRes, voxelSize, truncdist, pose, params, frameSize, device="cuda",
-                 materialize_grads: bool = False, accelerate: bool = True):
+                 materialize_grads: bool = False, accelerate: bool = False):
         rx, ry, rz = (int(r) for r in volumeRes)
         dev = torch.device(device)
         self.fgBgProbs = torch.empty((ry * rz, rx, 2), dtype=torch.float32, device=dev)
         self.fgProbs = torch.empty((ry * rz, rx), dtype=torch.float32, device=dev)
+        # voxel bounds of {fgProb > 0.5}: rays that miss them cannot hit (raycast cull; results unchanged)
+        self.fgBox = torch.tensor([1, 1, 1, 0, 0, 0], dtype=torch.int32, device=dev)
         self.classProbs = []
         self.exCount = 1
         self.nonExCount = 0
@@ -209,6 +214,7 @@ class ObjTSDF(TSDF):
         super().reset(pose)
         self.fgBgProbs.zero_()
         self.fgProbs.zero_()
+        self.fgBox.copy_(torch.tensor([1, 1, 1, 0, 0, 0], dtype=torch.int32))   # empty
 
     def getExProb(self) -> float:
         return float(self.exCount) / (self.exCount + self.nonExCount)
@@ -220,6 +226,9 @@ class ObjTSDF(TSDF):
     def _fg(self):
         return self.fgProbs
 
+    def _fg_box(self):
+        return self.fgBox
+
     # -- src/core/ObjTSDF.cpp:167-179
     def integrateMask(self, mask, occluded_mask, cam_pose: Affine, intr, stream=None):
         ops.updateFgBgProbs(mask, occluded_mask, self.tsdfVol, self.tsdfWeights, self.fgBgProbs,
@@ -228,7 +237,7 @@ class ObjTSDF(TSDF):
 
     # -- src/core/ObjTSDF.cpp:218-226
     def computeFgProbs(self, stream=None):
-        ops.computeFgProbs(self.fgBgProbs, self.fgProbs, None, stream)
+        ops.computeFgProbs(self.fgBgProbs, self.fgProbs, None, stream, fgBox=self.fgBox, volumeRes=self.volumeRes)
 
     def getFgProbVol(self) -> np.ndarray:
         return self.fgProbs.cpu().numpy()

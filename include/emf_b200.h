@@ -73,6 +73,10 @@ typedef struct emf_volume {
     float* weights;        /* tsdfWeights  Rx*Ry*Rz floats */
     const float* grads;    /* tsdfGrads (float3 per voxel) or NULL: gradients are then taken on the fly */
     const float* fg_probs; /* fgProbs (objects) or NULL (background) */
+    /* Optional (objects): device array of 6 ints written by emf_compute_fg_probs_box -- inclusive voxel bounds
+     * (x0, y0, z0, x1, y1, z1) of the voxels with fgProb > 0.5 (x0 > x1: none).  A ray of ObjTSDF::raycast can only
+     * hit where the masked weight is positive, so rays that miss this box are not marched.  NULL = off. */
+    const int32_t* fg_box;
     /* Optional acceleration state (no reference counterpart; results are unchanged).  NULL = off.
      * const_bits: three consecutive bitmaps -- a 4-voxel x-segment is all +1 / all 0 / all -1 -- one bit per
      *   segment, rows padded to whole 32-bit words: words per map = emf_bitmap_words_per_row(Rx) * Ry * Rz.
@@ -137,6 +141,11 @@ EMF_API int emf_update_fgbg_probs(const emf_image* mask, const emf_image* occlud
  * fg_vol_mask (u8, 255 where fgProb > 0.5) may be NULL. */
 EMF_API int emf_compute_fg_probs(const float* fgbg, int64_t n_voxels, float* fg_probs, uint8_t* fg_vol_mask,
                          emf_stream_t stream);
+
+/* emf_compute_fg_probs plus the bounding box of the foreground voxels (emf_volume::fg_box), one launch.
+ * fg_box: 6 ints on the device, fully rewritten. */
+EMF_API int emf_compute_fg_probs_box(const float* fgbg, const int res[3], float* fg_probs, uint8_t* fg_vol_mask,
+                             int32_t* fg_box, emf_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Level 2: class-surface operations (one call = one reference method).
