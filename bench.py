@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--brick-maps", action="store_true",
+                    help="maintain constant-brick maps and let the raycast jump through them (bit-identical results)")
     ap.add_argument("--materialize-grads", action="store_true",
                     help="also materialise the float3 gradient volumes every frame (reference behaviour)")
     return ap.parse_args()
@@ -167,7 +169,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from emfusion_b200 import ops
-    from emfusion_b200.engine import EMFusionEngine
+    from emfusion_b200.native import NativeEngine
+    from emfusion_b200.poses import rel_pose_OC
     from emfusion_b200.synth import Scene
     from emfusion_b200.volume import ObjTSDF, Params
 
@@ -183,7 +186,8 @@ def run_ours(args):
     prm = Params(frameSize=(w, h), intr=scene.K, globalVolumeDims=(bg,) * 3, globalVoxelSize=5.12 / bg,
                  objVolumeDims=(ob,) * 3)
     ObjTSDF.nextID = 0
-    eng = EMFusionEngine(prm, dev, rank=rank, world_size=world, materialize_grads=args.materialize_grads)
+    eng = NativeEngine(prm, dev, rank=rank, world_size=world, materialize_grads=args.materialize_grads,
+                       accelerate=args.brick_maps)
     for i in range(k):
         eng.add_object(scene.object_pose(i, 0), scene.object_voxel_size(i, ob))
     frames = render_stream(scene, N_STREAM_FRAMES)
@@ -205,51 +209,38 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step(f, stage_events=None):
+    def step(f, depth=None, timed=False):
+        """one frame through the public API: points, association, raycast + composite, integrate"""
         i = f % N_STREAM_FRAMES
-        eng.pose = cams[i]
-        for o in eng.objects:
-            o.pose = oposes[i][o.id]
-        eng.set_depth(d_dev[i])
-        if stage_events is not None:
-            stage_events[0].record()
-        eng.computeAssociationWeights()
-        if stage_events is not None:
-            stage_events[1].record()
-        eng.raycast()
-        if stage_events is not None:
-            stage_events[2].record()
-        eng.integrateDepth()
-        if stage_events is not None:
-            stage_events[3].record()
+        eng.processFrame(d_dev[i] if depth is None else depth, cams[i], oposes[i], timed=timed)
 
     f = 1
     for _ in range(max(args.warmup, 3)):
         step(f); f += 1
-    # ---- timed: K frames, device time, max over ranks
+    # ---- timed: EXACTLY K frames back to back, device time between two events, max over ranks
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ops.launches_total()
     barrier()
     start.record()
     for s in range(args.steps):
-        step(f, ev[s]); f += 1
+        step(f); f += 1
     stop.record()
     barrier()
     launches = ops.launches_total() - l0
     clocks = sampler.stop() if sampler else None
-    ms_total = start.elapsed_time(stop)
-    stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev])   # assoc, raycast, integrate
-    ms_stage = stage.mean(0)
-    ms_hot = float(stage.sum(1).mean())
-    t = torch.tensor([ms_total, ms_hot, *ms_stage.tolist()], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_hot = float(t[0]), float(t[1])
-    ms_stage = t[2:].cpu().numpy()
+    ms_step = start.elapsed_time(stop) / args.steps
 
-    # ---- e2e: host depth in (pinned), composited result out, every step, through the public API
+    # ---- stage breakdown (separate pass, one device sync per frame to read the engine's stage events)
+    n_stage = min(args.steps, 10)
+    stage = np.zeros((n_stage, 3))
+    if world == 1:
+        for s in range(n_stage):
+            step(f, timed=True); f += 1
+            stage[s] = eng.stage_ms()
+    ms_stage = stage.mean(0)
+
+    # ---- e2e: host depth in (pinned), composited result out, every step, through the same public API
     seg_host = torch.empty((h, w), dtype=torch.uint8).pin_memory()
     ray_host = torch.empty((h, w), dtype=torch.float32).pin_memory()
     d_in = torch.empty((h, w), dtype=torch.float32, device=dev)
@@ -257,46 +248,65 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
-        i = f % N_STREAM_FRAMES
-        d_in.copy_(d_pin[i], non_blocking=True)
-        d_dev_saved = d_dev[i]
-        d_dev[i] = d_in
-        step(f); f += 1
-        d_dev[i] = d_dev_saved
+        d_in.copy_(d_pin[f % N_STREAM_FRAMES], non_blocking=True)
+        step(f, depth=d_in); f += 1
         if rank == 0:
             seg_host.copy_(eng.modelSegmentation, non_blocking=True)
             ray_host.copy_(eng.raylengths, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t2[0]) / args.steps
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e = float(t[0]), float(t[1])
 
     nvox = total_voxels(args.config)
     if rank == 0:
         peak, peak_src = peaks()
-        # dominant kernel: k_integrate; algorithmic bytes = 16 B/voxel x voxels of the volumes it integrated
-        int_vox = bg ** 3 + sum(ob ** 3 for o in eng.objects if o.id in eng.vis_objs) if world == 1 else None
-        achieved = (16.0 * int_vox / (ms_stage[2] * 1e-3) / 1e9) if int_vox else None
+        roof = {"bound": "hbm", "kernel": "k_integrate_rows", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": peak_src}
+        if world == 1:
+            # algorithmic bytes of the integrate launch: 16 B/voxel x the voxels of the volumes it integrated (upper-bound
+            # convention); next to it the exact bytes from the kernel's own counters (separate untimed launch)
+            vis = eng.vis_objs
+            vols = [v for v in eng.local_volumes() if v.id == 0 or v.id in vis]
+            int_vox = sum(v.numVoxels() for v in vols)
+            st = torch.zeros(8, dtype=torch.int64, device=dev)
+            i = f % N_STREAM_FRAMES
+            scratch = [(v.tsdfVol.clone(), v.tsdfWeights.clone()) for v in vols]
+            cv = [ops.volume(t_, w_, v.volumeRes, v.voxelSize, v.truncdist, vid=v.id) for v, (t_, w_) in zip(vols, scratch)]
+            ops.integrateVolumes(cv, [rel_pose_OC(cams[i], v.pose) for v in vols], prm.intr, d_dev[i],
+                                 eng._assoc_images(vols), 64.0, stats=st)
+            c = st.cpu().numpy()
+            exact = 16.0 * c[0] + 8.0 * c[1] + 4.0 * (c[2] + c[3])
+            sec = ms_stage[2] * 1e-3
+            roof.update({"achieved": 16.0 * int_vox / sec / 1e9, "frac": 16.0 * int_vox / sec / 1e9 / peak,
+                         "algorithmic_bytes": 16.0 * int_vox, "kernel_ms": float(ms_stage[2]),
+                         "exact_bytes": float(exact), "achieved_exact": float(exact) / sec / 1e9,
+                         "frac_exact": float(exact) / sec / 1e9 / peak,
+                         "convention": "achieved = 16 B/voxel x every voxel of the integrated volumes (upper bound: voxels outside "
+                                       "the frustum move 0 B, so frac can exceed 1); *_exact = bytes the kernel really has to move "
+                                       "(16 B updated, 8 B newly-occluded, 4 B weight-only), from its own counters",
+                         "counters": {"updated": int(c[0]), "marked_occluded": int(c[1]), "occluded_seen": int(c[2]),
+                                      "check_only": int(c[3]), "outside_image_in_interval": int(c[4])}})
+            del scratch
         out = {
-            "metric": "Mvoxels/s (integrate+raycast+assoc)", "value": nvox / (ms_hot * 1e-3) / 1e6, "unit": "Mvoxels/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_hot,
+            "metric": "Mvoxels/s (integrate+raycast+assoc)", "value": nvox / (ms_step * 1e-3) / 1e6, "unit": "Mvoxels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "voxels_per_frame": nvox, "l2_policy": "working set (1.5 GB/frame) > L2 (126 MB)",
+            "config": {"workload": name, "voxels_per_frame": nvox, "l2_policy": "working set (>1 GB/frame) > L2 (126 MB)",
+                       "step": "one frame = computePoints + association + raycast/composite + integrate, K frames back to back",
                        "parallelism": f"objects sharded over {world} GPU(s), background on GPU 0",
                        "gradients": "materialised per frame" if args.materialize_grads else "on the fly (no float3 volume)",
-                       "visible_objects": len(eng.vis_objs)},
+                       "brick_maps": bool(args.brick_maps), "visible_objects": len(eng.vis_objs)},
             "stages_ms": {"association": float(ms_stage[0]), "raycast+composite": float(ms_stage[1]),
-                          "integrate": float(ms_stage[2]), "frame_incl_points_and_host": ms_total / args.steps},
+                          "integrate": float(ms_stage[2])} if world == 1 else None,
             "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h * w * 4, "d2h_bytes_per_step": h * w * 5},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_integrate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                         "convention": "16 B/voxel x every voxel of the integrated volumes (upper bound; out-of-frustum voxels move 0 B)"},
+            "roofline": roof,
         }
         if not args.no_cpu_baseline and world == 1:
             try:
@@ -387,15 +397,25 @@ def run_reference(args):
     for _ in range(max(args.warmup, 3)):
         step(f); f += 1
     sampler = ClockSampler(0)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    # timed: EXACTLY K frames back to back between two events (every reference frame ends in a host barrier, as in
+    # src/core/EMFusion.cpp:886-888, so this is also its wall time)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    start.record()
     for s in range(args.steps):
-        step(f, ev[s]); f += 1
+        step(f); f += 1
+    stop.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
+    ms_hot = start.elapsed_time(stop) / args.steps
+    # stage breakdown, separate pass
+    n_stage = min(args.steps, 10)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_stage)]
+    for s in range(n_stage):
+        step(f, ev[s]); f += 1
+    torch.cuda.synchronize()
     stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in ev])
     ms_stage = stage.mean(0)
-    ms_hot = float(stage.sum(1).mean())
     # e2e: host depth in, composited segmentation + raylengths out
     seg_host = torch.empty((h, w), dtype=torch.uint8).pin_memory()
     ray_host = torch.empty((h, w), dtype=torch.float32).pin_memory()
@@ -414,6 +434,7 @@ def run_reference(args):
            "unit": "Mvoxels/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_hot,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": name, "voxels_per_frame": nvox, "visible_objects": n_vis,
+                      "step": "one frame = computePoints + association + raycast/composite + integrate (+ gradients), K frames back to back",
                       "what": "reference CUDA kernels (src/core/cuda/*.cu compiled unchanged, sm_100a) + restated OpenCV-CUDA "
                               "element-wise launches, per-volume streams and host barriers as in src/core/EMFusion.cpp"},
            "stages_ms": {"association": float(ms_stage[0]), "raycast+composite": float(ms_stage[1]), "integrate+gradients": float(ms_stage[2])},

@@ -41,8 +41,20 @@ class Volume(C.Structure):
                 ("const_bits", C.c_void_p), ("brick_map", C.c_void_p), ("res", C.c_int * 3), ("voxel_size", C.c_float), ("truncdist", C.c_float), ("id", C.c_int)]
 
 
+class EngineConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("K", C.c_float * 9), ("params", TsdfParams),
+                ("boundary", C.c_int), ("visibility_thresh", C.c_int)]
+
+
 _P = C.POINTER
 _SIGS = {
+    "emf_fill_image_f32": [_P(Image), C.c_float, C.c_void_p],
+    "emf_engine_set_volumes": [C.c_void_p, C.c_int, _P(Volume), C.c_int, C.c_void_p],
+    "emf_engine_frame": [C.c_void_p, _P(Image), _P(Pose), _P(Pose), C.c_uint, C.c_void_p],
+    "emf_engine_stage_ms": [C.c_void_p, _P(C.c_float)],
+    "emf_engine_image": [C.c_void_p, C.c_int, C.c_int, _P(Image)],
+    "emf_engine_vis_counts": [C.c_void_p, _P(C.c_int32), C.c_int],
+    "emf_engine_force_integrate": [C.c_void_p, C.c_int],
     "emf_compute_points": [_P(Image), _P(Image), _P(C.c_float), C.c_void_p],
     "emf_update_tsdf": [_P(Image), _P(Image), C.c_void_p, C.c_void_p, _P(Pose), _P(C.c_float), _P(C.c_int),
                         C.c_float, C.c_float, C.c_float, C.c_void_p],
@@ -71,7 +83,8 @@ _SIGS = {
     "emf_reset_bitmaps": [_P(Volume), C.c_void_p],
     "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],
 }
-EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes"])
+EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes", "emf_engine_create", "emf_engine_destroy",
+                                "emf_engine_vis_counts_device"])
 
 _lib = None
 
@@ -92,6 +105,12 @@ def lib() -> C.CDLL:
             fn.restype = C.c_int
         L.emf_brick_map_bytes.argtypes = [_P(C.c_int)]
         L.emf_brick_map_bytes.restype = C.c_size_t
+        L.emf_engine_create.argtypes = [_P(EngineConfig)]
+        L.emf_engine_create.restype = C.c_void_p
+        L.emf_engine_destroy.argtypes = [C.c_void_p]
+        L.emf_engine_destroy.restype = None
+        L.emf_engine_vis_counts_device.argtypes = [C.c_void_p]
+        L.emf_engine_vis_counts_device.restype = C.c_void_p
         L.emf_version.restype = C.c_char_p
         L.emf_version.argtypes = []
         _lib = L

@@ -148,6 +148,12 @@ __global__ void __launch_bounds__(256) k_points(Img<const float> depth, Img<floa
     p[2] = d;
 }
 
+__global__ void __launch_bounds__(256) k_fill_f32(Img<float> im, float v) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < im.w && y < im.h) im.at(y, x) = v;
+}
+
 static int fill_assoc_vol(AssocVol& d, const emf_volume& v, const emf_pose& T, const emf_image* out,
                           const emf_image* mask_out, const emf_tsdf_params& prm, int w, int h) {
     if (!v.tsdf || !res_ok(v.res) || !image_ok(out, 4) || out->width != w || out->height != h) return EMF_ERR_INVALID;
@@ -246,5 +252,12 @@ extern "C" EMF_API int emf_compute_points(const emf_image* depth, const emf_imag
     const dim3 grid((depth->width + 31) / 32, (depth->height + 7) / 8);
     k_points<<<grid, 256, 0, (cudaStream_t)stream>>>(view<const float>(depth), view<float>(points), K[0], K[4], K[2],
                                                      K[5]);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_fill_image_f32(const emf_image* img, float value, emf_stream_t stream) {
+    if (!image_ok(img, 4)) return EMF_ERR_INVALID;
+    const dim3 grid((img->width + 31) / 32, (img->height + 7) / 8);
+    k_fill_f32<<<grid, 256, 0, (cudaStream_t)stream>>>(view<float>(img), value);
     return launch_status();
 }

@@ -1,0 +1,263 @@
+// engine.cu -- native frame engine: the three hot methods of emf::EMFusion as ONE host call per frame.
+//
+//   EMFusion::computeAssociationWeights   reference src/core/EMFusion.cpp:635-670
+//   EMFusion::raycast (+ composite)       reference src/core/EMFusion.cpp:726-795
+//   EMFusion::integrateDepth              reference src/core/EMFusion.cpp:865-889
+//
+// The reference drives these with ~2 300 launches, K+1 streams and four host barriers per frame (32 objects).
+// Here a frame is: computePoints, association (all volumes, normaliser fused), raycast (all volumes), composite,
+// integrate (all volumes, visibility-gated ON THE DEVICE by the composite's counters) -- five launches on one stream,
+// no device->host read on the path (visibility counts are copied out asynchronously for the caller's bookkeeping).
+//
+// The engine owns only per-frame image scratch (points, per-volume raycast / association images, composite outputs,
+// counters); the volumes stay caller-owned (emf_volume descriptors).  Host code only: every kernel is reached through
+// the level-3 entry points of emf_b200.h.
+#include "common.cuh"
+#include <algorithm>
+#include <new>
+#include <vector>
+
+struct emf_engine {
+    emf_engine_config cfg;
+    int n_vol = 0, has_bg = 0;
+    std::vector<emf_volume> vols;
+    std::vector<int> ids, gates;
+    std::vector<char> force;          // integrate this volume once regardless of its visibility counter (new objects)
+    std::vector<int> rects;
+    // device scratch (one allocation)
+    char* pool = nullptr;
+    size_t pool_bytes = 0;
+    emf_image points{}, norm{}, ray{}, vert{}, nrm{}, seg{}, zero_f{}, zero_f3{}, zero_u8{};
+    std::vector<emf_image> a_img, v_ray, v_vert, v_norm, v_mask;
+    int32_t* vis_count = nullptr;
+    int32_t* vis_host = nullptr;       // pinned
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t vis_ready = nullptr;
+    bool timed_valid = false;
+};
+
+namespace {
+
+size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+    char* base; size_t off;
+    emf_image img(int w, int h, size_t elem) {
+        emf_image i; i.ptr = base ? base + off : nullptr; i.pitch = (size_t)w * elem; i.width = w; i.height = h;
+        off += up256(i.pitch * h);
+        return i;
+    }
+    void* raw(size_t bytes) { void* p = base ? base + off : nullptr; off += up256(bytes); return p; }
+};
+
+void carve(emf_engine* e, char* base, size_t* total) {
+    Carver c{base, 0};
+    const int w = e->cfg.width, h = e->cfg.height, n = e->n_vol;
+    e->points = c.img(w, h, 12); e->norm = c.img(w, h, 4);
+    e->ray = c.img(w, h, 4); e->vert = c.img(w, h, 12); e->nrm = c.img(w, h, 12); e->seg = c.img(w, h, 1);
+    e->zero_f = c.img(w, h, 4); e->zero_f3 = c.img(w, h, 12); e->zero_u8 = c.img(w, h, 1);
+    e->a_img.resize(n); e->v_ray.resize(n); e->v_vert.resize(n); e->v_norm.resize(n); e->v_mask.resize(n);
+    for (int i = 0; i < n; ++i) {
+        e->a_img[i] = c.img(w, h, 4); e->v_ray[i] = c.img(w, h, 4); e->v_vert[i] = c.img(w, h, 12);
+        e->v_norm[i] = c.img(w, h, 12); e->v_mask[i] = c.img(w, h, 1);
+    }
+    e->vis_count = (int32_t*)c.raw(sizeof(int32_t) * EMF_MAX_VOLUMES);
+    *total = c.off;
+}
+
+}  // namespace
+
+extern "C" EMF_API emf_engine* emf_engine_create(const emf_engine_config* cfg) {
+    if (!cfg || cfg->width <= 0 || cfg->height <= 0) return nullptr;
+    emf_engine* e = new (std::nothrow) emf_engine();
+    if (!e) return nullptr;
+    e->cfg = *cfg;
+    bool ok = cudaMallocHost((void**)&e->vis_host, sizeof(int32_t) * EMF_MAX_VOLUMES) == cudaSuccess;
+    for (int k = 0; k < 5 && ok; ++k) ok = cudaEventCreate(&e->ev[k]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->vis_ready, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { emf_engine_destroy(e); return nullptr; }
+    for (int k = 0; k < EMF_MAX_VOLUMES; ++k) e->vis_host[k] = 0;
+    return e;
+}
+
+extern "C" EMF_API void emf_engine_destroy(emf_engine* e) {
+    if (!e) return;
+    if (e->pool) cudaFree(e->pool);
+    if (e->vis_host) cudaFreeHost(e->vis_host);
+    for (int k = 0; k < 5; ++k) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
+    if (e->vis_ready) cudaEventDestroy(e->vis_ready);
+    delete e;
+}
+
+extern "C" EMF_API int emf_engine_set_volumes(emf_engine* e, int n_vol, const emf_volume* vols, int has_background,
+                                      emf_stream_t stream) {
+    if (!e || n_vol < 0 || (n_vol > 0 && !vols)) return EMF_ERR_INVALID;
+    if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
+    const bool realloc = n_vol != e->n_vol || !e->pool;
+    // what the engine held so far: per-volume images survive a change of the volume list (matched by id)
+    const std::vector<emf_volume> old_vols = e->vols;
+    const int old_has_bg = e->has_bg;
+    const std::vector<emf_image> o_a = e->a_img, o_r = e->v_ray, o_v = e->v_vert, o_n = e->v_norm, o_m = e->v_mask;
+    const emf_image o_frame[6] = {e->points, e->norm, e->ray, e->vert, e->nrm, e->seg};
+    char* old_pool = e->pool;
+    e->n_vol = n_vol; e->has_bg = has_background ? 1 : 0;
+    e->vols.assign(vols, vols + n_vol);
+    e->ids.clear(); e->gates.clear();
+    for (int i = 0; i < n_vol; ++i) {
+        const bool bg = e->has_bg && i == 0;
+        if (!bg) e->ids.push_back(vols[i].id);
+        e->gates.push_back(bg ? -1 : (int)e->ids.size() - 1);
+    }
+    e->force.assign(n_vol, 0);
+    e->rects.assign((size_t)4 * (n_vol > 0 ? n_vol : 1), 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (realloc) {
+        size_t total = 0;
+        carve(e, nullptr, &total);
+        char* pool = nullptr;
+        if (cudaMalloc((void**)&pool, total) != cudaSuccess) { e->pool = old_pool; e->vols = old_vols; e->n_vol = (int)old_vols.size(); e->has_bg = old_has_bg; carve(e, old_pool, &total); return EMF_ERR_CUDA; }
+        e->pool = pool; e->pool_bytes = total;
+        carve(e, e->pool, &total);
+        cudaMemsetAsync(e->pool, 0, total, s);
+        const size_t w = e->cfg.width, h = e->cfg.height;
+        if (old_pool) {
+            const emf_image n_frame[6] = {e->points, e->norm, e->ray, e->vert, e->nrm, e->seg};
+            for (int k = 0; k < 6; ++k) cudaMemcpyAsync(n_frame[k].ptr, o_frame[k].ptr, n_frame[k].pitch * h, cudaMemcpyDeviceToDevice, s);
+        }
+        for (int i = 0; i < n_vol; ++i) {
+            const bool bg = e->has_bg && i == 0;
+            int j = -1;
+            for (int k = 0; k < (int)old_vols.size() && old_pool; ++k)
+                if ((old_has_bg && k == 0) == bg && old_vols[k].id == vols[i].id) { j = k; break; }
+            if (j >= 0) {
+                cudaMemcpyAsync(e->a_img[i].ptr, o_a[j].ptr, w * h * 4, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(e->v_ray[i].ptr, o_r[j].ptr, w * h * 4, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(e->v_vert[i].ptr, o_v[j].ptr, w * h * 12, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(e->v_norm[i].ptr, o_n[j].ptr, w * h * 12, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(e->v_mask[i].ptr, o_m[j].ptr, w * h, cudaMemcpyDeviceToDevice, s);
+            } else {
+                // a new volume's association image starts at 1 (reference src/core/EMFusion.cpp:55,916)
+                emf_fill_image_f32(&e->a_img[i], 1.0f, stream);
+            }
+        }
+        if (old_pool) { cudaStreamSynchronize(s); cudaFree(old_pool); }
+    } else {
+        carve(e, e->pool, &e->pool_bytes);
+    }
+    return emfb::launch_status();
+}
+
+extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, const emf_pose* T_co, const emf_pose* T_oc,
+                                unsigned flags, emf_stream_t stream) {
+    if (!e || !e->pool) return EMF_ERR_INVALID;
+    const int n = e->n_vol, w = e->cfg.width, h = e->cfg.height;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool timed = (flags & EMF_FRAME_TIMED) != 0;
+    int rc = EMF_OK;
+    e->timed_valid = false;
+    if (flags & EMF_FRAME_POINTS) {
+        if (!emfb::image_ok(depth, 4) || depth->width != w || depth->height != h) return EMF_ERR_INVALID;
+        rc = emf_compute_points(depth, &e->points, e->cfg.K, stream);
+        if (rc != EMF_OK) return rc;
+    }
+    if (timed) cudaEventRecord(e->ev[0], s);
+    if ((flags & (EMF_FRAME_ASSOC | EMF_FRAME_ASSOC_PARTIAL)) && n > 0) {
+        if (!T_co) return EMF_ERR_INVALID;
+        const int mode = (flags & EMF_FRAME_ASSOC_PARTIAL) ? 1 : 0;
+        rc = emf_assoc_weights(n, e->vols.data(), T_co, &e->points, &e->cfg.params, e->a_img.data(), mode, &e->norm, stream);
+        if (rc != EMF_OK) return rc;
+    } else if ((flags & EMF_FRAME_ASSOC_PARTIAL) && n == 0) {
+        cudaMemsetAsync(e->norm.ptr, 0, e->norm.pitch * h, s);
+    }
+    if ((flags & EMF_FRAME_NORMALISE) && n > 0) {
+        rc = emf_assoc_normalise(n, e->a_img.data(), &e->norm, stream);
+        if (rc != EMF_OK) return rc;
+    }
+    if (timed) cudaEventRecord(e->ev[1], s);
+    if ((flags & EMF_FRAME_RAYCAST) && n > 0) {
+        if (!T_co) return EMF_ERR_INVALID;
+        for (int i = 0; i < n; ++i) {
+            rc = emf_volume_screen_rect(e->vols[i].res, e->vols[i].voxel_size, &T_co[i], e->cfg.K, w, h, &e->rects[4 * i]);
+            if (rc != EMF_OK) return rc;
+        }
+        rc = emf_raycast_volumes(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), e->v_ray.data(), e->v_vert.data(),
+                                 e->v_norm.data(), e->v_mask.data(), nullptr, stream);
+        if (rc != EMF_OK) return rc;
+    }
+    if (flags & EMF_FRAME_COMPOSITE) {
+        // visibility is re-derived by every raycast (vis_objs.clear(), reference src/core/EMFusion.cpp:745): objects
+        // created before it are gated like all others; only objects created after it (:550) are integrated unseen
+        std::fill(e->force.begin(), e->force.end(), (char)0);
+        const int o0 = e->has_bg ? 1 : 0, n_obj = n - o0;
+        const emf_image* bg_ray = e->has_bg ? &e->v_ray[0] : &e->zero_f;
+        const emf_image* bg_vert = e->has_bg ? &e->v_vert[0] : &e->zero_f3;
+        const emf_image* bg_norm = e->has_bg ? &e->v_norm[0] : &e->zero_f3;
+        const emf_image* bg_mask = e->has_bg ? &e->v_mask[0] : &e->zero_u8;
+        rc = emf_raycast_composite(n_obj, e->ids.data(), e->rects.data() + 4 * o0, e->v_ray.data() + o0, e->v_vert.data() + o0,
+                                   e->v_norm.data() + o0, e->v_mask.data() + o0, bg_ray, bg_vert, bg_norm, bg_mask,
+                                   e->cfg.boundary, &e->ray, &e->vert, &e->nrm, &e->seg, e->vis_count, stream);
+        if (rc != EMF_OK) return rc;
+        if (n_obj > 0) {
+            cudaMemcpyAsync(e->vis_host, e->vis_count, sizeof(int32_t) * n_obj, cudaMemcpyDeviceToHost, s);
+            cudaEventRecord(e->vis_ready, s);
+        }
+    }
+    if (timed) cudaEventRecord(e->ev[2], s);
+    if ((flags & EMF_FRAME_INTEGRATE) && n > 0) {
+        if (!T_oc || !emfb::image_ok(depth, 4)) return EMF_ERR_INVALID;
+        const emf_image* assoc = e->a_img.data();
+        const bool gate = (flags & EMF_FRAME_INTEGRATE_ALL) == 0;
+        std::vector<int> g(e->gates);
+        for (int i = 0; i < n; ++i) if (e->force[i]) { g[i] = -1; e->force[i] = 0; }
+        rc = emf_integrate_volumes_gated(n, e->vols.data(), T_oc, e->cfg.K, depth, assoc, e->cfg.params.max_tsdf_weight,
+                                         gate ? e->vis_count : nullptr, gate ? g.data() : nullptr,
+                                         e->cfg.visibility_thresh, nullptr, stream);
+        if (rc != EMF_OK) return rc;
+        rc = emf_update_brick_maps(n, e->vols.data(), stream);
+        if (rc != EMF_OK) return rc;
+    }
+    if (timed) { cudaEventRecord(e->ev[3], s); e->timed_valid = true; }
+    return emfb::launch_status();
+}
+
+extern "C" EMF_API int emf_engine_stage_ms(emf_engine* e, float ms[3]) {
+    if (!e || !ms || !e->timed_valid) return EMF_ERR_INVALID;
+    if (cudaEventSynchronize(e->ev[3]) != cudaSuccess) return EMF_ERR_CUDA;
+    for (int k = 0; k < 3; ++k)
+        if (cudaEventElapsedTime(&ms[k], e->ev[k], e->ev[k + 1]) != cudaSuccess) return EMF_ERR_CUDA;
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_image(emf_engine* e, int what, int index, emf_image* out) {
+    if (!e || !out || !e->pool) return EMF_ERR_INVALID;
+    const bool vi = index >= 0 && index < e->n_vol;
+    switch (what) {
+    case EMF_IMG_POINTS: *out = e->points; return EMF_OK;
+    case EMF_IMG_NORM: *out = e->norm; return EMF_OK;
+    case EMF_IMG_RAY: *out = e->ray; return EMF_OK;
+    case EMF_IMG_VERT: *out = e->vert; return EMF_OK;
+    case EMF_IMG_NORMALS: *out = e->nrm; return EMF_OK;
+    case EMF_IMG_SEG: *out = e->seg; return EMF_OK;
+    case EMF_IMG_VOL_ASSOC: if (!vi) return EMF_ERR_INVALID; *out = e->a_img[index]; return EMF_OK;
+    case EMF_IMG_VOL_RAY: if (!vi) return EMF_ERR_INVALID; *out = e->v_ray[index]; return EMF_OK;
+    case EMF_IMG_VOL_VERT: if (!vi) return EMF_ERR_INVALID; *out = e->v_vert[index]; return EMF_OK;
+    case EMF_IMG_VOL_NORMALS: if (!vi) return EMF_ERR_INVALID; *out = e->v_norm[index]; return EMF_OK;
+    case EMF_IMG_VOL_MASK: if (!vi) return EMF_ERR_INVALID; *out = e->v_mask[index]; return EMF_OK;
+    default: return EMF_ERR_INVALID;
+    }
+}
+
+extern "C" EMF_API int32_t* emf_engine_vis_counts_device(emf_engine* e) { return e ? e->vis_count : nullptr; }
+
+extern "C" EMF_API int emf_engine_vis_counts(emf_engine* e, int32_t* counts_out, int n) {
+    if (!e || !counts_out || n < 0 || n > EMF_MAX_VOLUMES) return EMF_ERR_INVALID;
+    if (cudaEventSynchronize(e->vis_ready) != cudaSuccess) return EMF_ERR_CUDA;
+    for (int k = 0; k < n; ++k) counts_out[k] = e->vis_host[k];
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_force_integrate(emf_engine* e, int vol_index) {
+    if (!e || vol_index < 0 || vol_index >= e->n_vol) return EMF_ERR_INVALID;
+    e->force[vol_index] = 1;
+    return EMF_OK;
+}

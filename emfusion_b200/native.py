@@ -1,0 +1,263 @@
+"""NativeEngine -- the frame-level host mirror on top of the C++ frame engine (csrc/engine.cu, emf_engine_* in
+include/emf_b200.h): one C call per frame (five launches, no device->host read on the path) instead of the
+per-stage Python calls of engine.EMFusionEngine.  Same attribute names as EMFusionEngine (which mirror emf::EMFusion's
+members, reference include/EMFusion/core/EMFusion.h:452-471); the image attributes are torch views of engine-owned
+memory.
+
+Multi-GPU (world_size > 1): objects are sharded round-robin (rank 0 also owns the background); the frame runs in
+three phase groups around the two exchanges of SURVEY.md section 8e -- all-reduce of the per-pixel normaliser, gather
+of the per-rank pre-composited raycast to rank 0 -- both through torch.distributed (NCCL) on the engine's stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import Image, Pose, Volume, check
+from .engine import EMFusionEngine
+from .poses import Affine, rel_pose_arrays
+from .volume import ObjTSDF, Params
+
+# phases (include/emf_b200.h)
+F_POINTS, F_ASSOC, F_ASSOC_PARTIAL, F_NORMALISE, F_RAYCAST, F_COMPOSITE, F_INTEGRATE, F_INTEGRATE_ALL = (
+    0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80)
+F_TIMED = 0x200
+F_ALL = F_POINTS | F_ASSOC | F_RAYCAST | F_COMPOSITE | F_INTEGRATE
+IMG_POINTS, IMG_NORM, IMG_RAY, IMG_VERT, IMG_NORMALS, IMG_SEG = range(6)
+IMG_VOL_ASSOC, IMG_VOL_RAY, IMG_VOL_VERT, IMG_VOL_NORMALS, IMG_VOL_MASK = range(16, 21)
+
+
+class _DevMem:
+    """device memory -> torch tensor without a copy (CUDA array interface)"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class NativeEngine(EMFusionEngine):
+    def __init__(self, params: Params, device="cuda", rank: int = 0, world_size: int = 1, group=None,
+                 materialize_grads: bool = False, accelerate: bool = False):
+        super().__init__(params, device, rank, world_size, group, materialize_grads, accelerate)
+        L = _lib.lib()
+        cfg = _lib.EngineConfig()
+        cfg.width, cfg.height = self.w, self.h
+        cfg.K[:] = np.asarray(params.intr, dtype=np.float32).reshape(9).tolist()
+        cfg.params = params.tsdfParams.c()
+        cfg.boundary = int(params.boundary)
+        cfg.visibility_thresh = int(params.visibilityThresh)
+        self._e = L.emf_engine_create(C.byref(cfg))
+        if not self._e:
+            raise _lib.EmfError("emf_engine_create failed")
+        self._L = L
+        self._dirty = True
+        self._stage = (C.c_float * 3)()
+        self._counts = (C.c_int32 * _lib.EMF_MAX_VOLUMES)()
+        self._sync_volumes()
+
+    def __del__(self):
+        e, self._e = getattr(self, "_e", None), None
+        if e:
+            self._L.emf_engine_destroy(e)
+
+    # ---- volume list -> engine --------------------------------------------------------------------------
+    def add_object(self, obj_pose: Affine, voxelSize: float, volumeRes=None) -> Optional[ObjTSDF]:
+        obj = super().add_object(obj_pose, voxelSize, volumeRes)
+        self._dirty = True
+        self._new_ids = getattr(self, "_new_ids", set())
+        if obj is not None:
+            self._new_ids.add(obj.id)
+        return obj
+
+    def _view(self, what, index, shape, typestr):
+        im = Image()
+        check(self._L.emf_engine_image(self._e, what, index, C.byref(im)), "emf_engine_image")
+        return torch.as_tensor(_DevMem(im.ptr, shape, typestr), device=self.device)
+
+    def _sync_volumes(self):
+        vols = self.local_volumes()
+        arr = (Volume * max(len(vols), 1))()
+        for i, v in enumerate(vols):
+            arr[i] = v.c_volume(with_grads=True)
+        self._keep = vols
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._L.emf_engine_set_volumes(self._e, len(vols), arr, 1 if self.background is not None else 0, s),
+              "emf_engine_set_volumes")
+        h, w = self.h, self.w
+        self.points = self._view(IMG_POINTS, 0, (h, w, 3), "<f4")
+        self.associationNorm = self._view(IMG_NORM, 0, (h, w), "<f4")
+        self.raylengths = self._view(IMG_RAY, 0, (h, w), "<f4")
+        self.vertices = self._view(IMG_VERT, 0, (h, w, 3), "<f4")
+        self.normals = self._view(IMG_NORMALS, 0, (h, w, 3), "<f4")
+        self.modelSegmentation = self._view(IMG_SEG, 0, (h, w), "|u1")
+        self.associationWeights, self.obj_raylengths, self.obj_vertices = {}, {}, {}
+        self.obj_normals, self.obj_modelSegmentation = {}, {}
+        for i, v in enumerate(vols):
+            a = self._view(IMG_VOL_ASSOC, i, (h, w), "<f4")
+            r = self._view(IMG_VOL_RAY, i, (h, w), "<f4")
+            ve = self._view(IMG_VOL_VERT, i, (h, w, 3), "<f4")
+            n = self._view(IMG_VOL_NORMALS, i, (h, w, 3), "<f4")
+            m = self._view(IMG_VOL_MASK, i, (h, w), "|u1")
+            if v.id == 0:
+                self.bg_associationWeights, self.bg_raylengths, self.bg_vertices, self.bg_normals, self.bg_mask = a, r, ve, n, m
+            else:
+                self.associationWeights[v.id], self.obj_raylengths[v.id], self.obj_vertices[v.id] = a, r, ve
+                self.obj_normals[v.id], self.obj_modelSegmentation[v.id] = n, m
+        ptr = self._L.emf_engine_vis_counts_device(self._e)
+        self.vis_count = torch.as_tensor(_DevMem(ptr, (_lib.EMF_MAX_VOLUMES,), "<i4"), device=self.device)
+        for i, v in enumerate(vols):
+            if v.id in getattr(self, "_new_ids", ()):
+                check(self._L.emf_engine_force_integrate(self._e, i), "emf_engine_force_integrate")
+        self._new_ids = set()
+        self._dirty = False
+
+    # ---- one call = some phases of a frame ----------------------------------------------------------------
+    def _frame(self, flags: int, depth: Optional[torch.Tensor] = None):
+        if self._dirty:
+            self._sync_volumes()
+        vols = self._keep
+        T_co, T_oc = rel_pose_arrays(self.pose, [v.pose for v in vols]) if vols else (np.zeros((1, 12), np.float32),) * 2
+        self._T = (T_co, T_oc)     # keep alive until the call returns
+        d = depth if depth is not None else self.depth
+        check(self._L.emf_engine_frame(self._e, C.byref(ops.image(d)), T_co.ctypes.data_as(C.POINTER(Pose)),
+                                       T_oc.ctypes.data_as(C.POINTER(Pose)), int(flags),
+                                       torch.cuda.current_stream(self.device).cuda_stream), "emf_engine_frame")
+        n = len(vols)
+        launches = 0
+        if flags & F_POINTS: launches += 1
+        if flags & (F_ASSOC | F_ASSOC_PARTIAL) and n: launches += 1
+        if flags & F_NORMALISE and n: launches += 1
+        if flags & F_RAYCAST and n: launches += 1
+        if flags & F_COMPOSITE: launches += 1
+        if flags & F_INTEGRATE and n: launches += 1 + (2 if any(v.constBits is not None for v in vols) else 0)
+        ops.LAUNCHES["engineFrame"] = ops.LAUNCHES.get("engineFrame", 0) + launches
+
+    def set_depth(self, depth: torch.Tensor):
+        self.depth = depth
+        self._frame(F_POINTS)
+
+    def computeAssociationWeights(self):
+        if self.world == 1:
+            self._frame(F_ASSOC)
+            return
+        import torch.distributed as dist
+        self._frame(F_ASSOC_PARTIAL)
+        dist.all_reduce(self.associationNorm, op=dist.ReduceOp.SUM, group=self.group)
+        self._frame(F_NORMALISE)
+
+    def raycast(self):
+        if self.world == 1:
+            self._frame(F_RAYCAST | F_COMPOSITE)
+            self._pending_vis = True
+            return
+        # rank 0 composites by hand below (its pre-composite must not contain the background); the other ranks
+        # pre-composite against an empty background inside the engine
+        self._frame(F_RAYCAST if self.rank == 0 else (F_RAYCAST | F_COMPOSITE))
+        self._composite_distributed()
+
+    def _composite_distributed(self):
+        """gather of the per-rank pre-composites to rank 0, merge there in (raylength, list-order) order, visibility
+        from the final segmentation broadcast to every rank's device counters (the integrate gate)"""
+        import torch.distributed as dist
+        h, w, dev = self.h, self.w, self.device
+        if self.rank == 0:
+            objs = self.objects
+            g = self._gather_bufs or {}
+            if not g:
+                z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)
+                g = dict(ray=z(h, w), vert=z(h, w, 3), norm=z(h, w, 3), seg=z(h, w, dt=torch.uint8), zray=z(h, w),
+                         zvert=z(h, w, 3), zmask=z(h, w, dt=torch.uint8), cnt=torch.zeros(96, dtype=torch.int32, device=dev))
+                self._gather_bufs = g
+            rects = self._rects(objs)
+            ops.raycastComposite([o.id for o in objs], rects, [self.obj_raylengths[o.id] for o in objs],
+                                 [self.obj_vertices[o.id] for o in objs], [self.obj_normals[o.id] for o in objs],
+                                 [self.obj_modelSegmentation[o.id] for o in objs], g["zray"], g["zvert"], g["zvert"],
+                                 g["zmask"], self.params.boundary, g["ray"], g["vert"], g["norm"], g["seg"], g["cnt"])
+            src = (g["ray"], g["vert"], g["norm"], g["seg"])
+        else:
+            src = (self.raylengths, self.vertices, self.normals, self.modelSegmentation)
+        packed = torch.cat([src[0].reshape(-1), src[1].reshape(-1), src[2].reshape(-1), src[3].reshape(-1).to(torch.float32)])
+        if self.rank == 0:
+            bufs = [torch.empty_like(packed) for _ in range(self.world)]
+            dist.gather(packed, bufs, dst=0, group=self.group)
+            self._merge_on_root(bufs)
+        else:
+            dist.gather(packed, None, dst=0, group=self.group)
+        n_all = len(self.all_ids)
+        counts = torch.zeros((max(n_all, 1),), dtype=torch.int32, device=dev)
+        if self.rank == 0 and n_all:
+            seg = self.modelSegmentation
+            b = self.params.boundary
+            hist = torch.bincount(seg[b:h - b, b:w - b].reshape(-1).to(torch.int64), minlength=256)
+            ids = torch.tensor([min(i, 255) for i in self.all_ids], device=dev)
+            counts[:n_all] = hist[ids].to(torch.int32)
+        dist.broadcast(counts, src=0, group=self.group)
+        # this rank's objects, in its local list order, gate the integrate on the device
+        local = [self.all_ids.index(o.id) for o in self.objects]
+        if local:
+            self.vis_count[:len(local)] = counts[torch.tensor(local, device=dev)]
+        self._global_counts = counts
+        self._pending_vis = True
+
+    def _resolve_visibility(self):
+        """vis_objs for host-side bookkeeping (reads the asynchronously copied counters; not on the frame's path)"""
+        if not getattr(self, "_pending_vis", False):
+            return
+        self._pending_vis = False
+        if self.world == 1:
+            n = len(self.objects)
+            check(self._L.emf_engine_vis_counts(self._e, self._counts, n), "emf_engine_vis_counts")
+            self._vis_objs = {o.id for o, c in zip(self.objects, self._counts[:n]) if c > self.params.visibilityThresh}
+        else:
+            cs = self._global_counts.cpu().numpy()
+            self._vis_objs = {i for i, c in zip(self.all_ids, cs) if int(c) > self.params.visibilityThresh}
+
+    @property
+    def vis_objs(self):
+        self._resolve_visibility()
+        return self._vis_objs
+
+    @vis_objs.setter
+    def vis_objs(self, v):
+        self._vis_objs = set(v)
+        self._pending_vis = False
+
+    def integrateDepth(self, only_visible: bool = True):
+        self._frame(F_INTEGRATE | (0 if only_visible else F_INTEGRATE_ALL))
+        for v in self._keep:
+            v._grads_dirty = True
+            v.updateGradients()
+
+    def processFrame(self, depth: torch.Tensor, cam_pose: Optional[Affine] = None, obj_poses: Optional[dict] = None,
+                     timed: bool = False):
+        self.depth = depth
+        if cam_pose is not None:
+            self.pose = cam_pose
+        if obj_poses:
+            for o in self.objects:
+                if o.id in obj_poses:
+                    o.pose = obj_poses[o.id]
+        t = F_TIMED if timed else 0
+        if self.frameCount == 0:
+            self._frame(F_POINTS | F_INTEGRATE | F_INTEGRATE_ALL | t)
+        elif self.world == 1:
+            self._frame(F_ALL | t)
+            self._pending_vis = True
+        else:
+            self._frame(F_POINTS)
+            self.computeAssociationWeights()
+            self.raycast()
+            self._frame(F_INTEGRATE)
+        if self.materialize_grads:
+            for v in self._keep:
+                v._grads_dirty = True
+                v.updateGradients()
+        self.frameCount += 1
+
+    def stage_ms(self):
+        """device ms of (association, raycast + composite, integrate) of the last timed frame"""
+        check(self._L.emf_engine_stage_ms(self._e, self._stage), "emf_engine_stage_ms")
+        return [float(x) for x in self._stage]

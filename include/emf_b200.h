@@ -236,6 +236,74 @@ static inline int emf_bitmap_words_per_row(int rx) { return (rx / 4 + 31) / 32; 
 EMF_API int emf_volume_screen_rect(const int res[3], float voxel_size, const emf_pose* T_co, const float K[9],
                            int width, int height, int rect_out[4]);
 
+/* W x H f32 image <- value (the reference's setTo on association images, src/core/EMFusion.cpp:55,916). */
+EMF_API int emf_fill_image_f32(const emf_image* img, float value, emf_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Level 4: the native frame engine -- one host call per frame.
+ *
+ * emf::EMFusion::processFrame's hot part (src/core/EMFusion.cpp:76-103 minus tracking and Mask R-CNN):
+ * computePoints, computeAssociationWeights, raycast (+ composite), integrateDepth, as five launches on one stream
+ * with no device->host read on the path: the visibility filter of integrateDepth (:869-872) is evaluated on the
+ * device from the composite's counters.  The engine owns only image scratch; volumes stay caller-owned.
+ * ------------------------------------------------------------------------- */
+typedef struct emf_engine emf_engine;
+
+typedef struct emf_engine_config {
+    int width, height;          /* Params::frameSize */
+    float K[9];                 /* Params::intr */
+    emf_tsdf_params params;     /* Params::tsdfParams */
+    int boundary;               /* Params::boundary (20) */
+    int visibility_thresh;      /* Params::visibilityThresh (1600) */
+} emf_engine_config;
+
+/* phases of emf_engine_frame (any combination, executed in this order) */
+#define EMF_FRAME_POINTS 0x1u          /* points <- depth */
+#define EMF_FRAME_ASSOC 0x2u           /* association of every volume, normalised (single GPU) */
+#define EMF_FRAME_ASSOC_PARTIAL 0x4u   /* un-normalised weights + their per-pixel sum in EMF_IMG_NORM (multi-GPU, before the all-reduce) */
+#define EMF_FRAME_NORMALISE 0x8u       /* divide by EMF_IMG_NORM (multi-GPU, after the all-reduce) */
+#define EMF_FRAME_RAYCAST 0x10u        /* raycast of every volume */
+#define EMF_FRAME_COMPOSITE 0x20u      /* composite + visibility counters (against an empty background if there is none) */
+#define EMF_FRAME_INTEGRATE 0x40u      /* integrate the background and the visible objects */
+#define EMF_FRAME_INTEGRATE_ALL 0x80u  /* ... every volume regardless of visibility (first frame) */
+#define EMF_FRAME_TIMED 0x200u         /* record stage events for emf_engine_stage_ms */
+#define EMF_FRAME_ALL (EMF_FRAME_POINTS | EMF_FRAME_ASSOC | EMF_FRAME_RAYCAST | EMF_FRAME_COMPOSITE | EMF_FRAME_INTEGRATE)
+
+/* engine-owned images (emf_engine_image) */
+enum {
+    EMF_IMG_POINTS = 0, EMF_IMG_NORM, EMF_IMG_RAY, EMF_IMG_VERT, EMF_IMG_NORMALS, EMF_IMG_SEG,   /* frame level */
+    EMF_IMG_VOL_ASSOC = 16, EMF_IMG_VOL_RAY, EMF_IMG_VOL_VERT, EMF_IMG_VOL_NORMALS, EMF_IMG_VOL_MASK /* per volume (index) */
+};
+
+EMF_API emf_engine* emf_engine_create(const emf_engine_config* cfg);   /* NULL on failure */
+EMF_API void emf_engine_destroy(emf_engine* e);
+
+/* The volumes of the following frames: vols[0] is the background if has_background, objects follow in list order.
+ * Descriptors are copied.  When the count changes the image scratch is reallocated: images of volumes that were
+ * already there (same id) keep their content, a new volume's association image starts at 1 (src/core/EMFusion.cpp:55,916),
+ * everything else at 0. */
+EMF_API int emf_engine_set_volumes(emf_engine* e, int n_vol, const emf_volume* vols, int has_background, emf_stream_t stream);
+
+/* One frame (or some of its phases).  depth: W x H f32 on the device.  T_co[i] = pose_i^-1 * cam_pose,
+ * T_oc[i] = cam_pose^-1 * pose_i for the n_vol volumes (either may be NULL if no phase needs it). */
+EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, const emf_pose* T_co, const emf_pose* T_oc, unsigned flags,
+                     emf_stream_t stream);
+
+/* Device times of {association, raycast + composite, integrate} of the last EMF_FRAME_TIMED frame (waits for it). */
+EMF_API int emf_engine_stage_ms(emf_engine* e, float ms[3]);
+
+/* View of an engine-owned image (valid until the next emf_engine_set_volumes that changes the volume count). */
+EMF_API int emf_engine_image(emf_engine* e, int what, int index, emf_image* out);
+
+/* Visibility counters of the last composite, one per object in list order: on the device (for gating and for the
+ * multi-GPU path to overwrite), and copied to the host (waits for the asynchronous copy only). */
+EMF_API int32_t* emf_engine_vis_counts_device(emf_engine* e);
+EMF_API int emf_engine_vis_counts(emf_engine* e, int32_t* counts_out, int n);
+
+/* Integrate volume vol_index at the next EMF_FRAME_INTEGRATE whatever its visibility counter says (an object created
+ * after the last composite: emf::EMFusion::createObj adds it to vis_objs, src/core/EMFusion.cpp:918). */
+EMF_API int emf_engine_force_integrate(emf_engine* e, int vol_index);
+
 /* Library identification: returns a static string "emf_b200 <version> sm_100a". */
 EMF_API const char* emf_version(void);
 
