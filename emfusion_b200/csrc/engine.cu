@@ -30,6 +30,8 @@ struct emf_engine {
     emf_image points{}, norm{}, ray{}, vert{}, nrm{}, seg{}, zero_f{}, zero_f3{}, zero_u8{};
     std::vector<emf_image> a_img, v_ray, v_vert, v_norm, v_mask;
     int32_t* vis_count = nullptr;
+    void* int_ws = nullptr;            // integrate workspace (depth pyramid)
+    size_t int_ws_bytes = 0;
     int32_t* vis_host = nullptr;       // pinned
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t vis_ready = nullptr;
@@ -62,6 +64,8 @@ void carve(emf_engine* e, char* base, size_t* total) {
         e->v_norm[i] = c.img(w, h, 12); e->v_mask[i] = c.img(w, h, 1);
     }
     e->vis_count = (int32_t*)c.raw(sizeof(int32_t) * EMF_MAX_VOLUMES);
+    e->int_ws_bytes = emf_integrate_workspace_bytes(w, h);
+    e->int_ws = c.raw(e->int_ws_bytes);
     *total = c.off;
 }
 
@@ -209,9 +213,9 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         const bool gate = (flags & EMF_FRAME_INTEGRATE_ALL) == 0;
         std::vector<int> g(e->gates);
         for (int i = 0; i < n; ++i) if (e->force[i]) { g[i] = -1; e->force[i] = 0; }
-        rc = emf_integrate_volumes_gated(n, e->vols.data(), T_oc, e->cfg.K, depth, assoc, e->cfg.params.max_tsdf_weight,
-                                         gate ? e->vis_count : nullptr, gate ? g.data() : nullptr,
-                                         e->cfg.visibility_thresh, nullptr, stream);
+        rc = emf_integrate_volumes_ws(n, e->vols.data(), T_oc, e->cfg.K, depth, assoc, e->cfg.params.max_tsdf_weight,
+                                      gate ? e->vis_count : nullptr, gate ? g.data() : nullptr,
+                                      e->cfg.visibility_thresh, nullptr, e->int_ws, e->int_ws_bytes, stream);
         if (rc != EMF_OK) return rc;
         rc = emf_update_brick_maps(n, e->vols.data(), stream);
         if (rc != EMF_OK) return rc;

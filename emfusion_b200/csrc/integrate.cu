@@ -29,6 +29,8 @@
 
 namespace emfb {
 
+constexpr int kPyrLevels = 6;   // depth pyramid levels 1..6 (tiles of 2..64 pixels)
+
 struct IntVol {
     float* tsdf;
     float* weights;
@@ -58,9 +60,12 @@ struct IntParams {
     int gate_thresh;              // a gated volume is integrated iff gate_counts[gate] > gate_thresh
     unsigned long long* stats;    // nullable: [0] updated [1] marked -1 [2] occluded-seen [3] check-only [4] skipped-in-interval
     float g_rel, g_abs;           // |(|pc| / lambda(pixel)) - pc.z| <= g_rel * pc.z + g_abs (classification guard)
+    const float2* pyr[kPyrLevels + 1];   // depth (min, max) pyramid, level l = tiles of 2^l pixels (k_integrate_seg); [0] unused
+    int pyr_w[kPyrLevels + 1];           // tiles per row of level l
 };
 
 constexpr int kIntThreads = 256;
+constexpr int kSegThreads = 256;
 constexpr int kSimpleThreads = 128;
 constexpr float kMarginPx = 3.0f;    // frustum half-planes are pushed out by this many pixels
 constexpr float kMinDepthCull = 0.02f;   // rows that come closer than this to the camera plane are not culled
@@ -322,6 +327,343 @@ __global__ void __launch_bounds__(kIntThreads, 4) k_integrate_rows(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// depth (min, max) pyramid: level l holds, per tile of 2^l x 2^l pixels, the smallest and the largest depth.
+// A pixel without a measurement (d <= 0 or NaN) poisons its tiles with (0, +inf), so that nothing whose footprint
+// contains it can be classified wholesale.  One CTA reduces one 64 x 64 pixel tile through all levels.
+// ---------------------------------------------------------------------------------------------
+struct PyrParams {
+    const float* depth; size_t pitch; int w, h;
+    float2* lvl[kPyrLevels + 1];
+    int lw[kPyrLevels + 1], lh[kPyrLevels + 1];
+};
+
+__global__ void __launch_bounds__(256) k_depth_pyramid(const __grid_constant__ PyrParams P) {
+    __shared__ float2 s_a[32][33];
+    const int tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 64;
+    const int t = threadIdx.x;
+    // level 1 straight from the image: thread -> 4 of the 32 x 32 level-1 tiles
+    for (int i = t; i < 32 * 32; i += 256) {
+        const int lx = i & 31, ly = i >> 5;
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int x = tx0 + 2 * lx + dx, y = ty0 + 2 * ly + dy;
+                if (x < P.w && y < P.h) {
+                    const float d = __ldg((const float*)((const char*)P.depth + (size_t)y * P.pitch) + x);
+                    if (d > 0.0f) { mn = fminf(mn, d); mx = fmaxf(mx, d); }
+                    else { mn = 0.0f; mx = INFINITY; }
+                }
+            }
+        s_a[ly][lx] = make_float2(mn, mx);
+        const int gx = (tx0 >> 1) + lx, gy = (ty0 >> 1) + ly;
+        if (gx < P.lw[1] && gy < P.lh[1]) P.lvl[1][(size_t)gy * P.lw[1] + gx] = make_float2(mn, mx);
+    }
+    __syncthreads();
+    // levels 2..6 in shared memory (in place: level l occupies the top-left (64 >> l)^2 corner)
+    for (int l = 2; l <= kPyrLevels; ++l) {
+        const int n = 64 >> l;
+        float2 v = make_float2(INFINITY, -INFINITY);
+        const int lx = t % n, ly = t / n;
+        const bool on = t < n * n;
+        if (on) {
+            const float2 a = s_a[2 * ly][2 * lx], b = s_a[2 * ly][2 * lx + 1], c = s_a[2 * ly + 1][2 * lx], d = s_a[2 * ly + 1][2 * lx + 1];
+            v.x = fminf(fminf(a.x, b.x), fminf(c.x, d.x));
+            v.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+        }
+        __syncthreads();
+        if (on) {
+            s_a[ly][lx] = v;
+            const int gx = (tx0 >> l) + lx, gy = (ty0 >> l) + ly;
+            if (gx < P.lw[l] && gy < P.lh[l]) P.lvl[l][(size_t)gy * P.lw[l] + gx] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_integrate_seg: k_integrate_rows with one more level of "decide cheaply, compute exactly only where needed".
+//
+//  * A lane's 4-voxel segment is first classified AS A WHOLE: its two end voxels are projected (approximately), the
+//    depth pyramid gives the smallest and largest measurement over the padded pixel box of the segment (<= 3 x 3
+//    tiles of the level whose tile size exceeds half the box), and if even the farthest voxel is in front of the
+//    nearest measurement by more than the truncation distance plus a guard -- or the nearest voxel behind the
+//    farthest measurement -- all four voxels take the free-space (value +1, weight +1) or occluded branch with
+//    no per-voxel projection at all.  Pinhole cameras only (launcher).
+//  * The segments that cannot be decided wholesale (near surfaces, depth edges, image border, no measurement) are
+//    compacted across the warp: their 4 x n voxels are dealt one per lane, so that the exact per-voxel path -- the
+//    canonical arithmetic of the reference, bit for bit -- runs on full warps instead of a few lanes.
+//  * Result: bit-identical to k_integrate_rows / the reference kernel.
+// ---------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_constant__ IntParams P) {
+    extern __shared__ float s_tab[];   // [0, w): (x - cx) / fx ; [w, w + h): (y - cy) / fy   (exact IEEE quotients)
+    __shared__ uint8_t s_src[kSegThreads / 32][32];
+    for (int i = threadIdx.x; i < P.w + P.h; i += kSegThreads)
+        s_tab[i] = i < P.w ? fdiv(fsub((float)i, P.K[2]), P.K[0]) : fdiv(fsub((float)(i - P.w), P.K[5]), P.K[4]);
+    __syncthreads();
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warps_per_cta = kSegThreads / 32;
+    const int gwarp = blockIdx.x * warps_per_cta + wid;
+    const int n_warps = gridDim.x * warps_per_cta;
+    unsigned long long st[5] = {0, 0, 0, 0, 0};
+    const float fw = (float)P.w, fh = (float)P.h;
+
+    int vi = 0;
+    for (int item = gwarp; item < P.total_items; item += n_warps) {
+        while (vi + 1 < P.n_vol && P.v[vi + 1].first_item <= item) ++vi;   // rows are dealt in ascending order
+        const IntVol& V = P.v[vi];
+        if (V.gate >= 0 && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh)) continue;   // not visible: not integrated
+        const int rx = V.rx, ry = V.ry;
+        const int row = item - V.first_item;          // z * Ry + y
+        const int z = row / ry;
+        const int y = row - z * ry;
+        const float s = V.voxel;
+        const float hx = fmul((float)(rx - 1), 0.5f);
+        const float cy = fmul(fsub((float)y, fmul((float)(ry - 1), 0.5f)), s);
+        const float cz = fmul(fsub((float)z, fmul((float)(V.rz - 1), 0.5f)), s);
+        const float my0 = fmul(V.R[1], cy), my1 = fmul(V.R[4], cy), my2 = fmul(V.R[7], cy);
+
+        // ---- the row as a line in homogeneous pixel coordinates, q(x) = qa + x * qb (plain float math: only used for
+        //      decisions that carry their own safety margins), and the conservative x-interval that can project into the image
+        int xa = 0, xb = rx - 1;
+        float qxa, qxb, qya, qyb, qza, qzb;
+        {
+            const float c0 = -hx * s;
+            const float ax = V.t[0] + (V.R[0] * c0 + my0 + V.R[2] * cz), bx = V.R[0] * s;
+            const float ay = V.t[1] + (V.R[3] * c0 + my1 + V.R[5] * cz), by = V.R[3] * s;
+            const float az = V.t[2] + (V.R[6] * c0 + my2 + V.R[8] * cz), bz = V.R[6] * s;
+            qxa = P.K[0] * ax + P.K[2] * az; qxb = P.K[0] * bx + P.K[2] * bz;
+            qya = P.K[4] * ay + P.K[5] * az; qyb = P.K[4] * by + P.K[5] * bz;
+            qza = az; qzb = bz;
+            const float xe = (float)(rx - 1);
+            const float zmin = fminf(az, az + bz * xe);
+            if (zmin > kMinDepthCull) {   // whole row safely in front of the camera: cull by the four image edges
+                float lo = 0.0f, hi = xe;
+                const float m0 = 0.5f + kMarginPx, mw = fw - 0.5f + kMarginPx, mh = fh - 0.5f + kMarginPx;
+                const float al[4] = {qxa + m0 * qza, mw * qza - qxa, qya + m0 * qza, mh * qza - qya};
+                const float be[4] = {qxb + m0 * qzb, mw * qzb - qxb, qyb + m0 * qzb, mh * qzb - qyb};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (be[k] > 0.0f) lo = fmaxf(lo, __fdividef(-al[k], be[k]) - 0.01f);
+                    else if (be[k] < 0.0f) hi = fminf(hi, __fdividef(-al[k], be[k]) + 0.01f);
+                    else if (al[k] < 0.0f) hi = -1.0f;
+                }
+                if (!(lo <= hi)) continue;
+                xa = max(0, (int)floorf(lo) - 1);
+                xb = min(rx - 1, (int)ceilf(hi) + 1);
+                if (xa > xb) continue;
+            }
+        }
+        xa &= ~127;                     // whole 128-voxel chunks: one bitmap word per warp iteration
+        const int64_t row_off = (int64_t)row * rx;
+        const ConstDiv div_trunc(V.trunc);
+        const float ntrunc = -V.trunc;
+        const float band = V.trunc + P.g_abs;
+
+        for (int xbase = xa; xbase <= xb; xbase += 128) {   // warp-uniform trip count (collectives below)
+            const int x0 = xbase + 4 * lane;
+            const bool active = x0 <= xb && x0 < rx;
+            // ---- phase A: classify the segment as a whole.  0 skip, 1 free, 2 occluded, 3 per voxel
+            int cls = 0;
+            if (active) {
+                cls = 3;
+                const float xf0 = (float)x0, xf3 = (float)(x0 + 3);
+                const float z0 = fmaf(xf0, qzb, qza), z3 = fmaf(xf3, qzb, qza);
+                const float zlo = fminf(z0, z3), zhi = fmaxf(z0, z3);
+                if (zlo > 0.05f) {
+                    const float r0 = rcp_approx(z0), r3 = rcp_approx(z3);
+                    const float u0 = fmaf(xf0, qxb, qxa) * r0, u3 = fmaf(xf3, qxb, qxa) * r3;
+                    const float v0 = fmaf(xf0, qyb, qya) * r0, v3 = fmaf(xf3, qyb, qya) * r3;
+                    // pixel box of the four voxels (the projection of a line segment is monotone in each coordinate),
+                    // padded by one pixel for the rounding to the nearest pixel and the approximations above
+                    const float ulo = fminf(u0, u3) - 1.0f, uhi = fmaxf(u0, u3) + 1.0f;
+                    const float vlo = fminf(v0, v3) - 1.0f, vhi = fmaxf(v0, v3) + 1.0f;
+                    if (uhi < -0.5f || ulo > fw - 0.5f || vhi < -0.5f || vlo > fh - 0.5f) {
+                        cls = 0;   // every voxel projects outside the image: the reference touches nothing
+                    } else if (ulo >= 0.0f && vlo >= 0.0f && uhi <= fw - 1.0f && vhi <= fh - 1.0f) {
+                        const int iu0 = (int)ulo, iv0 = (int)vlo, iu1 = (int)uhi + 1, iv1 = (int)vhi + 1;   // inclusive, inside the image... iu1 <= w - 1 + 1
+                        const int e = max(iu1 - iu0, iv1 - iv0);
+                        const int L = 32 - __clz(e >> 1);      // tile 2^L > e / 2  =>  the box spans at most 3 tiles per axis
+                        if (L <= kPyrLevels) {
+                            const float2* __restrict__ lv = P.pyr[L];
+                            const int pw = P.pyr_w[L];
+                            const int a0 = iu0 >> L, a1 = min(iu1, P.w - 1) >> L, b0 = iv0 >> L, b1 = min(iv1, P.h - 1) >> L;
+                            float dmin = INFINITY, dmax = -INFINITY;
+#pragma unroll
+                            for (int db = 0; db < 3; ++db) {
+                                const float2* rowp = lv + (size_t)min(b0 + db, b1) * pw;
+#pragma unroll
+                                for (int da = 0; da < 3; ++da) {
+                                    const float2 mm = __ldg(rowp + min(a0 + da, a1));
+                                    dmin = fminf(dmin, mm.x); dmax = fmaxf(dmax, mm.y);
+                                }
+                            }
+                            // |pc| / lambda(pixel) is within g_rel * pc.z of pc.z for every voxel (launcher)
+                            if (dmin - zhi > fmaf(zhi, P.g_rel, band)) cls = 1;
+                            else if (zlo - dmax > fmaf(zlo, P.g_rel, band)) cls = 2;
+                        }
+                    }
+                }
+            }
+            // ---- phase B: wholesale segments
+            int known = 0;                 // voxels whose final tsdf value this lane knows
+            float tv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (cls == 1) {
+                float* wp = V.weights + row_off + x0;
+                float* tp = V.tsdf + row_off + x0;
+                const float4 w4 = *reinterpret_cast<const float4*>(wp);
+                const float4 t4 = *reinterpret_cast<const float4*>(tp);
+                float w[4] = {w4.x, w4.y, w4.z, w4.w};
+                tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+                known = 0xF;
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // sdf >= trunc: value +1 with weight 1 (free space is never association-weighted)
+                    const float ws = fadd(w[j], 1.0f);
+                    if (ws > 0.0f) {
+                        const float num = ffma(w[j], tv[j], 1.0f);
+                        tv[j] = (num == ws && ws <= 3.0e38f) ? 1.0f : fdiv(num, ws);
+                        w[j] = fminf(ws, P.max_weight);
+                        any = true;
+                        if (STATS) ++st[0];
+                    }
+                }
+                if (any) {
+                    *reinterpret_cast<float4*>(wp) = make_float4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<float4*>(tp) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+                }
+            } else if (cls == 2) {
+                const float4 w4 = *reinterpret_cast<const float4*>(V.weights + row_off + x0);
+                float* tp = V.tsdf + row_off + x0;
+                const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (w[j] == 0.0f) { tv[j] = -1.0f; known |= 1 << j; if (STATS) ++st[1]; }
+                    else if (STATS) ++st[2];
+                }
+                if (known == 0xF) *reinterpret_cast<float4*>(tp) = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (known & (1 << j)) tp[j] = -1.0f;
+                }
+            }
+            // ---- phase C: the other segments, one voxel per lane
+            const unsigned mixed = __ballot_sync(kFull, cls == 3);
+            uint32_t set_m[3] = {0u, 0u, 0u};      // segments (by owner lane) whose four voxels end up as constant m
+            if (mixed) {
+                if (cls == 3) s_src[wid][__popc(mixed & ((1u << lane) - 1u))] = (uint8_t)lane;
+                __syncwarp();
+                const int ntask = 4 * __popc(mixed);
+                for (int base = 0; base < ntask; base += 32) {
+                    const int k = base + lane;
+                    const bool on = k < ntask;
+                    const int src = on ? s_src[wid][k >> 2] : 0;
+                    const int x = xbase + 4 * src + (k & 3);
+                    float tfin = 2.0f;     // final tsdf of the voxel (2 = not a constant)
+                    if (on) {
+                        float* wp = V.weights + row_off + x;
+                        float* tp = V.tsdf + row_off + x;
+                        const float w = *wp;
+                        float tcur = *tp;
+                        tfin = tcur;
+                        const float cx = fmul(fsub((float)x, hx), s);
+                        const float pcx = fadd(V.t[0], ffma(V.R[2], cz, ffma(V.R[0], cx, my0)));
+                        const float pcy = fadd(V.t[1], ffma(V.R[5], cz, ffma(V.R[3], cx, my1)));
+                        const float pcz = fadd(V.t[2], ffma(V.R[8], cz, ffma(V.R[6], cx, my2)));
+                        if (!(pcz > 0.0f)) {
+                            if (w == 0.0f) { *tp = 0.0f; tfin = 0.0f; }
+                            if (STATS) ++st[3];
+                        } else {
+                            const float qx = ffma(P.K[2], pcz, fmul(P.K[0], pcx));
+                            const float qy = ffma(P.K[5], pcz, fmul(P.K[4], pcy));
+                            const float rz = rcp_approx(pcz);
+                            const int px = round_quotient(qx, pcz, rz);
+                            const int py = round_quotient(qy, pcz, rz);
+                            if ((unsigned)px >= (unsigned)P.w || (unsigned)py >= (unsigned)P.h) {
+                                if (STATS) ++st[4];
+                            } else {
+                                const float d = __ldg((const float*)((const char*)P.depth + (size_t)py * P.depth_pitch) + px);
+                                if (!(d > 0.0f)) {
+                                    if (w == 0.0f) { *tp = 0.0f; tfin = 0.0f; }
+                                    if (STATS) ++st[3];
+                                } else {
+                                    const float lx = s_tab[px], ly = s_tab[P.w + py];
+                                    const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
+                                    const float inv_lambda = frcp(lambda);
+                                    const float nrm = norm3(pcx, pcy, pcz);
+                                    const float sdf = ffma(-nrm, inv_lambda, d);   // depth - (1/lambda)*|pc| as one FFMA (reference SASS)
+                                    if (sdf >= ntrunc) {
+                                        const float q = div_trunc(sdf);
+                                        const float val = copysignf(fminf(1.0f, fabsf(q)), sdf);
+                                        float a = 1.0f;
+                                        if (sdf < V.trunc)
+                                            a = __ldg((const float*)((const char*)V.assoc + (size_t)py * V.assoc_pitch) + px);
+                                        const float ws = fadd(w, a);
+                                        if (ws > 0.0f) {
+                                            tcur = fdiv(ffma(w, tcur, fmul(val, a)), ws);
+                                            *tp = tcur; *wp = fminf(ws, P.max_weight);
+                                            tfin = tcur;
+                                            if (STATS) ++st[0];
+                                        }
+                                    } else if (w == 0.0f) {
+                                        *tp = -1.0f; tfin = -1.0f;
+                                        if (STATS) ++st[1];
+                                    } else if (STATS) ++st[2];
+                                }
+                            }
+                        }
+                    }
+                    if (V.const_bits) {   // the four voxels of a segment sit in four consecutive lanes
+                        int c = on ? value_code(tfin) : kMixed;
+                        const int c1 = __shfl_xor_sync(kFull, c, 1); c = (c == c1) ? c : kMixed;
+                        const int c2 = __shfl_xor_sync(kFull, c, 2); c = (c == c2) ? c : kMixed;
+#pragma unroll
+                        for (int m = 1; m <= 3; ++m)
+                            set_m[m - 1] |= __reduce_or_sync(kFull, (on && (lane & 3) == 0 && c == m) ? (1u << src) : 0u);
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- constant-segment bitmaps: one bit per 4-voxel segment in each of three maps (all +1 / all 0 / all -1).
+            //      A word covers this warp's 128-voxel chunk, so it has one owner.
+            if (V.const_bits && __any_sync(kFull, cls != 0)) {
+                int code = -1;    // common code of the values this lane knows; kMixed if they differ or are not constants
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (known & (1 << j)) {
+                        const int c = value_code(tv[j]);
+                        code = (code == -1 || code == c) ? c : kMixed;
+                    }
+                const bool full = (known == 0xF);
+                const size_t word = (size_t)row * V.wpr + (xbase >> 7);
+#pragma unroll
+                for (int m = 1; m <= 3; ++m) {
+                    const uint32_t set = __ballot_sync(kFull, cls != 3 && full && code == m) | set_m[m - 1];
+                    // a partially known segment keeps its old bit only if what was seen agrees with it
+                    const uint32_t keep = __ballot_sync(kFull, cls != 3 && !full && (code == -1 || code == m));
+                    if (lane == m - 1) {
+                        uint32_t* wp32 = V.const_bits + (size_t)(m - 1) * V.map_words + word;
+                        *wp32 = keep ? (set | (*wp32 & keep)) : set;
+                    }
+                }
+            }
+        }
+    }
+    if (STATS && P.stats) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long v = st[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (lane == 0 && v) atomicAdd(P.stats + k, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // any resolution / alignment: one thread per voxel, straight canonical arithmetic
 // ---------------------------------------------------------------------------------------------
 template <bool PINHOLE>
@@ -394,9 +736,21 @@ static int sm_count() {
     return g_sm_count;
 }
 
+size_t pyramid_layout(int w, int h, size_t off[kPyrLevels + 1], int lw[kPyrLevels + 1], int lh[kPyrLevels + 1]) {
+    size_t total = 0;
+    off[0] = 0; lw[0] = w; lh[0] = h;
+    for (int l = 1; l <= kPyrLevels; ++l) {
+        lw[l] = (w + (1 << l) - 1) >> l; lh[l] = (h + (1 << l) - 1) >> l;
+        off[l] = total;
+        total += (((size_t)lw[l] * lh[l] * sizeof(float2)) + 255) & ~(size_t)255;
+    }
+    return total;
+}
+
 int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float* K, const emf_image* depth,
                      const emf_image* assoc, float max_weight, const int32_t* gate_counts, const int* gates,
-                     int gate_thresh, unsigned long long* stats, cudaStream_t stream) {
+                     int gate_thresh, unsigned long long* stats, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
     if (n_vol <= 0 || !vols || !T_oc || !K || !assoc) return EMF_ERR_INVALID;
     if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
     if (!image_ok(depth, 4)) return EMF_ERR_INVALID;
@@ -448,6 +802,36 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
     const size_t tab_bytes = (size_t)(P.w + P.h) * sizeof(float);
     const bool table = tab_bytes <= 40 * 1024;
     const size_t smem = table ? tab_bytes : 0;
+    // ---- segment-level path: needs the depth pyramid workspace, a plain pinhole camera and the pixel-ray table
+    {
+        size_t off[kPyrLevels + 1]; int lw[kPyrLevels + 1], lh[kPyrLevels + 1];
+        const size_t need = pyramid_layout(P.w, P.h, off, lw, lh);
+        if (workspace && workspace_bytes >= need && pin && table && ((uintptr_t)workspace & 15) == 0) {
+            PyrParams Q;
+            Q.depth = P.depth; Q.pitch = P.depth_pitch; Q.w = P.w; Q.h = P.h;
+            P.pyr[0] = nullptr; P.pyr_w[0] = 0; Q.lvl[0] = nullptr; Q.lw[0] = 0; Q.lh[0] = 0;
+            for (int l = 1; l <= kPyrLevels; ++l) {
+                Q.lvl[l] = (float2*)((char*)workspace + off[l]); Q.lw[l] = lw[l]; Q.lh[l] = lh[l];
+                P.pyr[l] = Q.lvl[l]; P.pyr_w[l] = lw[l];
+            }
+            const dim3 pgrid((P.w + 63) / 64, (P.h + 63) / 64);
+            k_depth_pyramid<<<pgrid, 256, 0, stream>>>(Q);
+            static int occ_s = 0, occ_n = 0;
+            int& occ = stats ? occ_s : occ_n;
+            if (occ == 0) {
+                if (stats) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_seg<true>, kSegThreads, smem);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_seg<false>, kSegThreads, smem);
+                if (occ <= 0) occ = 2;
+            }
+            int64_t blocks = (int64_t)sm_count() * occ;
+            const int64_t min_blocks = (items + kSegThreads / 32 - 1) / (kSegThreads / 32);
+            if (blocks > min_blocks) blocks = min_blocks;
+            if (stats) k_integrate_seg<true><<<(unsigned)blocks, kSegThreads, smem, stream>>>(P);
+            else k_integrate_seg<false><<<(unsigned)blocks, kSegThreads, smem, stream>>>(P);
+            return launch_status();
+        }
+    }
+    for (int l = 0; l <= kPyrLevels; ++l) { P.pyr[l] = nullptr; P.pyr_w[l] = 0; }
     const dim3 block(kIntThreads);
     // persistent grid: every SM filled to the kernel's occupancy, rows dealt round-robin to warps
 #define EMF_LAUNCH_ROWS(PIN, TAB)                                                                          \
@@ -474,10 +858,16 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
 
 }  // namespace emfb
 
+extern "C" EMF_API size_t emf_integrate_workspace_bytes(int width, int height) {
+    if (width <= 0 || height <= 0) return 0;
+    size_t off[emfb::kPyrLevels + 1]; int lw[emfb::kPyrLevels + 1], lh[emfb::kPyrLevels + 1];
+    return emfb::pyramid_layout(width, height, off, lw, lh);
+}
+
 extern "C" EMF_API int emf_integrate_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
                                      const emf_image* depth, const emf_image* assoc, float max_weight,
                                      emf_stream_t stream) {
-    return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, nullptr, nullptr, 0, nullptr,
+    return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, nullptr, nullptr, 0, nullptr, nullptr, 0,
                                   (cudaStream_t)stream);
 }
 
@@ -486,7 +876,15 @@ extern "C" EMF_API int emf_integrate_volumes_gated(int n_vol, const emf_volume* 
                                            float max_weight, const int32_t* gate_counts, const int* gates,
                                            int gate_thresh, uint64_t* stats, emf_stream_t stream) {
     return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, gate_counts, gates, gate_thresh,
-                                  (unsigned long long*)stats, (cudaStream_t)stream);
+                                  (unsigned long long*)stats, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" EMF_API int emf_integrate_volumes_ws(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
+                                        const emf_image* depth, const emf_image* assoc, float max_weight,
+                                        const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,
+                                        void* workspace, size_t workspace_bytes, emf_stream_t stream) {
+    return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, gate_counts, gates, gate_thresh,
+                                  (unsigned long long*)stats, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" EMF_API int emf_update_tsdf(const emf_image* depth, const emf_image* assoc_weights, float* tsdf, float* weights,
@@ -497,6 +895,6 @@ extern "C" EMF_API int emf_update_tsdf(const emf_image* depth, const emf_image* 
     v.tsdf = tsdf; v.weights = weights;
     v.res[0] = res[0]; v.res[1] = res[1]; v.res[2] = res[2];
     v.voxel_size = voxel_size; v.truncdist = truncdist; v.id = 0;
-    return emfb::launch_integrate(1, &v, T_oc, K, depth, assoc_weights, max_weight, nullptr, nullptr, 0, nullptr,
+    return emfb::launch_integrate(1, &v, T_oc, K, depth, assoc_weights, max_weight, nullptr, nullptr, 0, nullptr, nullptr, 0,
                                   (cudaStream_t)stream);
 }

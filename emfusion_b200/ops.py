@@ -229,10 +229,36 @@ def raycastComposite(ids, rects, obj_ray, obj_vert, obj_norm, obj_mask, bg_ray, 
     _count("raycastComposite")
 
 
+_WORKSPACES = {}
+
+
+def integrateWorkspace(depth):
+    """cached device workspace (depth pyramid) for frames of this size on this device"""
+    key = (depth.device, depth.shape[0], depth.shape[1])
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        n = int(_lib.lib().emf_integrate_workspace_bytes(int(depth.shape[1]), int(depth.shape[0])))
+        ws = torch.empty((n,), dtype=torch.uint8, device=depth.device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def integrateVolumes(vols, rel_poses_OC, intr, depth, assoc, maxWeight, stream=None, gate_counts=None, gates=None,
-                     gate_thresh=0, stats=None):
+                     gate_thresh=0, stats=None, workspace="auto"):
     """gate_counts (int32 CUDA tensor) + gates (per-volume index or -1): device-side visibility filter;
-    stats: optional uint64/int64 CUDA tensor of 5 counters (accumulated)."""
+    stats: optional uint64/int64 CUDA tensor of 5 counters (accumulated);
+    workspace: "auto" (cached depth-pyramid workspace -> segment-level kernel), None (per-voxel kernel) or a uint8 tensor."""
+    if workspace == "auto":
+        workspace = integrateWorkspace(depth)
+    if workspace is not None:
+        g = (C.c_int * len(vols))(*[int(x) for x in gates]) if gates is not None else None
+        check(_lib.lib().emf_integrate_volumes_ws(len(vols), _vol_array(vols), poses(rel_poses_OC), _f9(intr),
+                                                  image(depth), images(assoc), maxWeight, _ptr(gate_counts), g,
+                                                  int(gate_thresh), _ptr(stats), workspace.data_ptr(), workspace.numel(),
+                                                  _stream(stream)), "integrateVolumes")
+        _count("integrateVolumes")
+        _count("integrateVolumes")
+        return
     if gate_counts is None and stats is None:
         check(_lib.lib().emf_integrate_volumes(len(vols), _vol_array(vols), poses(rel_poses_OC), _f9(intr),
                                                image(depth), images(assoc), maxWeight, _stream(stream)),

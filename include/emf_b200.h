@@ -218,6 +218,16 @@ EMF_API int emf_integrate_volumes_gated(int n_vol, const emf_volume* vols, const
                                 const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,
                                 emf_stream_t stream);
 
+/* emf_integrate_volumes_gated with a workspace of emf_integrate_workspace_bytes(W, H) bytes (device memory, 16-byte
+ * aligned, contents irrelevant): the call builds a (min, max) pyramid of the depth image in it and classifies whole
+ * 4-voxel segments against it before any per-voxel work (integrate.cu).  Same results, bit for bit; without a
+ * workspace (NULL) or with a camera matrix that is not a plain pinhole the per-voxel kernel runs. */
+EMF_API int emf_integrate_volumes_ws(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
+                             const emf_image* depth, const emf_image* assoc, float max_weight,
+                             const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,
+                             void* workspace, size_t workspace_bytes, emf_stream_t stream);
+EMF_API size_t emf_integrate_workspace_bytes(int width, int height);
+
 /* Derives brick_map from const_bits for every volume that carries both (others are skipped); two launches.
  * Call after integrating and before raycasting. */
 EMF_API int emf_update_brick_maps(int n_vol, const emf_volume* vols, emf_stream_t stream);
