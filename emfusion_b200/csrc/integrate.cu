@@ -62,10 +62,12 @@ struct IntParams {
     float g_rel, g_abs;           // |(|pc| / lambda(pixel)) - pc.z| <= g_rel * pc.z + g_abs (classification guard)
     const float2* pyr[kPyrLevels + 1];   // depth (min, max) pyramid, level l = tiles of 2^l pixels (k_integrate_seg); [0] unused
     int pyr_w[kPyrLevels + 1];           // tiles per row of level l
+    int* work_counter;                   // k_integrate_seg: next batch of rows (zeroed by k_depth_pyramid)
 };
 
 constexpr int kIntThreads = 256;
 constexpr int kSegThreads = 256;
+constexpr int kRowBatch = 8;     // rows whose set-up a warp computes at once (one per lane) in k_integrate_seg
 constexpr int kSimpleThreads = 128;
 constexpr float kMarginPx = 3.0f;    // frustum half-planes are pushed out by this many pixels
 constexpr float kMinDepthCull = 0.02f;   // rows that come closer than this to the camera plane are not culled
@@ -335,12 +337,14 @@ struct PyrParams {
     const float* depth; size_t pitch; int w, h;
     float2* lvl[kPyrLevels + 1];
     int lw[kPyrLevels + 1], lh[kPyrLevels + 1];
+    int* work_counter;
 };
 
 __global__ void __launch_bounds__(256) k_depth_pyramid(const __grid_constant__ PyrParams P) {
     __shared__ float2 s_a[32][33];
     const int tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 64;
     const int t = threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && t == 0) *P.work_counter = 0;
     // level 1 straight from the image: thread -> 4 of the 32 x 32 level-1 tiles
     for (int i = t; i < 32 * 32; i += 256) {
         const int lx = i & 31, ly = i >> 5;
@@ -411,52 +415,92 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
     unsigned long long st[5] = {0, 0, 0, 0, 0};
     const float fw = (float)P.w, fh = (float)P.h;
 
-    int vi = 0;
-    for (int item = gwarp; item < P.total_items; item += n_warps) {
-        while (vi + 1 < P.n_vol && P.v[vi + 1].first_item <= item) ++vi;   // rows are dealt in ascending order
+    // Rows are handed out in batches of kRowBatch consecutive rows from a global counter (zeroed by k_depth_pyramid):
+    // dynamic, because the cost of a row ranges from nothing (outside the frustum) to four full chunks.  The per-row
+    // set-up -- the row as a line in homogeneous pixel coordinates and the x-interval that can project into the image --
+    // is computed for the rows of a batch at once, one row per lane; rows with an empty interval cost nothing more.
+    (void)gwarp; (void)n_warps;
+    for (;;) {
+        int batch = 0;
+        if (lane == 0) batch = atomicAdd(P.work_counter, 1);
+        batch = __shfl_sync(kFull, batch, 0);
+        const int item0 = batch * kRowBatch;
+        if (item0 >= P.total_items) break;
+        int l_vi = 0, l_row = 0, l_xa = 0, l_xb = -1;
+        float l_q[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        {
+            const int item = item0 + lane;
+            if (lane < kRowBatch && item < P.total_items) {
+                int lo = 0, hi = P.n_vol - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (P.v[mid].first_item <= item) lo = mid; else hi = mid - 1;
+                }
+                l_vi = lo;
+                const IntVol& V = P.v[lo];
+                const bool gated_out = V.gate >= 0 && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh);   // not visible: not integrated
+                if (!gated_out) {
+                    const int rx = V.rx, ry = V.ry;
+                    l_row = item - V.first_item;          // z * Ry + y
+                    const int z = l_row / ry;
+                    const int y = l_row - z * ry;
+                    const float s = V.voxel;
+                    const float hx = (float)(rx - 1) * 0.5f;
+                    const float cy = ((float)y - (float)(ry - 1) * 0.5f) * s;
+                    const float cz = ((float)z - (float)(V.rz - 1) * 0.5f) * s;
+                    // q(x) = qa + x * qb (plain float math: only used for decisions that carry their own safety margins)
+                    const float c0 = -hx * s;
+                    const float ax = V.t[0] + (V.R[0] * c0 + V.R[1] * cy + V.R[2] * cz), bx = V.R[0] * s;
+                    const float ay = V.t[1] + (V.R[3] * c0 + V.R[4] * cy + V.R[5] * cz), by = V.R[3] * s;
+                    const float az = V.t[2] + (V.R[6] * c0 + V.R[7] * cy + V.R[8] * cz), bz = V.R[6] * s;
+                    const float qxa = P.K[0] * ax + P.K[2] * az, qxb = P.K[0] * bx + P.K[2] * bz;
+                    const float qya = P.K[4] * ay + P.K[5] * az, qyb = P.K[4] * by + P.K[5] * bz;
+                    l_q[0] = qxa; l_q[1] = qxb; l_q[2] = qya; l_q[3] = qyb; l_q[4] = az; l_q[5] = bz;
+                    l_xa = 0; l_xb = rx - 1;
+                    const float xe = (float)(rx - 1);
+                    const float zmin = fminf(az, az + bz * xe);
+                    if (zmin > kMinDepthCull) {   // whole row safely in front of the camera: cull by the four image edges
+                        float lo_x = 0.0f, hi_x = xe;
+                        const float m0 = 0.5f + kMarginPx, mw = fw - 0.5f + kMarginPx, mh = fh - 0.5f + kMarginPx;
+                        const float al[4] = {qxa + m0 * az, mw * az - qxa, qya + m0 * az, mh * az - qya};
+                        const float be[4] = {qxb + m0 * bz, mw * bz - qxb, qyb + m0 * bz, mh * bz - qyb};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (be[k] > 0.0f) lo_x = fmaxf(lo_x, __fdividef(-al[k], be[k]) - 0.01f);
+                            else if (be[k] < 0.0f) hi_x = fminf(hi_x, __fdividef(-al[k], be[k]) + 0.01f);
+                            else if (al[k] < 0.0f) hi_x = -1.0f;
+                        }
+                        if (lo_x <= hi_x) {
+                            l_xa = max(0, (int)floorf(lo_x) - 1);
+                            l_xb = min(rx - 1, (int)ceilf(hi_x) + 1);
+                        } else {
+                            l_xb = -1;
+                        }
+                    }
+                }
+            }
+        }
+        unsigned todo = __ballot_sync(kFull, l_xa <= l_xb);
+        while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int vi = __shfl_sync(kFull, l_vi, src_lane);
+        const int row = __shfl_sync(kFull, l_row, src_lane);
+        int xa = __shfl_sync(kFull, l_xa, src_lane);
+        const int xb = __shfl_sync(kFull, l_xb, src_lane);
+        const float qxa = __shfl_sync(kFull, l_q[0], src_lane), qxb = __shfl_sync(kFull, l_q[1], src_lane);
+        const float qya = __shfl_sync(kFull, l_q[2], src_lane), qyb = __shfl_sync(kFull, l_q[3], src_lane);
+        const float qza = __shfl_sync(kFull, l_q[4], src_lane), qzb = __shfl_sync(kFull, l_q[5], src_lane);
         const IntVol& V = P.v[vi];
-        if (V.gate >= 0 && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh)) continue;   // not visible: not integrated
         const int rx = V.rx, ry = V.ry;
-        const int row = item - V.first_item;          // z * Ry + y
         const int z = row / ry;
         const int y = row - z * ry;
         const float s = V.voxel;
+        // (i - (R-1)/2.f) * voxelSize ; (R-1)*0.5 is exact -- canonical, for the exact per-voxel path
         const float hx = fmul((float)(rx - 1), 0.5f);
         const float cy = fmul(fsub((float)y, fmul((float)(ry - 1), 0.5f)), s);
         const float cz = fmul(fsub((float)z, fmul((float)(V.rz - 1), 0.5f)), s);
         const float my0 = fmul(V.R[1], cy), my1 = fmul(V.R[4], cy), my2 = fmul(V.R[7], cy);
-
-        // ---- the row as a line in homogeneous pixel coordinates, q(x) = qa + x * qb (plain float math: only used for
-        //      decisions that carry their own safety margins), and the conservative x-interval that can project into the image
-        int xa = 0, xb = rx - 1;
-        float qxa, qxb, qya, qyb, qza, qzb;
-        {
-            const float c0 = -hx * s;
-            const float ax = V.t[0] + (V.R[0] * c0 + my0 + V.R[2] * cz), bx = V.R[0] * s;
-            const float ay = V.t[1] + (V.R[3] * c0 + my1 + V.R[5] * cz), by = V.R[3] * s;
-            const float az = V.t[2] + (V.R[6] * c0 + my2 + V.R[8] * cz), bz = V.R[6] * s;
-            qxa = P.K[0] * ax + P.K[2] * az; qxb = P.K[0] * bx + P.K[2] * bz;
-            qya = P.K[4] * ay + P.K[5] * az; qyb = P.K[4] * by + P.K[5] * bz;
-            qza = az; qzb = bz;
-            const float xe = (float)(rx - 1);
-            const float zmin = fminf(az, az + bz * xe);
-            if (zmin > kMinDepthCull) {   // whole row safely in front of the camera: cull by the four image edges
-                float lo = 0.0f, hi = xe;
-                const float m0 = 0.5f + kMarginPx, mw = fw - 0.5f + kMarginPx, mh = fh - 0.5f + kMarginPx;
-                const float al[4] = {qxa + m0 * qza, mw * qza - qxa, qya + m0 * qza, mh * qza - qya};
-                const float be[4] = {qxb + m0 * qzb, mw * qzb - qxb, qyb + m0 * qzb, mh * qzb - qyb};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (be[k] > 0.0f) lo = fmaxf(lo, __fdividef(-al[k], be[k]) - 0.01f);
-                    else if (be[k] < 0.0f) hi = fminf(hi, __fdividef(-al[k], be[k]) + 0.01f);
-                    else if (al[k] < 0.0f) hi = -1.0f;
-                }
-                if (!(lo <= hi)) continue;
-                xa = max(0, (int)floorf(lo) - 1);
-                xb = min(rx - 1, (int)ceilf(hi) + 1);
-                if (xa > xb) continue;
-            }
-        }
         xa &= ~127;                     // whole 128-voxel chunks: one bitmap word per warp iteration
         const int64_t row_off = (int64_t)row * rx;
         const ConstDiv div_trunc(V.trunc);
@@ -653,6 +697,7 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
             }
         }
     }
+    }   // batches
     if (STATS && P.stats) {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -744,6 +789,7 @@ size_t pyramid_layout(int w, int h, size_t off[kPyrLevels + 1], int lw[kPyrLevel
         off[l] = total;
         total += (((size_t)lw[l] * lh[l] * sizeof(float2)) + 255) & ~(size_t)255;
     }
+    total += 256;   // work counter of k_integrate_seg (last 256 bytes)
     return total;
 }
 
@@ -814,6 +860,8 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
                 Q.lvl[l] = (float2*)((char*)workspace + off[l]); Q.lw[l] = lw[l]; Q.lh[l] = lh[l];
                 P.pyr[l] = Q.lvl[l]; P.pyr_w[l] = lw[l];
             }
+            Q.work_counter = (int*)((char*)workspace + need - 256);
+            P.work_counter = Q.work_counter;
             const dim3 pgrid((P.w + 63) / 64, (P.h + 63) / 64);
             k_depth_pyramid<<<pgrid, 256, 0, stream>>>(Q);
             static int occ_s = 0, occ_n = 0;
@@ -832,6 +880,7 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
         }
     }
     for (int l = 0; l <= kPyrLevels; ++l) { P.pyr[l] = nullptr; P.pyr_w[l] = 0; }
+    P.work_counter = nullptr;
     const dim3 block(kIntThreads);
     // persistent grid: every SM filled to the kernel's occupancy, rows dealt round-robin to warps
 #define EMF_LAUNCH_ROWS(PIN, TAB)                                                                          \
