@@ -188,15 +188,16 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
                                  e->v_norm.data(), e->v_mask.data(), nullptr, stream);
         if (rc != EMF_OK) return rc;
     }
-    if (flags & EMF_FRAME_COMPOSITE) {
+    if (flags & (EMF_FRAME_COMPOSITE | EMF_FRAME_COMPOSITE_NOBG)) {
         // visibility is re-derived by every raycast (vis_objs.clear(), reference src/core/EMFusion.cpp:745): objects
         // created before it are gated like all others; only objects created after it (:550) are integrated unseen
         std::fill(e->force.begin(), e->force.end(), (char)0);
         const int o0 = e->has_bg ? 1 : 0, n_obj = n - o0;
-        const emf_image* bg_ray = e->has_bg ? &e->v_ray[0] : &e->zero_f;
-        const emf_image* bg_vert = e->has_bg ? &e->v_vert[0] : &e->zero_f3;
-        const emf_image* bg_norm = e->has_bg ? &e->v_norm[0] : &e->zero_f3;
-        const emf_image* bg_mask = e->has_bg ? &e->v_mask[0] : &e->zero_u8;
+        const bool with_bg = e->has_bg && !(flags & EMF_FRAME_COMPOSITE_NOBG);
+        const emf_image* bg_ray = with_bg ? &e->v_ray[0] : &e->zero_f;
+        const emf_image* bg_vert = with_bg ? &e->v_vert[0] : &e->zero_f3;
+        const emf_image* bg_norm = with_bg ? &e->v_norm[0] : &e->zero_f3;
+        const emf_image* bg_mask = with_bg ? &e->v_mask[0] : &e->zero_u8;
         rc = emf_raycast_composite(n_obj, e->ids.data(), e->rects.data() + 4 * o0, e->v_ray.data() + o0, e->v_vert.data() + o0,
                                    e->v_norm.data() + o0, e->v_mask.data() + o0, bg_ray, bg_vert, bg_norm, bg_mask,
                                    e->cfg.boundary, &e->ray, &e->vert, &e->nrm, &e->seg, e->vis_count, stream);

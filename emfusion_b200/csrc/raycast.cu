@@ -522,6 +522,77 @@ __global__ void __launch_bounds__(256) k_composite(const __grid_constant__ CompP
         if (s_cnt[k]) atomicAdd(P.vis_count + k, s_cnt[k]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: merge of the per-rank pre-composites on the rank that owns the background.
+// Every rank composites its own objects (k_composite against an empty background: list order is preserved inside a
+// shard); here the per-rank winners are merged in (raylength, list index) order -- what the reference's sequential
+// "strictly nearer, or first in the list" loop (src/core/EMFusion.cpp:760-771) computes over all objects -- followed by
+// the background rule, the fill from the background and the visibility counts (:773-794).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxParts = 16;
+struct MergeParams {
+    const float* ray[kMaxParts]; const float* vert[kMaxParts]; const float* norm[kMaxParts]; const uint8_t* seg[kMaxParts];
+    size_t ray_pitch[kMaxParts], vert_pitch[kMaxParts], norm_pitch[kMaxParts], seg_pitch[kMaxParts];
+    int n_parts, n_obj, w, h, boundary;
+    int16_t lut[256];          // segmentation id -> list index (-1: none)
+    const float* bg_ray; size_t bg_ray_pitch;
+    const float* bg_vert; size_t bg_vert_pitch;
+    const float* bg_norm; size_t bg_norm_pitch;
+    const uint8_t* bg_mask; size_t bg_mask_pitch;
+    float* o_ray; size_t o_ray_pitch;
+    float* o_vert; size_t o_vert_pitch;
+    float* o_norm; size_t o_norm_pitch;
+    uint8_t* o_seg; size_t o_seg_pitch;
+    int32_t* vis_count;
+};
+
+__global__ void __launch_bounds__(256) k_composite_merge(const __grid_constant__ MergeParams P) {
+    __shared__ int s_cnt[EMF_MAX_VOLUMES];
+    for (int k = threadIdx.x; k < P.n_obj; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < P.w && y < P.h) {
+        float r = 0.0f;
+        int best = 1 << 30, win = -1, seg = 0;
+        for (int p = 0; p < P.n_parts; ++p) {
+            const int sg = P.seg[p][(size_t)y * P.seg_pitch[p] + x];
+            if (!sg) continue;
+            const int idx = P.lut[sg] < 0 ? (1 << 29) : P.lut[sg];
+            const float t = *((const float*)((const char*)P.ray[p] + (size_t)y * P.ray_pitch[p]) + x);
+            // sequential rule in list order == lexicographic minimum over (raylength, list index); a winner whose
+            // raylength is <= 0 is replaced by any later object
+            const bool take = win < 0 || (r <= 0.0f && idx > best) || t < r || (t == r && idx < best && !(r <= 0.0f));
+            if (take) { r = t; best = idx; win = p; seg = sg; }
+        }
+        const bool bgm = P.bg_mask[(size_t)y * P.bg_mask_pitch + x] != 0;
+        if (bgm) {
+            const float bt = *((const float*)((const char*)P.bg_ray + (size_t)y * P.bg_ray_pitch) + x);
+            if (fsub(r, bt) > 0.05f) seg = 0;
+        }
+        *((float*)((char*)P.o_ray + (size_t)y * P.o_ray_pitch) + x) = r;
+        P.o_seg[(size_t)y * P.o_seg_pitch + x] = (uint8_t)seg;
+        const float* vs; const float* ns;
+        if (seg == 0) {
+            vs = (const float*)((const char*)P.bg_vert + (size_t)y * P.bg_vert_pitch) + 3 * x;
+            ns = (const float*)((const char*)P.bg_norm + (size_t)y * P.bg_norm_pitch) + 3 * x;
+        } else {
+            vs = (const float*)((const char*)P.vert[win] + (size_t)y * P.vert_pitch[win]) + 3 * x;
+            ns = (const float*)((const char*)P.norm[win] + (size_t)y * P.norm_pitch[win]) + 3 * x;
+        }
+        float* vo = (float*)((char*)P.o_vert + (size_t)y * P.o_vert_pitch) + 3 * x;
+        float* no = (float*)((char*)P.o_norm + (size_t)y * P.o_norm_pitch) + 3 * x;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+        if (seg != 0 || bgm) { v0 = vs[0]; v1 = vs[1]; v2 = vs[2]; n0 = ns[0]; n1 = ns[1]; n2 = ns[2]; }
+        vo[0] = v0; vo[1] = v1; vo[2] = v2; no[0] = n0; no[1] = n1; no[2] = n2;
+        if (seg != 0 && P.lut[seg] >= 0 && x >= P.boundary && x < P.w - P.boundary && y >= P.boundary && y < P.h - P.boundary)
+            atomicAdd(&s_cnt[P.lut[seg]], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < P.n_obj; k += blockDim.x)
+        if (s_cnt[k]) atomicAdd(P.vis_count + k, s_cnt[k]);
+}
+
 }  // namespace emfb
 
 using namespace emfb;
@@ -632,5 +703,45 @@ extern "C" EMF_API int emf_raycast_composite(int n_obj, const int* ids, const in
     if (n_obj > 0) cudaMemsetAsync(vis_count, 0, sizeof(int32_t) * n_obj, (cudaStream_t)stream);
     const dim3 grid((w + 31) / 32, (h + 7) / 8);
     k_composite<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_composite_merge(int n_parts, const emf_image* part_ray, const emf_image* part_vert,
+                                   const emf_image* part_norm, const emf_image* part_seg, int n_obj, const int* ids,
+                                   const emf_image* bg_ray, const emf_image* bg_vert, const emf_image* bg_norm,
+                                   const emf_image* bg_mask, int boundary, const emf_image* ray, const emf_image* vert,
+                                   const emf_image* norm, const emf_image* seg, int32_t* vis_count, emf_stream_t stream) {
+    if (n_parts <= 0 || n_parts > kMaxParts || n_obj < 0 || n_obj > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
+    if (!part_ray || !part_vert || !part_norm || !part_seg || (n_obj > 0 && (!ids || !vis_count))) return EMF_ERR_INVALID;
+    if (!image_ok(bg_ray, 4) || !image_ok(bg_vert, 12) || !image_ok(bg_norm, 12) || !image_ok(bg_mask, 1) ||
+        !image_ok(ray, 4) || !image_ok(vert, 12) || !image_ok(norm, 12) || !image_ok(seg, 1))
+        return EMF_ERR_INVALID;
+    MergeParams P;
+    const int w = ray->width, h = ray->height;
+    for (int p = 0; p < n_parts; ++p) {
+        if (!image_ok(&part_ray[p], 4) || !image_ok(&part_vert[p], 12) || !image_ok(&part_norm[p], 12) ||
+            !image_ok(&part_seg[p], 1) || part_ray[p].width != w || part_ray[p].height != h)
+            return EMF_ERR_INVALID;
+        P.ray[p] = (const float*)part_ray[p].ptr; P.ray_pitch[p] = part_ray[p].pitch;
+        P.vert[p] = (const float*)part_vert[p].ptr; P.vert_pitch[p] = part_vert[p].pitch;
+        P.norm[p] = (const float*)part_norm[p].ptr; P.norm_pitch[p] = part_norm[p].pitch;
+        P.seg[p] = (const uint8_t*)part_seg[p].ptr; P.seg_pitch[p] = part_seg[p].pitch;
+    }
+    for (int k = 0; k < 256; ++k) P.lut[k] = -1;
+    for (int k = n_obj - 1; k >= 0; --k) P.lut[ids[k] > 255 ? 255 : (ids[k] < 0 ? 0 : ids[k])] = (int16_t)k;   // first in list wins a shared id
+    P.lut[0] = -1;
+    P.n_parts = n_parts; P.n_obj = n_obj; P.w = w; P.h = h; P.boundary = boundary;
+    P.bg_ray = (const float*)bg_ray->ptr; P.bg_ray_pitch = bg_ray->pitch;
+    P.bg_vert = (const float*)bg_vert->ptr; P.bg_vert_pitch = bg_vert->pitch;
+    P.bg_norm = (const float*)bg_norm->ptr; P.bg_norm_pitch = bg_norm->pitch;
+    P.bg_mask = (const uint8_t*)bg_mask->ptr; P.bg_mask_pitch = bg_mask->pitch;
+    P.o_ray = (float*)ray->ptr; P.o_ray_pitch = ray->pitch;
+    P.o_vert = (float*)vert->ptr; P.o_vert_pitch = vert->pitch;
+    P.o_norm = (float*)norm->ptr; P.o_norm_pitch = norm->pitch;
+    P.o_seg = (uint8_t*)seg->ptr; P.o_seg_pitch = seg->pitch;
+    P.vis_count = vis_count;
+    if (n_obj > 0) cudaMemsetAsync(vis_count, 0, sizeof(int32_t) * n_obj, (cudaStream_t)stream);
+    const dim3 grid((w + 31) / 32, (h + 7) / 8);
+    k_composite_merge<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
 }

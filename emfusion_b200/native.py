@@ -25,6 +25,7 @@ from .volume import ObjTSDF, Params
 # phases (include/emf_b200.h)
 F_POINTS, F_ASSOC, F_ASSOC_PARTIAL, F_NORMALISE, F_RAYCAST, F_COMPOSITE, F_INTEGRATE, F_INTEGRATE_ALL = (
     0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80)
+F_COMPOSITE_NOBG = 0x100
 F_TIMED = 0x200
 F_ALL = F_POINTS | F_ASSOC | F_RAYCAST | F_COMPOSITE | F_INTEGRATE
 IMG_POINTS, IMG_NORM, IMG_RAY, IMG_VERT, IMG_NORMALS, IMG_SEG = range(6)
@@ -131,7 +132,7 @@ class NativeEngine(EMFusionEngine):
         if flags & (F_ASSOC | F_ASSOC_PARTIAL) and n: launches += 1
         if flags & F_NORMALISE and n: launches += 1
         if flags & F_RAYCAST and n: launches += 1
-        if flags & F_COMPOSITE: launches += 1
+        if flags & (F_COMPOSITE | F_COMPOSITE_NOBG): launches += 1
         if flags & F_INTEGRATE and n: launches += 1 + (2 if any(v.constBits is not None for v in vols) else 0)
         ops.LAUNCHES["engineFrame"] = ops.LAUNCHES.get("engineFrame", 0) + launches
 
@@ -153,53 +154,57 @@ class NativeEngine(EMFusionEngine):
             self._frame(F_RAYCAST | F_COMPOSITE)
             self._pending_vis = True
             return
-        # rank 0 composites by hand below (its pre-composite must not contain the background); the other ranks
-        # pre-composite against an empty background inside the engine
-        self._frame(F_RAYCAST if self.rank == 0 else (F_RAYCAST | F_COMPOSITE))
+        # every rank composites its own objects against an EMPTY background; rank 0 merges after the gather
+        self._frame(F_RAYCAST | F_COMPOSITE_NOBG)
         self._composite_distributed()
 
+    def _packed(self):
+        """the pre-composite block [ray | vert | normals | seg] of the engine pool as one uint8 tensor (+ offsets)"""
+        p0 = self.raylengths.data_ptr()
+        offs = (0, self.vertices.data_ptr() - p0, self.normals.data_ptr() - p0, self.modelSegmentation.data_ptr() - p0)
+        size = offs[3] + self.h * self.w
+        assert 0 < offs[1] < offs[2] < offs[3]
+        return torch.as_tensor(_DevMem(p0, (size,), "|u1"), device=self.device), offs, size
+
     def _composite_distributed(self):
-        """gather of the per-rank pre-composites to rank 0, merge there in (raylength, list-order) order, visibility
-        from the final segmentation broadcast to every rank's device counters (the integrate gate)"""
+        """gather of the per-rank pre-composites to rank 0 (one NCCL call), merge there (one launch, emf_composite_merge),
+        visibility counts broadcast to every rank's device counters (the integrate gate); no host synchronisation"""
         import torch.distributed as dist
         h, w, dev = self.h, self.w, self.device
+        packed, offs, size = self._packed()
+        n_all = len(self.all_ids)
+        g = self._gather_bufs
+        if g is None or g["size"] != size or g["n_all"] != n_all:
+            g = dict(size=size, n_all=n_all, counts=torch.zeros((max(n_all, 1),), dtype=torch.int32, device=dev),
+                     local=torch.tensor([self.all_ids.index(o.id) for o in self.objects], dtype=torch.int64, device=dev))
+            if self.rank == 0:
+                g["all"] = torch.empty((self.world, size), dtype=torch.uint8, device=dev)
+                g["out"] = [torch.empty((h, w), dtype=torch.float32, device=dev), torch.empty((h, w, 3), dtype=torch.float32, device=dev),
+                            torch.empty((h, w, 3), dtype=torch.float32, device=dev), torch.empty((h, w), dtype=torch.uint8, device=dev)]
+            self._gather_bufs = g
         if self.rank == 0:
-            objs = self.objects
-            g = self._gather_bufs or {}
-            if not g:
-                z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)
-                g = dict(ray=z(h, w), vert=z(h, w, 3), norm=z(h, w, 3), seg=z(h, w, dt=torch.uint8), zray=z(h, w),
-                         zvert=z(h, w, 3), zmask=z(h, w, dt=torch.uint8), cnt=torch.zeros(96, dtype=torch.int32, device=dev))
-                self._gather_bufs = g
-            rects = self._rects(objs)
-            ops.raycastComposite([o.id for o in objs], rects, [self.obj_raylengths[o.id] for o in objs],
-                                 [self.obj_vertices[o.id] for o in objs], [self.obj_normals[o.id] for o in objs],
-                                 [self.obj_modelSegmentation[o.id] for o in objs], g["zray"], g["zvert"], g["zvert"],
-                                 g["zmask"], self.params.boundary, g["ray"], g["vert"], g["norm"], g["seg"], g["cnt"])
-            src = (g["ray"], g["vert"], g["norm"], g["seg"])
-        else:
-            src = (self.raylengths, self.vertices, self.normals, self.modelSegmentation)
-        packed = torch.cat([src[0].reshape(-1), src[1].reshape(-1), src[2].reshape(-1), src[3].reshape(-1).to(torch.float32)])
-        if self.rank == 0:
-            bufs = [torch.empty_like(packed) for _ in range(self.world)]
-            dist.gather(packed, bufs, dst=0, group=self.group)
-            self._merge_on_root(bufs)
+            dist.gather(packed, list(g["all"].unbind(0)), dst=0, group=self.group)
+            base = g["all"].data_ptr()
+            mk = lambda r, o, el: Image(base + r * size + o, w * el, w, h)
+            arr = lambda o, el: (Image * self.world)(*[mk(r, o, el) for r in range(self.world)])
+            ids = (C.c_int * max(n_all, 1))(*[int(i) for i in self.all_ids])
+            out = g["out"]
+            check(self._L.emf_composite_merge(self.world, arr(offs[0], 4), arr(offs[1], 12), arr(offs[2], 12), arr(offs[3], 1),
+                                              n_all, ids, ops.image(self.bg_raylengths), ops.image(self.bg_vertices),
+                                              ops.image(self.bg_normals), ops.image(self.bg_mask), int(self.params.boundary),
+                                              ops.image(out[0]), ops.image(out[1]), ops.image(out[2]), ops.image(out[3]),
+                                              g["counts"].data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                  "emf_composite_merge")
+            ops.LAUNCHES["compositeMerge"] = ops.LAUNCHES.get("compositeMerge", 0) + 1
+            # the merged composite replaces rank 0's pre-composite in the engine's frame images
+            self.raylengths.copy_(out[0]); self.vertices.copy_(out[1]); self.normals.copy_(out[2]); self.modelSegmentation.copy_(out[3])
         else:
             dist.gather(packed, None, dst=0, group=self.group)
-        n_all = len(self.all_ids)
-        counts = torch.zeros((max(n_all, 1),), dtype=torch.int32, device=dev)
-        if self.rank == 0 and n_all:
-            seg = self.modelSegmentation
-            b = self.params.boundary
-            hist = torch.bincount(seg[b:h - b, b:w - b].reshape(-1).to(torch.int64), minlength=256)
-            ids = torch.tensor([min(i, 255) for i in self.all_ids], device=dev)
-            counts[:n_all] = hist[ids].to(torch.int32)
-        dist.broadcast(counts, src=0, group=self.group)
+        dist.broadcast(g["counts"], src=0, group=self.group)
         # this rank's objects, in its local list order, gate the integrate on the device
-        local = [self.all_ids.index(o.id) for o in self.objects]
-        if local:
-            self.vis_count[:len(local)] = counts[torch.tensor(local, device=dev)]
-        self._global_counts = counts
+        if g["local"].numel():
+            self.vis_count[:g["local"].numel()] = g["counts"][g["local"]]
+        self._global_counts = g["counts"]
         self._pending_vis = True
 
     def _resolve_visibility(self):

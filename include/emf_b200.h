@@ -199,6 +199,17 @@ EMF_API int emf_raycast_composite(int n_obj, const int* ids, const int* rects, c
                           const emf_image* bg_mask, int boundary, const emf_image* ray, const emf_image* vert,
                           const emf_image* norm, const emf_image* seg, int32_t* vis_count, emf_stream_t stream);
 
+/* Multi-GPU composite: every rank runs emf_raycast_composite on its own objects against an EMPTY background (mask == 0)
+ * and the n_parts results (ray / vert / norm / seg images, e.g. gathered with NCCL) are merged here, on the rank that
+ * owns the background, in (raylength, list order) order -- the outcome of the reference's sequential loop over all
+ * objects (src/core/EMFusion.cpp:760-771) -- followed by the background rule, the fill and the visibility counts
+ * (:773-794).  ids: all n_obj objects in global list order; vis_count[n_obj] (device, zeroed by the call). */
+EMF_API int emf_composite_merge(int n_parts, const emf_image* part_ray, const emf_image* part_vert, const emf_image* part_norm,
+                        const emf_image* part_seg, int n_obj, const int* ids, const emf_image* bg_ray,
+                        const emf_image* bg_vert, const emf_image* bg_norm, const emf_image* bg_mask, int boundary,
+                        const emf_image* ray, const emf_image* vert, const emf_image* norm, const emf_image* seg,
+                        int32_t* vis_count, emf_stream_t stream);
+
 /* emf::EMFusion::integrateDepth, src/core/EMFusion.cpp:865-889, one launch for all volumes.
  * T_oc[i] = cam_pose^-1 * pose_i; assoc[i] = that volume's association image. */
 EMF_API int emf_integrate_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
@@ -276,6 +287,7 @@ typedef struct emf_engine_config {
 #define EMF_FRAME_COMPOSITE 0x20u      /* composite + visibility counters (against an empty background if there is none) */
 #define EMF_FRAME_INTEGRATE 0x40u      /* integrate the background and the visible objects */
 #define EMF_FRAME_INTEGRATE_ALL 0x80u  /* ... every volume regardless of visibility (first frame) */
+#define EMF_FRAME_COMPOSITE_NOBG 0x100u /* ... composite against an empty background even if there is one (multi-GPU pre-composite) */
 #define EMF_FRAME_TIMED 0x200u         /* record stage events for emf_engine_stage_ms */
 #define EMF_FRAME_ALL (EMF_FRAME_POINTS | EMF_FRAME_ASSOC | EMF_FRAME_RAYCAST | EMF_FRAME_COMPOSITE | EMF_FRAME_INTEGRATE)
 
