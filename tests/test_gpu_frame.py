@@ -9,6 +9,7 @@ import torch
 
 from emfusion_b200 import ops
 from emfusion_b200.engine import EMFusionEngine
+from emfusion_b200.native import NativeEngine
 from emfusion_b200.poses import Affine, rel_pose_CO, rel_pose_OC
 from emfusion_b200.synth import Scene
 from emfusion_b200.volume import ObjTSDF, Params
@@ -17,15 +18,18 @@ from tests.test_gpu_parity import DEV, assert_bits, cu
 
 pytestmark = pytest.mark.gpu
 
-CASES = [("k3_64", 320, 240, 64, 3, 32), ("k8_96", 640, 480, 96, 8, 32)]
+CASES = [("k3_64", 320, 240, 64, 3, 32), ("k8_96", 640, 480, 96, 8, 32),
+         # BASELINE.json sizes: config 4's volumes (512^3 background, 128^3 objects; 4 of the 32 objects) and config 5's
+         # 1024^3 background at 1280x960 (64-bit offsets: tsdf 4 GiB, reference gradients 12 GiB)
+         ("cfg4_512_128", 640, 480, 512, 4, 128), ("cfg5_1024", 1280, 960, 1024, 1, 128)]
 
 
-def build_engine(w, h, bg_res, n_obj, obj_res, seed=1, world=1, rank=0):
+def build_engine(w, h, bg_res, n_obj, obj_res, seed=1, world=1, rank=0, cls=EMFusionEngine):
     scene = Scene(n_objects=n_obj, width=w, height=h, seed=seed, dropout=0.01)
     prm = Params(frameSize=(w, h), intr=scene.K, globalVolumeDims=(bg_res,) * 3, globalVoxelSize=5.12 / bg_res,
                  objVolumeDims=(obj_res,) * 3, visibilityThresh=(40 * 40 * w * h) // (640 * 480), boundary=max(2, 20 * w // 640))
     ObjTSDF.nextID = 0
-    eng = EMFusionEngine(prm, DEV, rank=rank, world_size=world)
+    eng = cls(prm, DEV, rank=rank, world_size=world)
     for k in range(n_obj):
         eng.add_object(scene.object_pose(k, 0), scene.object_voxel_size(k, obj_res))
     return scene, prm, eng
@@ -47,10 +51,13 @@ def run_frames(scene, eng, n_frames, with_masks=True):
 
 
 @pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("engine", ["staged", "native"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_engine_vs_reference_frames(case, cuda_dev):
+def test_engine_vs_reference_frames(case, engine, cuda_dev):
     _, w, h, bg_res, n_obj, obj_res = case
-    scene, prm, eng = build_engine(w, h, bg_res, n_obj, obj_res)
+    if engine == "staged" and bg_res >= 512:
+        pytest.skip("full-size cases run once, through the native engine")
+    scene, prm, eng = build_engine(w, h, bg_res, n_obj, obj_res, cls=NativeEngine if engine == "native" else EMFusionEngine)
     # reference state: separately allocated volumes driven by the reference launch sequence
     vols = eng.local_volumes()
     rv = []
@@ -64,7 +71,7 @@ def test_engine_vs_reference_frames(case, cuda_dev):
     for i in range(len(vols)):
         ref.fill_assoc(i, 1.0)
     K = prm.intr
-    n_frames = 4
+    n_frames = 4 if bg_res <= 512 else 3
     for f in range(n_frames):
         depth, inst = scene.render(f)
         d = cu(depth)
