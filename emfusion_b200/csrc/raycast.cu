@@ -60,7 +60,8 @@ struct RayParams {
                                  //           [2] jumps [3] weight samples
 };
 
-constexpr int kTileW = 16, kTileH = 8;   // CTA tile; warp = 8 x 4 pixels
+constexpr int kWarpW = 8, kWarpH = 4;     // pixels of one warp
+constexpr int kTileW = 2 * kWarpW, kTileH = 2 * kWarpH;   // CTA tile = 2 x 2 warps
 constexpr int kRayThreads = kTileW * kTileH;
 
 // trilinear TSDF sample with 32-bit element offsets (volumes are < 2^31 voxels: res_ok)
@@ -120,8 +121,11 @@ __device__ __forceinline__ void trilinear_grad(const RayVol& V, float vx, float 
 }
 
 // v < 0 || v + pad >= R on every axis, with the rounded additions folded into per-volume thresholds
+// (for the non-negative thresholds and the finite, never -0.0 coordinates of a marching ray, `v < 0 || v >= thr` is one
+// unsigned comparison of the bit patterns: a set sign bit compares above every threshold)
 __device__ __forceinline__ bool out_of_thr(float vx, float vy, float vz, const float* thr) {
-    return vx < 0.0f || vx >= thr[0] || vy < 0.0f || vy >= thr[1] || vz < 0.0f || vz >= thr[2];
+    return __float_as_uint(vx) >= __float_as_uint(thr[0]) || __float_as_uint(vy) >= __float_as_uint(thr[1]) ||
+           __float_as_uint(vz) >= __float_as_uint(thr[2]);
 }
 
 // march state of one ray
@@ -133,12 +137,19 @@ struct Ray {
 };
 struct RayConst {
     float dx, dy, dz, ox, oy, oz, hxh, hyh, hzh, s, half_s, tmax;
+    bool sane;   // the divisor and every |o + dir t| of this ray are inside ConstDiv's exponent window
 };
 
+// v = (R-1)/2 + (o + dir t) / s.  The three IEEE divisions share one exponent-range test (ConstDiv::fast is the
+// unguarded sequence): all numerators are far below 2^64 for any finite ray (c.sane), so only a numerator that is tiny
+// (or exactly zero) sends the sample through the guarded operator.
 __device__ __forceinline__ void ray_position(Ray& r, const RayConst& c, const ConstDiv& div_s) {
-    r.vx = fadd(c.hxh, div_s(ffma(c.dx, r.tcur, c.ox)));
-    r.vy = fadd(c.hyh, div_s(ffma(c.dy, r.tcur, c.oy)));
-    r.vz = fadd(c.hzh, div_s(ffma(c.dz, r.tcur, c.oz)));
+    const float nx = ffma(c.dx, r.tcur, c.ox), ny = ffma(c.dy, r.tcur, c.oy), nz = ffma(c.dz, r.tcur, c.oz);
+    if (c.sane && fminf(fminf(fabsf(nx), fabsf(ny)), fabsf(nz)) > 5.5e-20f) {
+        r.vx = fadd(c.hxh, div_s.fast(nx)); r.vy = fadd(c.hyh, div_s.fast(ny)); r.vz = fadd(c.hzh, div_s.fast(nz));
+    } else {
+        r.vx = fadd(c.hxh, div_s(nx)); r.vy = fadd(c.hyh, div_s(ny)); r.vz = fadd(c.hzh, div_s(nz));
+    }
 }
 
 // one march step of the reference algorithm (TSDF.cu:523-572); returns true when the ray is finished
@@ -191,10 +202,10 @@ __global__ void __launch_bounds__(kRayThreads, 8) k_raycast(const __grid_constan
     const RayVol& V = P.v[lo];
     const int lb = b - V.first_block;
     const int ty = lb / V.tiles_x, tx = lb - ty * V.tiles_x;
-    // warp = 8x4 pixel patch inside the 16x8 CTA tile
+    // warp = kWarpW x kWarpH pixel patch inside the CTA tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xr = V.x0 + tx * kTileW + (warp & 1) * 8 + (lane & 7);
-    const int yr = V.y0 + ty * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    const int xr = V.x0 + tx * kTileW + (warp & 1) * kWarpW + (lane % kWarpW);
+    const int yr = V.y0 + ty * kTileH + (warp >> 1) * kWarpH + (lane / kWarpW);
     const bool valid = xr < V.x1 && yr < V.y1;
     if (!JUMP && !valid) return;
     const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);   // (JUMP: lanes outside the rectangle idle in the loop)
@@ -254,6 +265,7 @@ __global__ void __launch_bounds__(kRayThreads, 8) k_raycast(const __grid_constan
         else c.tmax = fminf(c.tmax, tb);
     }
     const ConstDiv div_s(s);
+    c.sane = div_s.ok && fabsf(c.ox) + fabsf(c.oy) + fabsf(c.oz) + fabsf(r.tcur) + fabsf(c.tmax) + V.trunc < 1.0e18f;
     const int rx = V.rx, plane = V.rx * V.ry;
     r.step = V.trunc;
     r.vx = r.vy = r.vz = r.f = 0.f;
