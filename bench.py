@@ -117,51 +117,56 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(cfg, seed=0):
-    """Scalar C oracle (OpenMP, all host cores) on a bounded sample of the same workload:
-    same 640x480 frame and scene, background at half resolution + 4 of the objects."""
+def cpu_baseline(cfg, seed=0, budget_s=20.0):
+    """Scalar C oracle (OpenMP over z-slabs / image rows, all host cores) on a bounded sample of the same workload: the
+    configuration's own volumes and frame size, as many stream frames as fit in ~budget_s seconds (at least one)."""
     from tests import oracle_c
     from tests import scenario as S
+    from emfusion_b200.poses import rel_pose_CO, rel_pose_OC
     o = oracle_c.load()
     name, bg, k, ob, w, h = CONFIGS[cfg]
-    bg_s, k_s = (min(bg, 256), min(k, 4))
-    t0 = time.time()
-    sc = S.make("cpu", o, w, h, (bg_s,) * 3, k_s, (ob,) * 3, n_frames=2, integrate_frames=1, seed=seed)
-    setup = time.time() - t0
-    f = 1
-    from emfusion_b200.poses import rel_pose_CO, rel_pose_OC
-    cam = sc.cam(f)
-    t0 = time.time()
-    pts = o.compute_points(sc.depths[f], sc.K)
-    imgs = []
-    for v in sc.vols():
-        T = rel_pose_CO(cam, v.pose)
-        a, _ = o.assoc_volume(v.tsdf, v.fg_probs, pts, S.R9(T), S.T3(T), v.res, v.voxel, v.trunc)
-        imgs.append(a)
-    o.normalise(imgs)
-    t_assoc = time.time() - t0
-    t0 = time.time()
-    rc = []
-    for v in sc.vols():
-        T = rel_pose_CO(cam, v.pose)
-        g = o.compute_grads(v.tsdf, v.res)
-        wts = v.weights if v.fg_probs is None else o.raycast_weights(v.weights, (v.fg_probs > 0.5).astype(np.uint8) * 255)
-        rc.append(o.raycast(v.tsdf, g, wts, S.R9(T), S.T3(T), sc.K, v.res, v.voxel, v.trunc, w, h))
-    if k_s:
-        o.composite([v.vid for v in sc.objs], [r["ray"] for r in rc[1:]], [r["vert"] for r in rc[1:]],
-                    [r["norm"] for r in rc[1:]], [r["mask"] for r in rc[1:]], rc[0]["ray"], rc[0]["vert"],
-                    rc[0]["norm"], rc[0]["mask"], 20)
-    t_ray = time.time() - t0
-    t0 = time.time()
-    for v, a in zip(sc.vols(), imgs):
-        T = rel_pose_OC(cam, v.pose)
-        o.update_tsdf(sc.depths[f], a, v.tsdf, v.weights, S.R9(T), S.T3(T), sc.K, v.res, v.voxel, v.trunc, 64.0)
-    t_int = time.time() - t0
-    nvox = bg_s ** 3 + k_s * ob ** 3
+    k_s = min(k, 8)                                    # 8 of the objects (their volumes are identical in size)
+    sc = S.make("cpu", o, w, h, (bg,) * 3, k_s, (ob,) * 3, n_frames=8, integrate_frames=1, seed=seed)
+    nvox = bg ** 3 + k_s * ob ** 3
+    t_assoc = t_ray = t_int = 0.0
+    frames = 0
+    t_start = time.time()
+    for f in range(1, 8):
+        cam = sc.cam(f)
+        t0 = time.time()
+        pts = o.compute_points(sc.depths[f], sc.K)
+        imgs = []
+        for v in sc.vols():
+            T = rel_pose_CO(cam, v.pose)
+            a, _ = o.assoc_volume(v.tsdf, v.fg_probs, pts, S.R9(T), S.T3(T), v.res, v.voxel, v.trunc)
+            imgs.append(a)
+        o.normalise(imgs)
+        t_assoc += time.time() - t0
+        t0 = time.time()
+        rc = []
+        for v in sc.vols():
+            T = rel_pose_CO(cam, v.pose)
+            g = o.compute_grads(v.tsdf, v.res)
+            wts = v.weights if v.fg_probs is None else o.raycast_weights(v.weights, (v.fg_probs > 0.5).astype(np.uint8) * 255)
+            rc.append(o.raycast(v.tsdf, g, wts, S.R9(T), S.T3(T), sc.K, v.res, v.voxel, v.trunc, w, h))
+            del g
+        if k_s:
+            o.composite([v.vid for v in sc.objs], [r["ray"] for r in rc[1:]], [r["vert"] for r in rc[1:]],
+                        [r["norm"] for r in rc[1:]], [r["mask"] for r in rc[1:]], rc[0]["ray"], rc[0]["vert"],
+                        rc[0]["norm"], rc[0]["mask"], 20)
+        t_ray += time.time() - t0
+        t0 = time.time()
+        for v, a in zip(sc.vols(), imgs):
+            T = rel_pose_OC(cam, v.pose)
+            o.update_tsdf(sc.depths[f], a, v.tsdf, v.weights, S.R9(T), S.T3(T), sc.K, v.res, v.voxel, v.trunc, 64.0)
+        t_int += time.time() - t0
+        frames += 1
+        if time.time() - t_start > budget_s:
+            break
     tot = t_assoc + t_ray + t_int
-    return {"value": nvox / tot / 1e6, "unit": "Mvoxels/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"1 frame {w}x{h}: bg {bg_s}^3 + {k_s} obj @{ob}^3 ({nvox} voxels); assoc {t_assoc:.2f}s "
-                      f"raycast {t_ray:.2f}s integrate {t_int:.2f}s (OpenMP, gradients materialised inside raycast leg)"}
+    return {"value": nvox * frames / tot / 1e6, "unit": "Mvoxels/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{frames} frame(s) {w}x{h}: bg {bg}^3 + {k_s} obj @{ob}^3 ({nvox} voxels/frame); assoc {t_assoc:.2f}s "
+                      f"raycast+gradients {t_ray:.2f}s integrate {t_int:.2f}s (scalar C oracle, OpenMP, all host cores)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -264,8 +269,16 @@ def run_ours(args):
     nvox = total_voxels(args.config)
     if rank == 0:
         peak, peak_src = peaks()
-        roof = {"bound": "hbm", "kernel": "k_integrate_rows", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+        roof = {"bound": "hbm", "kernel": "k_integrate_seg", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "peak_source": peak_src}
+        try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as fh:
+                tr = json.load(fh)["k_integrate_seg"]
+            if args.config == 4 and world == 1:
+                roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roof["traffic_source"] = "profiles/r1c_ncu_full_summary.md"
+        except Exception:
+            pass
         if world == 1:
             # algorithmic bytes of the integrate launch: 16 B/voxel x the voxels of the volumes it integrated (upper-bound
             # convention); next to it the exact bytes from the kernel's own counters (separate untimed launch)
