@@ -55,6 +55,7 @@ _SIGS = {
     "emf_engine_image": [C.c_void_p, C.c_int, C.c_int, _P(Image)],
     "emf_engine_vis_counts": [C.c_void_p, _P(C.c_int32), C.c_int],
     "emf_engine_force_integrate": [C.c_void_p, C.c_int],
+    "emf_engine_set_background_rows": [C.c_void_p, C.c_int, C.c_int],
     "emf_compute_points": [_P(Image), _P(Image), _P(C.c_float), C.c_void_p],
     "emf_update_tsdf": [_P(Image), _P(Image), C.c_void_p, C.c_void_p, _P(Pose), _P(C.c_float), _P(C.c_int),
                         C.c_float, C.c_float, C.c_float, C.c_void_p],

@@ -38,7 +38,7 @@ struct AssocParams {
     float k2;       // 1 / (2 sigma)            (src/core/TSDF.cpp:154)
     float alpha;    //                          (src/core/TSDF.cpp:131)
     float k3;       // (1 - alpha) * uniPrior   (src/core/TSDF.cpp:133)
-    int mode;       // 0 normalise in place; 1 write partial normaliser; 2 raw (single volume)
+    int mode;       // 0 normalise in place; 1 write partial normaliser; 2 raw (single volume); 3 as 1 without volume 0
     float* norm; size_t norm_pitch;
 };
 
@@ -78,10 +78,11 @@ __global__ void __launch_bounds__(256) k_assoc(const __grid_constant__ AssocPara
         const float wgt = assoc_one(V, P, px, py, pz, invalid);
         *((float*)((char*)V.out + (size_t)y * V.out_pitch) + x) = wgt;
         if (V.mask_out) V.mask_out[(size_t)y * V.mask_pitch + x] = invalid ? 255 : 0;
-        n = (i == 0) ? wgt : fadd(n, wgt);   // copyTo, then add in table order (EMFusion.cpp:654-657)
+        if (P.mode == 3 && i == 0) { n = 0.0f; }      // a replica of the background: its weight is summed by its owner
+        else n = (i == 0) ? wgt : fadd(n, wgt);      // copyTo, then add in table order (EMFusion.cpp:654-657)
         if (wgt != 0.0f) nz[i >> 5] |= 1u << (i & 31);
     }
-    if (P.mode == 1) { *((float*)((char*)P.norm + (size_t)y * P.norm_pitch) + x) = n; return; }
+    if (P.mode == 1 || P.mode == 3) { *((float*)((char*)P.norm + (size_t)y * P.norm_pitch) + x) = n; return; }
     if (P.mode != 0) return;
     if (P.norm) *((float*)((char*)P.norm + (size_t)y * P.norm_pitch) + x) = n;
 #pragma unroll
@@ -184,8 +185,8 @@ extern "C" EMF_API int emf_assoc_weights(int n_vol, const emf_volume* vols, cons
                                  const emf_image* norm_partial, emf_stream_t stream) {
     if (n_vol <= 0 || !vols || !T_co || !params || !assoc_out || !image_ok(points, 12)) return EMF_ERR_INVALID;
     if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
-    if (mode != 0 && mode != 1) return EMF_ERR_INVALID;
-    if (mode == 1 && !image_ok(norm_partial, 4)) return EMF_ERR_INVALID;
+    if (mode != 0 && mode != 1 && mode != 3) return EMF_ERR_INVALID;
+    if (mode != 0 && !image_ok(norm_partial, 4)) return EMF_ERR_INVALID;
     AssocParams P;
     const int w = points->width, h = points->height;
     for (int i = 0; i < n_vol; ++i) {

@@ -24,6 +24,7 @@ struct emf_engine {
     std::vector<int> ids, gates;
     std::vector<char> force;          // integrate this volume once regardless of its visibility counter (new objects)
     std::vector<int> rects;
+    int bg_y0 = 0, bg_y1 = 1 << 30;    // rows of the background's raycast
     // device scratch (one allocation)
     char* pool = nullptr;
     size_t pool_bytes = 0;
@@ -165,12 +166,12 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         if (rc != EMF_OK) return rc;
     }
     if (timed) cudaEventRecord(e->ev[0], s);
-    if ((flags & (EMF_FRAME_ASSOC | EMF_FRAME_ASSOC_PARTIAL)) && n > 0) {
+    if ((flags & (EMF_FRAME_ASSOC | EMF_FRAME_ASSOC_PARTIAL | EMF_FRAME_ASSOC_PARTIAL_NOBG)) && n > 0) {
         if (!T_co) return EMF_ERR_INVALID;
-        const int mode = (flags & EMF_FRAME_ASSOC_PARTIAL) ? 1 : 0;
+        const int mode = (flags & EMF_FRAME_ASSOC_PARTIAL_NOBG) ? (e->has_bg ? 3 : 1) : ((flags & EMF_FRAME_ASSOC_PARTIAL) ? 1 : 0);
         rc = emf_assoc_weights(n, e->vols.data(), T_co, &e->points, &e->cfg.params, e->a_img.data(), mode, &e->norm, stream);
         if (rc != EMF_OK) return rc;
-    } else if ((flags & EMF_FRAME_ASSOC_PARTIAL) && n == 0) {
+    } else if ((flags & (EMF_FRAME_ASSOC_PARTIAL | EMF_FRAME_ASSOC_PARTIAL_NOBG)) && n == 0) {
         cudaMemsetAsync(e->norm.ptr, 0, e->norm.pitch * h, s);
     }
     if ((flags & EMF_FRAME_NORMALISE) && n > 0) {
@@ -183,6 +184,13 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         for (int i = 0; i < n; ++i) {
             rc = emf_volume_screen_rect(e->vols[i].res, e->vols[i].voxel_size, &T_co[i], e->cfg.K, w, h, &e->rects[4 * i]);
             if (rc != EMF_OK) return rc;
+        }
+        if (e->has_bg && (e->rects[0] > 0 || e->rects[1] > 0 || e->rects[2] < w || e->rects[3] < h))
+            // the composite reads the background's hit mask over the whole frame: pixels its box cannot cover are "no hit"
+            cudaMemsetAsync(e->v_mask[0].ptr, 0, e->v_mask[0].pitch * h, s);
+        if (e->has_bg) {   // band of rows of the background (multi-GPU, replicated background)
+            e->rects[1] = std::max(e->rects[1], e->bg_y0);
+            e->rects[3] = std::max(e->rects[1], std::min(e->rects[3], e->bg_y1));
         }
         rc = emf_raycast_volumes(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), e->v_ray.data(), e->v_vert.data(),
                                  e->v_norm.data(), e->v_mask.data(), nullptr, stream);
@@ -264,5 +272,11 @@ extern "C" EMF_API int emf_engine_vis_counts(emf_engine* e, int32_t* counts_out,
 extern "C" EMF_API int emf_engine_force_integrate(emf_engine* e, int vol_index) {
     if (!e || vol_index < 0 || vol_index >= e->n_vol) return EMF_ERR_INVALID;
     e->force[vol_index] = 1;
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_set_background_rows(emf_engine* e, int y0, int y1) {
+    if (!e || y0 < 0 || y1 < y0) return EMF_ERR_INVALID;
+    e->bg_y0 = y0; e->bg_y1 = y1;
     return EMF_OK;
 }

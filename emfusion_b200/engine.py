@@ -22,8 +22,9 @@ from .volume import ObjTSDF, Params, TSDF
 
 class EMFusionEngine:
     def __init__(self, params: Params, device="cuda", rank: int = 0, world_size: int = 1, group=None,
-                 materialize_grads: bool = False, accelerate: bool = False):
+                 materialize_grads: bool = False, accelerate: bool = False, replicate_background: bool = False):
         self.params = params
+        self.replicate_background = bool(replicate_background) and world_size > 1
         self.accelerate = accelerate
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
@@ -36,7 +37,7 @@ class EMFusionEngine:
         f32, u8 = torch.float32, torch.uint8
         dev = self.device
         self.background: Optional[TSDF] = None
-        if rank == 0:
+        if rank == 0 or self.replicate_background:
             # float * float as in the reference (src/core/EMFusion.cpp:31)
             self.background = TSDF(params.globalVolumeDims, params.globalVoxelSize,
                                    float(np.float32(params.globalRelTruncDist) * np.float32(params.globalVoxelSize)),
@@ -138,6 +139,8 @@ class EMFusionEngine:
             vert = [self.bg_vertices if v.id == 0 else self.obj_vertices[v.id] for v in vols]
             norm = [self.bg_normals if v.id == 0 else self.obj_normals[v.id] for v in vols]
             mask = [self.bg_mask if v.id == 0 else self.obj_modelSegmentation[v.id] for v in vols]
+            if self.background is not None and list(rects[0]) != [0, 0, self.w, self.h]:
+                self.bg_mask.zero_()   # the composite reads the background's mask over the whole frame
             ops.raycastVolumes([v.c_volume(with_grads=True) for v in vols],
                                [rel_pose_CO(self.pose, v.pose) for v in vols], self.params.intr, rects, ray, vert,
                                norm, mask)

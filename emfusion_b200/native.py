@@ -26,6 +26,7 @@ from .volume import ObjTSDF, Params
 F_POINTS, F_ASSOC, F_ASSOC_PARTIAL, F_NORMALISE, F_RAYCAST, F_COMPOSITE, F_INTEGRATE, F_INTEGRATE_ALL = (
     0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80)
 F_COMPOSITE_NOBG = 0x100
+F_ASSOC_PARTIAL_NOBG = 0x400
 F_TIMED = 0x200
 F_ALL = F_POINTS | F_ASSOC | F_RAYCAST | F_COMPOSITE | F_INTEGRATE
 IMG_POINTS, IMG_NORM, IMG_RAY, IMG_VERT, IMG_NORMALS, IMG_SEG = range(6)
@@ -41,8 +42,15 @@ class _DevMem:
 
 class NativeEngine(EMFusionEngine):
     def __init__(self, params: Params, device="cuda", rank: int = 0, world_size: int = 1, group=None,
-                 materialize_grads: bool = False, accelerate: bool = False):
-        super().__init__(params, device, rank, world_size, group, materialize_grads, accelerate)
+                 materialize_grads: bool = False, accelerate: bool = False, replicate_background: Optional[bool] = None):
+        """replicate_background (multi-GPU; default: on when the frame height divides by the world size): every rank
+        keeps and integrates its own copy of the background (replicas stay bit-identical: same inputs, deterministic
+        kernels) and raycasts a band of image rows of it; rank 0 gathers the bands.  Off = the background lives on
+        rank 0 only (BASELINE.json's layout), which bounds the speed-up by the background's share of the frame."""
+        if replicate_background is None:
+            replicate_background = world_size > 1 and params.frameSize[1] % world_size == 0
+        super().__init__(params, device, rank, world_size, group, materialize_grads, accelerate,
+                         replicate_background=replicate_background)
         L = _lib.lib()
         cfg = _lib.EngineConfig()
         cfg.width, cfg.height = self.w, self.h
@@ -55,6 +63,9 @@ class NativeEngine(EMFusionEngine):
             raise _lib.EmfError("emf_engine_create failed")
         self._L = L
         self._dirty = True
+        if self.replicate_background:
+            rows = self.h // self.world
+            check(L.emf_engine_set_background_rows(self._e, rank * rows, (rank + 1) * rows), "emf_engine_set_background_rows")
         self._stage = (C.c_float * 3)()
         self._counts = (C.c_int32 * _lib.EMF_MAX_VOLUMES)()
         self._sync_volumes()
@@ -129,7 +140,7 @@ class NativeEngine(EMFusionEngine):
         n = len(vols)
         launches = 0
         if flags & F_POINTS: launches += 1
-        if flags & (F_ASSOC | F_ASSOC_PARTIAL) and n: launches += 1
+        if flags & (F_ASSOC | F_ASSOC_PARTIAL | F_ASSOC_PARTIAL_NOBG) and n: launches += 1
         if flags & F_NORMALISE and n: launches += 1
         if flags & F_RAYCAST and n: launches += 1
         if flags & (F_COMPOSITE | F_COMPOSITE_NOBG): launches += 1
@@ -145,7 +156,8 @@ class NativeEngine(EMFusionEngine):
             self._frame(F_ASSOC)
             return
         import torch.distributed as dist
-        self._frame(F_ASSOC_PARTIAL)
+        # (a replica of the background is left out of the partial sum: rank 0 adds the background's weight)
+        self._frame(F_ASSOC_PARTIAL_NOBG if (self.replicate_background and self.rank != 0) else F_ASSOC_PARTIAL)
         dist.all_reduce(self.associationNorm, op=dist.ReduceOp.SUM, group=self.group)
         self._frame(F_NORMALISE)
 
@@ -182,6 +194,13 @@ class NativeEngine(EMFusionEngine):
                 g["out"] = [torch.empty((h, w), dtype=torch.float32, device=dev), torch.empty((h, w, 3), dtype=torch.float32, device=dev),
                             torch.empty((h, w, 3), dtype=torch.float32, device=dev), torch.empty((h, w), dtype=torch.uint8, device=dev)]
             self._gather_bufs = g
+        if self.replicate_background:
+            # bands of the background's raycast -> rank 0 (the band of rank r is rows [r h/N, (r+1) h/N))
+            rows = h // self.world
+            y0 = self.rank * rows
+            for img in (self.bg_raylengths, self.bg_vertices, self.bg_normals, self.bg_mask):
+                dst = list(img.reshape(self.world, -1).unbind(0)) if self.rank == 0 else None
+                dist.gather(img[y0:y0 + rows].reshape(-1), dst, dst=0, group=self.group)
         if self.rank == 0:
             dist.gather(packed, list(g["all"].unbind(0)), dst=0, group=self.group)
             base = g["all"].data_ptr()

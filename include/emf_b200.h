@@ -170,7 +170,8 @@ EMF_API int emf_compute_association(const emf_volume* vol, const emf_image* poin
  * T_co[i] = pose_i^-1 * cam_pose.  assoc_out[i]: W x H f32 per volume.
  * mode 0: compute + normalise across vols (single-GPU path; sum order = array order).
  * mode 1: compute un-normalised weights and write their per-pixel sum to
- *         norm_partial (multi-GPU: all-reduce norm_partial, then emf_assoc_normalise). */
+ *         norm_partial (multi-GPU: all-reduce norm_partial, then emf_assoc_normalise).
+ * mode 3: as mode 1, but vols[0] is left out of the sum (a replica of the background whose weight the owning rank adds). */
 EMF_API int emf_assoc_weights(int n_vol, const emf_volume* vols, const emf_pose* T_co, const emf_image* points,
                       const emf_tsdf_params* params, const emf_image* assoc_out, int mode,
                       const emf_image* norm_partial, emf_stream_t stream);
@@ -288,6 +289,7 @@ typedef struct emf_engine_config {
 #define EMF_FRAME_INTEGRATE 0x40u      /* integrate the background and the visible objects */
 #define EMF_FRAME_INTEGRATE_ALL 0x80u  /* ... every volume regardless of visibility (first frame) */
 #define EMF_FRAME_COMPOSITE_NOBG 0x100u /* ... composite against an empty background even if there is one (multi-GPU pre-composite) */
+#define EMF_FRAME_ASSOC_PARTIAL_NOBG 0x400u /* ... as ASSOC_PARTIAL, the background (a replica) left out of the partial sum */
 #define EMF_FRAME_TIMED 0x200u         /* record stage events for emf_engine_stage_ms */
 #define EMF_FRAME_ALL (EMF_FRAME_POINTS | EMF_FRAME_ASSOC | EMF_FRAME_RAYCAST | EMF_FRAME_COMPOSITE | EMF_FRAME_INTEGRATE)
 
@@ -321,6 +323,10 @@ EMF_API int emf_engine_image(emf_engine* e, int what, int index, emf_image* out)
  * multi-GPU path to overwrite), and copied to the host (waits for the asynchronous copy only). */
 EMF_API int32_t* emf_engine_vis_counts_device(emf_engine* e);
 EMF_API int emf_engine_vis_counts(emf_engine* e, int32_t* counts_out, int n);
+
+/* Restrict the background's raycast to image rows [y0, y1) (multi-GPU with a replicated background: every rank traces
+ * a band of rows, the bands are gathered on the compositing rank).  y0 = 0, y1 = height restores the full frame. */
+EMF_API int emf_engine_set_background_rows(emf_engine* e, int y0, int y1);
 
 /* Integrate volume vol_index at the next EMF_FRAME_INTEGRATE whatever its visibility counter says (an object created
  * after the last composite: emf::EMFusion::createObj adds it to vis_objs, src/core/EMFusion.cpp:918). */

@@ -15,11 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_engine_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("replicate", ["0", "1"], ids=["background_on_rank0", "background_replicated"])
+def test_two_rank_engine_equals_single_gpu(tmp_path, replicate):
     from tests import mgpu_check
     out2 = str(tmp_path / "w2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_check.py"), out2]
+           "--master-port", "2953" + replicate, os.path.join(ROOT, "tests", "mgpu_check.py"), out2, replicate]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     out1 = str(tmp_path / "w1")
