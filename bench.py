@@ -231,8 +231,10 @@ def run_ours(args):
     l0 = ops.launches_total()
     barrier()
     start.record()
+    t_host = time.perf_counter()
     for s in range(args.steps):
         step(f); f += 1
+    t_host = (time.perf_counter() - t_host) * 1e3 / args.steps     # host time to issue one frame (not a device time)
     stop.record()
     barrier()
     launches = ops.launches_total() - l0
@@ -321,7 +323,7 @@ def run_ours(args):
                           "integrate": float(ms_stage[2])} if world == 1 else None,
             "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h * w * 4, "d2h_bytes_per_step": h * w * 5},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_issue_ms_per_step": t_host,
             "clocks": clocks,
             "roofline": roof,
         }

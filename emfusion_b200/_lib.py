@@ -77,7 +77,8 @@ _SIGS = {
                               _P(Image), _P(Image), _P(Image), _P(Image), C.c_int, _P(Image), _P(Image), _P(Image),
                               _P(Image), C.c_void_p, C.c_void_p],
     "emf_composite_merge": [C.c_int, _P(Image), _P(Image), _P(Image), _P(Image), C.c_int, _P(C.c_int), _P(Image), _P(Image),
-                            _P(Image), _P(Image), C.c_int, _P(Image), _P(Image), _P(Image), _P(Image), C.c_void_p, C.c_void_p],
+                            _P(Image), _P(Image), C.c_int, _P(Image), _P(Image), _P(Image), _P(Image), C.c_void_p, C.c_int,
+                            _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p), C.c_void_p],
     "emf_integrate_volumes": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(Image), _P(Image), C.c_float,
                               C.c_void_p],
     "emf_integrate_volumes_gated": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(Image), _P(Image), C.c_float,

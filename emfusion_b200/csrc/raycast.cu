@@ -547,10 +547,13 @@ struct MergeParams {
     size_t ray_pitch[kMaxParts], vert_pitch[kMaxParts], norm_pitch[kMaxParts], seg_pitch[kMaxParts];
     int n_parts, n_obj, w, h, boundary;
     int16_t lut[256];          // segmentation id -> list index (-1: none)
-    const float* bg_ray; size_t bg_ray_pitch;
-    const float* bg_vert; size_t bg_vert_pitch;
-    const float* bg_norm; size_t bg_norm_pitch;
-    const uint8_t* bg_mask; size_t bg_mask_pitch;
+    float* bg_ray; size_t bg_ray_pitch;
+    float* bg_vert; size_t bg_vert_pitch;
+    float* bg_norm; size_t bg_norm_pitch;
+    uint8_t* bg_mask; size_t bg_mask_pitch;
+    // replicated background: part p holds rows [p * band_rows, (p + 1) * band_rows) of the background's raycast
+    int band_rows;             // 0: the bg_* images are complete inputs; > 0: they are assembled here from the bands
+    const float* b_ray[kMaxParts]; const float* b_vert[kMaxParts]; const float* b_norm[kMaxParts]; const uint8_t* b_mask[kMaxParts];
     float* o_ray; size_t o_ray_pitch;
     float* o_vert; size_t o_vert_pitch;
     float* o_norm; size_t o_norm_pitch;
@@ -577,17 +580,31 @@ __global__ void __launch_bounds__(256) k_composite_merge(const __grid_constant__
             const bool take = win < 0 || (r <= 0.0f && idx > best) || t < r || (t == r && idx < best && !(r <= 0.0f));
             if (take) { r = t; best = idx; win = p; seg = sg; }
         }
-        const bool bgm = P.bg_mask[(size_t)y * P.bg_mask_pitch + x] != 0;
+        float* bgv = (float*)((char*)P.bg_vert + (size_t)y * P.bg_vert_pitch) + 3 * x;
+        float* bgn = (float*)((char*)P.bg_norm + (size_t)y * P.bg_norm_pitch) + 3 * x;
+        float* bgr = (float*)((char*)P.bg_ray + (size_t)y * P.bg_ray_pitch) + x;
+        uint8_t* bgmp = P.bg_mask + (size_t)y * P.bg_mask_pitch + x;
+        if (P.band_rows > 0) {   // assemble the background's raycast from the band of the rank that traced this row
+            const int p = min(y / P.band_rows, P.n_parts - 1);
+            const size_t i = (size_t)(y - p * P.band_rows) * P.w + x;
+            const uint8_t m = P.b_mask[p][i];
+            *bgmp = m; *bgr = P.b_ray[p][i];
+            if (m) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { bgv[k] = P.b_vert[p][3 * i + k]; bgn[k] = P.b_norm[p][3 * i + k]; }
+            }
+        }
+        const bool bgm = *bgmp != 0;
         if (bgm) {
-            const float bt = *((const float*)((const char*)P.bg_ray + (size_t)y * P.bg_ray_pitch) + x);
+            const float bt = *bgr;
             if (fsub(r, bt) > 0.05f) seg = 0;
         }
         *((float*)((char*)P.o_ray + (size_t)y * P.o_ray_pitch) + x) = r;
         P.o_seg[(size_t)y * P.o_seg_pitch + x] = (uint8_t)seg;
         const float* vs; const float* ns;
         if (seg == 0) {
-            vs = (const float*)((const char*)P.bg_vert + (size_t)y * P.bg_vert_pitch) + 3 * x;
-            ns = (const float*)((const char*)P.bg_norm + (size_t)y * P.bg_norm_pitch) + 3 * x;
+            vs = bgv;
+            ns = bgn;
         } else {
             vs = (const float*)((const char*)P.vert[win] + (size_t)y * P.vert_pitch[win]) + 3 * x;
             ns = (const float*)((const char*)P.norm[win] + (size_t)y * P.norm_pitch[win]) + 3 * x;
@@ -722,8 +739,11 @@ extern "C" EMF_API int emf_composite_merge(int n_parts, const emf_image* part_ra
                                    const emf_image* part_norm, const emf_image* part_seg, int n_obj, const int* ids,
                                    const emf_image* bg_ray, const emf_image* bg_vert, const emf_image* bg_norm,
                                    const emf_image* bg_mask, int boundary, const emf_image* ray, const emf_image* vert,
-                                   const emf_image* norm, const emf_image* seg, int32_t* vis_count, emf_stream_t stream) {
+                                   const emf_image* norm, const emf_image* seg, int32_t* vis_count, int band_rows,
+                                   const void* const* band_ray, const void* const* band_vert, const void* const* band_norm,
+                                   const void* const* band_mask, emf_stream_t stream) {
     if (n_parts <= 0 || n_parts > kMaxParts || n_obj < 0 || n_obj > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
+    if (band_rows < 0 || (band_rows > 0 && (!band_ray || !band_vert || !band_norm || !band_mask))) return EMF_ERR_INVALID;
     if (!part_ray || !part_vert || !part_norm || !part_seg || (n_obj > 0 && (!ids || !vis_count))) return EMF_ERR_INVALID;
     if (!image_ok(bg_ray, 4) || !image_ok(bg_vert, 12) || !image_ok(bg_norm, 12) || !image_ok(bg_mask, 1) ||
         !image_ok(ray, 4) || !image_ok(vert, 12) || !image_ok(norm, 12) || !image_ok(seg, 1))
@@ -743,10 +763,16 @@ extern "C" EMF_API int emf_composite_merge(int n_parts, const emf_image* part_ra
     for (int k = n_obj - 1; k >= 0; --k) P.lut[ids[k] > 255 ? 255 : (ids[k] < 0 ? 0 : ids[k])] = (int16_t)k;   // first in list wins a shared id
     P.lut[0] = -1;
     P.n_parts = n_parts; P.n_obj = n_obj; P.w = w; P.h = h; P.boundary = boundary;
-    P.bg_ray = (const float*)bg_ray->ptr; P.bg_ray_pitch = bg_ray->pitch;
-    P.bg_vert = (const float*)bg_vert->ptr; P.bg_vert_pitch = bg_vert->pitch;
-    P.bg_norm = (const float*)bg_norm->ptr; P.bg_norm_pitch = bg_norm->pitch;
-    P.bg_mask = (const uint8_t*)bg_mask->ptr; P.bg_mask_pitch = bg_mask->pitch;
+    P.bg_ray = (float*)bg_ray->ptr; P.bg_ray_pitch = bg_ray->pitch;
+    P.bg_vert = (float*)bg_vert->ptr; P.bg_vert_pitch = bg_vert->pitch;
+    P.bg_norm = (float*)bg_norm->ptr; P.bg_norm_pitch = bg_norm->pitch;
+    P.bg_mask = (uint8_t*)bg_mask->ptr; P.bg_mask_pitch = bg_mask->pitch;
+    P.band_rows = band_rows;
+    for (int p = 0; p < n_parts && band_rows > 0; ++p) {
+        if (!band_ray[p] || !band_vert[p] || !band_norm[p] || !band_mask[p]) return EMF_ERR_INVALID;
+        P.b_ray[p] = (const float*)band_ray[p]; P.b_vert[p] = (const float*)band_vert[p];
+        P.b_norm[p] = (const float*)band_norm[p]; P.b_mask[p] = (const uint8_t*)band_mask[p];
+    }
     P.o_ray = (float*)ray->ptr; P.o_ray_pitch = ray->pitch;
     P.o_vert = (float*)vert->ptr; P.o_vert_pitch = vert->pitch;
     P.o_norm = (float*)norm->ptr; P.o_norm_pitch = norm->pitch;

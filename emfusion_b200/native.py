@@ -66,6 +66,7 @@ class NativeEngine(EMFusionEngine):
         if self.replicate_background:
             rows = self.h // self.world
             check(L.emf_engine_set_background_rows(self._e, rank * rows, (rank + 1) * rows), "emf_engine_set_background_rows")
+        self._T = None
         self._stage = (C.c_float * 3)()
         self._counts = (C.c_int32 * _lib.EMF_MAX_VOLUMES)()
         self._sync_volumes()
@@ -125,14 +126,18 @@ class NativeEngine(EMFusionEngine):
                 check(self._L.emf_engine_force_integrate(self._e, i), "emf_engine_force_integrate")
         self._new_ids = set()
         self._dirty = False
+        self._T = None
+        self._gather_bufs = None
+        self._pk = None
 
     # ---- one call = some phases of a frame ----------------------------------------------------------------
     def _frame(self, flags: int, depth: Optional[torch.Tensor] = None):
         if self._dirty:
             self._sync_volumes()
         vols = self._keep
-        T_co, T_oc = rel_pose_arrays(self.pose, [v.pose for v in vols]) if vols else (np.zeros((1, 12), np.float32),) * 2
-        self._T = (T_co, T_oc)     # keep alive until the call returns
+        if self._T is None:     # relative poses of the frame (cleared whenever a pose may have changed)
+            self._T = rel_pose_arrays(self.pose, [v.pose for v in vols]) if vols else (np.zeros((1, 12), np.float32),) * 2
+        T_co, T_oc = self._T
         d = depth if depth is not None else self.depth
         check(self._L.emf_engine_frame(self._e, C.byref(ops.image(d)), T_co.ctypes.data_as(C.POINTER(Pose)),
                                        T_oc.ctypes.data_as(C.POINTER(Pose)), int(flags),
@@ -149,6 +154,7 @@ class NativeEngine(EMFusionEngine):
 
     def set_depth(self, depth: torch.Tensor):
         self.depth = depth
+        self._T = None          # a new frame: poses may have been reassigned by the caller
         self._frame(F_POINTS)
 
     def computeAssociationWeights(self):
@@ -172,11 +178,14 @@ class NativeEngine(EMFusionEngine):
 
     def _packed(self):
         """the pre-composite block [ray | vert | normals | seg] of the engine pool as one uint8 tensor (+ offsets)"""
+        if getattr(self, "_pk", None) is not None:
+            return self._pk
         p0 = self.raylengths.data_ptr()
         offs = (0, self.vertices.data_ptr() - p0, self.normals.data_ptr() - p0, self.modelSegmentation.data_ptr() - p0)
         size = offs[3] + self.h * self.w
         assert 0 < offs[1] < offs[2] < offs[3]
-        return torch.as_tensor(_DevMem(p0, (size,), "|u1"), device=self.device), offs, size
+        self._pk = (torch.as_tensor(_DevMem(p0, (size,), "|u1"), device=self.device), offs, size)
+        return self._pk
 
     def _composite_distributed(self):
         """gather of the per-rank pre-composites to rank 0 (one NCCL call), merge there (one launch, emf_composite_merge),
@@ -185,40 +194,51 @@ class NativeEngine(EMFusionEngine):
         h, w, dev = self.h, self.w, self.device
         packed, offs, size = self._packed()
         n_all = len(self.all_ids)
+        rows = h // self.world if self.replicate_background else 0
+        # send block: [ray | vert | normals | seg] of the pre-composite, then (replicated background) this rank's band of the
+        # background's raycast [ray | vert | normals | mask]
+        band_off = (0, rows * w * 4, rows * w * 16, rows * w * 28)
+        total = size + rows * w * 29
         g = self._gather_bufs
-        if g is None or g["size"] != size or g["n_all"] != n_all:
-            g = dict(size=size, n_all=n_all, counts=torch.zeros((max(n_all, 1),), dtype=torch.int32, device=dev),
-                     local=torch.tensor([self.all_ids.index(o.id) for o in self.objects], dtype=torch.int64, device=dev))
+        if g is None or g.get("total") != total or g["n_all"] != n_all:
+            g = dict(total=total, n_all=n_all, counts=torch.zeros((max(n_all, 1),), dtype=torch.int32, device=dev),
+                     local=torch.tensor([self.all_ids.index(o.id) for o in self.objects], dtype=torch.int64, device=dev),
+                     send=torch.empty((total,), dtype=torch.uint8, device=dev) if rows else None)
             if self.rank == 0:
-                g["all"] = torch.empty((self.world, size), dtype=torch.uint8, device=dev)
-                g["out"] = [torch.empty((h, w), dtype=torch.float32, device=dev), torch.empty((h, w, 3), dtype=torch.float32, device=dev),
-                            torch.empty((h, w, 3), dtype=torch.float32, device=dev), torch.empty((h, w), dtype=torch.uint8, device=dev)]
+                g["all"] = torch.empty((self.world, total), dtype=torch.uint8, device=dev)
+            if rows:
+                y0 = self.rank * rows
+                u8 = lambda t: t.reshape(-1).view(torch.uint8)
+                g["pieces"] = [packed, u8(self.bg_raylengths[y0:y0 + rows]), u8(self.bg_vertices[y0:y0 + rows]),
+                               u8(self.bg_normals[y0:y0 + rows]), u8(self.bg_mask[y0:y0 + rows])]
             self._gather_bufs = g
-        if self.replicate_background:
-            # bands of the background's raycast -> rank 0 (the band of rank r is rows [r h/N, (r+1) h/N))
-            rows = h // self.world
-            y0 = self.rank * rows
-            for img in (self.bg_raylengths, self.bg_vertices, self.bg_normals, self.bg_mask):
-                dst = list(img.reshape(self.world, -1).unbind(0)) if self.rank == 0 else None
-                dist.gather(img[y0:y0 + rows].reshape(-1), dst, dst=0, group=self.group)
-        if self.rank == 0:
-            dist.gather(packed, list(g["all"].unbind(0)), dst=0, group=self.group)
-            base = g["all"].data_ptr()
-            mk = lambda r, o, el: Image(base + r * size + o, w * el, w, h)
-            arr = lambda o, el: (Image * self.world)(*[mk(r, o, el) for r in range(self.world)])
-            ids = (C.c_int * max(n_all, 1))(*[int(i) for i in self.all_ids])
-            out = g["out"]
-            check(self._L.emf_composite_merge(self.world, arr(offs[0], 4), arr(offs[1], 12), arr(offs[2], 12), arr(offs[3], 1),
-                                              n_all, ids, ops.image(self.bg_raylengths), ops.image(self.bg_vertices),
-                                              ops.image(self.bg_normals), ops.image(self.bg_mask), int(self.params.boundary),
-                                              ops.image(out[0]), ops.image(out[1]), ops.image(out[2]), ops.image(out[3]),
-                                              g["counts"].data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
-                  "emf_composite_merge")
-            ops.LAUNCHES["compositeMerge"] = ops.LAUNCHES.get("compositeMerge", 0) + 1
-            # the merged composite replaces rank 0's pre-composite in the engine's frame images
-            self.raylengths.copy_(out[0]); self.vertices.copy_(out[1]); self.normals.copy_(out[2]); self.modelSegmentation.copy_(out[3])
+        if rows:
+            torch.cat(g["pieces"], out=g["send"])
+            send = g["send"]
         else:
-            dist.gather(packed, None, dst=0, group=self.group)
+            send = packed
+        if self.rank == 0:
+            if "args" not in g:     # everything the merge call needs is fixed until the volume list changes
+                base = g["all"].data_ptr()
+                mk = lambda r, o, el: Image(base + r * total + o, w * el, w, h)
+                arr = lambda o, el: (Image * self.world)(*[mk(r, o, el) for r in range(self.world)])
+                ptrs = lambda o: (C.c_void_p * self.world)(*[base + r * total + size + o for r in range(self.world)])
+                g["list"] = list(g["all"].unbind(0))
+                g["args"] = (self.world, arr(offs[0], 4), arr(offs[1], 12), arr(offs[2], 12), arr(offs[3], 1), n_all,
+                             (C.c_int * max(n_all, 1))(*[int(i) for i in self.all_ids]), ops.image(self.bg_raylengths),
+                             ops.image(self.bg_vertices), ops.image(self.bg_normals), ops.image(self.bg_mask),
+                             int(self.params.boundary),
+                             # the merged composite goes straight into the engine's frame images (rank 0's own pre-composite
+                             # has been copied into the gather buffer like everyone else's)
+                             ops.image(self.raylengths), ops.image(self.vertices), ops.image(self.normals),
+                             ops.image(self.modelSegmentation), g["counts"].data_ptr(), rows,
+                             ptrs(band_off[0]) if rows else None, ptrs(band_off[1]) if rows else None,
+                             ptrs(band_off[2]) if rows else None, ptrs(band_off[3]) if rows else None)
+            dist.gather(send, g["list"], dst=0, group=self.group)
+            check(self._L.emf_composite_merge(*g["args"], torch.cuda.current_stream(dev).cuda_stream), "emf_composite_merge")
+            ops.LAUNCHES["compositeMerge"] = ops.LAUNCHES.get("compositeMerge", 0) + 1
+        else:
+            dist.gather(send, None, dst=0, group=self.group)
         dist.broadcast(g["counts"], src=0, group=self.group)
         # this rank's objects, in its local list order, gate the integrate on the device
         if g["local"].numel():
@@ -264,6 +284,7 @@ class NativeEngine(EMFusionEngine):
             for o in self.objects:
                 if o.id in obj_poses:
                     o.pose = obj_poses[o.id]
+        self._T = None
         t = F_TIMED if timed else 0
         if self.frameCount == 0:
             self._frame(F_POINTS | F_INTEGRATE | F_INTEGRATE_ALL | t)

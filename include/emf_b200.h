@@ -204,12 +204,16 @@ EMF_API int emf_raycast_composite(int n_obj, const int* ids, const int* rects, c
  * and the n_parts results (ray / vert / norm / seg images, e.g. gathered with NCCL) are merged here, on the rank that
  * owns the background, in (raylength, list order) order -- the outcome of the reference's sequential loop over all
  * objects (src/core/EMFusion.cpp:760-771) -- followed by the background rule, the fill and the visibility counts
- * (:773-794).  ids: all n_obj objects in global list order; vis_count[n_obj] (device, zeroed by the call). */
+ * (:773-794).  ids: all n_obj objects in global list order; vis_count[n_obj] (device, zeroed by the call).
+ * band_rows > 0 (replicated background): rank p traced rows [p * band_rows, (p + 1) * band_rows) of the background;
+ * band_ray/vert/norm/mask[p] point at its band (continuous rows of W floats / 3 W floats / W bytes) and the bg_* images
+ * are assembled from the bands by this call (they are then outputs).  band_rows == 0: bg_* are complete inputs. */
 EMF_API int emf_composite_merge(int n_parts, const emf_image* part_ray, const emf_image* part_vert, const emf_image* part_norm,
                         const emf_image* part_seg, int n_obj, const int* ids, const emf_image* bg_ray,
                         const emf_image* bg_vert, const emf_image* bg_norm, const emf_image* bg_mask, int boundary,
                         const emf_image* ray, const emf_image* vert, const emf_image* norm, const emf_image* seg,
-                        int32_t* vis_count, emf_stream_t stream);
+                        int32_t* vis_count, int band_rows, const void* const* band_ray, const void* const* band_vert,
+                        const void* const* band_norm, const void* const* band_mask, emf_stream_t stream);
 
 /* emf::EMFusion::integrateDepth, src/core/EMFusion.cpp:865-889, one launch for all volumes.
  * T_oc[i] = cam_pose^-1 * pose_i; assoc[i] = that volume's association image. */
