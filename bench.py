@@ -307,7 +307,9 @@ def run_ours(args):
                                        "the frustum move 0 B, so frac can exceed 1); *_exact = bytes the kernel really has to move "
                                        "(16 B updated, 8 B newly-occluded, 4 B weight-only), from its own counters",
                          "counters": {"updated": int(c[0]), "marked_occluded": int(c[1]), "occluded_seen": int(c[2]),
-                                      "check_only": int(c[3]), "outside_image_in_interval": int(c[4])}})
+                                      "check_only": int(c[3]), "outside_image_in_interval": int(c[4]),
+                                      "voxels_on_exact_path": int(c[5]), "segments_decided_free": int(c[6]),
+                                      "segments_decided_occluded": int(c[7])}})
             del scratch
         out = {
             "metric": "Mvoxels/s (integrate+raycast+assoc)", "value": nvox / (ms_step * 1e-3) / 1e6, "unit": "Mvoxels/s",

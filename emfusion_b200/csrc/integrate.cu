@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
     const int warps_per_cta = kSegThreads / 32;
     const int gwarp = blockIdx.x * warps_per_cta + wid;
     const int n_warps = gridDim.x * warps_per_cta;
-    unsigned long long st[5] = {0, 0, 0, 0, 0};
+    unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [5] voxels on the exact path [6] / [7] segments decided free / occluded
     const float fw = (float)P.w, fh = (float)P.h;
 
     // Rows are handed out in batches of kRowBatch consecutive rows from a global counter (zeroed by k_depth_pyramid):
@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
             // ---- phase B: wholesale segments
             int known = 0;                 // voxels whose final tsdf value this lane knows
             float tv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (STATS) { if (cls == 1) ++st[6]; else if (cls == 2) ++st[7]; }
             if (cls == 1) {
                 float* wp = V.weights + row_off + x0;
                 float* tp = V.tsdf + row_off + x0;
@@ -609,6 +610,7 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
                     const int x = xbase + 4 * src + (k & 3);
                     float tfin = 2.0f;     // final tsdf of the voxel (2 = not a constant)
                     if (on) {
+                        if (STATS) ++st[5];
                         float* wp = V.weights + row_off + x;
                         float* tp = V.tsdf + row_off + x;
                         const float w = *wp;
@@ -634,6 +636,20 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
                                 if (!(d > 0.0f)) {
                                     if (w == 0.0f) { *tp = 0.0f; tfin = 0.0f; }
                                     if (STATS) ++st[3];
+                                } else if (d - pcz > fmaf(pcz, P.g_rel, band)) {
+                                    // clearly in front of the measurement (same guard as the segment test): free space
+                                    const float ws = fadd(w, 1.0f);
+                                    if (ws > 0.0f) {
+                                        const float num = ffma(w, tcur, 1.0f);
+                                        tcur = (num == ws && ws <= 3.0e38f) ? 1.0f : fdiv(num, ws);
+                                        *tp = tcur; *wp = fminf(ws, P.max_weight);
+                                        tfin = tcur;
+                                        if (STATS) ++st[0];
+                                    }
+                                } else if (pcz - d > fmaf(pcz, P.g_rel, band)) {
+                                    // clearly behind it: occluded
+                                    if (w == 0.0f) { *tp = -1.0f; tfin = -1.0f; if (STATS) ++st[1]; }
+                                    else if (STATS) ++st[2];
                                 } else {
                                     const float lx = s_tab[px], ly = s_tab[P.w + py];
                                     const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
@@ -700,7 +716,7 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
     }   // batches
     if (STATS && P.stats) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < 8; ++k) {
             unsigned long long v = st[k];
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
             if (lane == 0 && v) atomicAdd(P.stats + k, v);
