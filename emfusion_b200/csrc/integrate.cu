@@ -63,6 +63,7 @@ struct IntParams {
     const float2* pyr[kPyrLevels + 1];   // depth (min, max) pyramid, level l = tiles of 2^l pixels (k_integrate_seg); [0] unused
     int pyr_w[kPyrLevels + 1];           // tiles per row of level l
     int* work_counter;                   // k_integrate_seg: next batch of rows (zeroed by k_depth_pyramid)
+    const float* inv_lambda;             // k_integrate_seg: 1 / |((x-cx)/fx, (y-cy)/fy, 1)| per pixel, exact (k_depth_pyramid)
 };
 
 constexpr int kIntThreads = 256;
@@ -338,6 +339,8 @@ struct PyrParams {
     float2* lvl[kPyrLevels + 1];
     int lw[kPyrLevels + 1], lh[kPyrLevels + 1];
     int* work_counter;
+    float* inv_lambda;    // W x H, continuous
+    float fx, fy, cx, cy;
 };
 
 __global__ void __launch_bounds__(256) k_depth_pyramid(const __grid_constant__ PyrParams P) {
@@ -345,6 +348,15 @@ __global__ void __launch_bounds__(256) k_depth_pyramid(const __grid_constant__ P
     const int tx0 = blockIdx.x * 64, ty0 = blockIdx.y * 64;
     const int t = threadIdx.x;
     if (blockIdx.x == 0 && blockIdx.y == 0 && t == 0) *P.work_counter = 0;
+    // 1 / lambda of every pixel of this tile, by the canonical sequence of the reference kernel (TSDF.cu:376-380):
+    // lambda = sqrt(((x-cx)/fx)^2 + ((y-cy)/fy)^2 + 1), then its IEEE reciprocal
+    for (int i = t; i < 64 * 64; i += 256) {
+        const int x = tx0 + (i & 63), y = ty0 + (i >> 6);
+        if (x < P.w && y < P.h) {
+            const float lx = fdiv(fsub((float)x, P.cx), P.fx), ly = fdiv(fsub((float)y, P.cy), P.fy);
+            P.inv_lambda[(size_t)y * P.w + x] = frcp(fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f)));
+        }
+    }
     // level 1 straight from the image: thread -> 4 of the 32 x 32 level-1 tiles
     for (int i = t; i < 32 * 32; i += 256) {
         const int lx = i & 31, ly = i >> 5;
@@ -402,11 +414,7 @@ __global__ void __launch_bounds__(256) k_depth_pyramid(const __grid_constant__ P
 // ---------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_constant__ IntParams P) {
-    extern __shared__ float s_tab[];   // [0, w): (x - cx) / fx ; [w, w + h): (y - cy) / fy   (exact IEEE quotients)
     __shared__ uint8_t s_src[kSegThreads / 32][32];
-    for (int i = threadIdx.x; i < P.w + P.h; i += kSegThreads)
-        s_tab[i] = i < P.w ? fdiv(fsub((float)i, P.K[2]), P.K[0]) : fdiv(fsub((float)(i - P.w), P.K[5]), P.K[4]);
-    __syncthreads();
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warps_per_cta = kSegThreads / 32;
@@ -651,9 +659,7 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
                                     if (w == 0.0f) { *tp = -1.0f; tfin = -1.0f; if (STATS) ++st[1]; }
                                     else if (STATS) ++st[2];
                                 } else {
-                                    const float lx = s_tab[px], ly = s_tab[P.w + py];
-                                    const float lambda = fsqrt(fadd(ffma(lx, lx, fmul(ly, ly)), 1.0f));
-                                    const float inv_lambda = frcp(lambda);
+                                    const float inv_lambda = __ldg(P.inv_lambda + (size_t)py * P.w + px);   // exact, per pixel
                                     const float nrm = norm3(pcx, pcy, pcz);
                                     const float sdf = ffma(-nrm, inv_lambda, d);   // depth - (1/lambda)*|pc| as one FFMA (reference SASS)
                                     if (sdf >= ntrunc) {
@@ -805,6 +811,7 @@ size_t pyramid_layout(int w, int h, size_t off[kPyrLevels + 1], int lw[kPyrLevel
         off[l] = total;
         total += (((size_t)lw[l] * lh[l] * sizeof(float2)) + 255) & ~(size_t)255;
     }
+    total += (((size_t)w * h * sizeof(float)) + 255) & ~(size_t)255;   // 1 / lambda per pixel
     total += 256;   // work counter of k_integrate_seg (last 256 bytes)
     return total;
 }
@@ -868,7 +875,7 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
     {
         size_t off[kPyrLevels + 1]; int lw[kPyrLevels + 1], lh[kPyrLevels + 1];
         const size_t need = pyramid_layout(P.w, P.h, off, lw, lh);
-        if (workspace && workspace_bytes >= need && pin && table && ((uintptr_t)workspace & 15) == 0) {
+        if (workspace && workspace_bytes >= need && pin && ((uintptr_t)workspace & 15) == 0) {
             PyrParams Q;
             Q.depth = P.depth; Q.pitch = P.depth_pitch; Q.w = P.w; Q.h = P.h;
             P.pyr[0] = nullptr; P.pyr_w[0] = 0; Q.lvl[0] = nullptr; Q.lw[0] = 0; Q.lh[0] = 0;
@@ -878,25 +885,28 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
             }
             Q.work_counter = (int*)((char*)workspace + need - 256);
             P.work_counter = Q.work_counter;
+            Q.inv_lambda = (float*)((char*)workspace + need - 256 - ((((size_t)P.w * P.h * sizeof(float)) + 255) & ~(size_t)255));
+            P.inv_lambda = Q.inv_lambda;
+            Q.fx = K[0]; Q.fy = K[4]; Q.cx = K[2]; Q.cy = K[5];
             const dim3 pgrid((P.w + 63) / 64, (P.h + 63) / 64);
             k_depth_pyramid<<<pgrid, 256, 0, stream>>>(Q);
             static int occ_s = 0, occ_n = 0;
             int& occ = stats ? occ_s : occ_n;
             if (occ == 0) {
-                if (stats) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_seg<true>, kSegThreads, smem);
-                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_seg<false>, kSegThreads, smem);
+                if (stats) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_seg<true>, kSegThreads, 0);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate_seg<false>, kSegThreads, 0);
                 if (occ <= 0) occ = 2;
             }
             int64_t blocks = (int64_t)sm_count() * occ;
             const int64_t min_blocks = (items + kSegThreads / 32 - 1) / (kSegThreads / 32);
             if (blocks > min_blocks) blocks = min_blocks;
-            if (stats) k_integrate_seg<true><<<(unsigned)blocks, kSegThreads, smem, stream>>>(P);
-            else k_integrate_seg<false><<<(unsigned)blocks, kSegThreads, smem, stream>>>(P);
+            if (stats) k_integrate_seg<true><<<(unsigned)blocks, kSegThreads, 0, stream>>>(P);
+            else k_integrate_seg<false><<<(unsigned)blocks, kSegThreads, 0, stream>>>(P);
             return launch_status();
         }
     }
     for (int l = 0; l <= kPyrLevels; ++l) { P.pyr[l] = nullptr; P.pyr_w[l] = 0; }
-    P.work_counter = nullptr;
+    P.work_counter = nullptr; P.inv_lambda = nullptr;
     const dim3 block(kIntThreads);
     // persistent grid: every SM filled to the kernel's occupancy, rows dealt round-robin to warps
 #define EMF_LAUNCH_ROWS(PIN, TAB)                                                                          \
