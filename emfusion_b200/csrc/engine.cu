@@ -36,6 +36,8 @@ struct emf_engine {
     int32_t* vis_host = nullptr;       // pinned
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t vis_ready = nullptr;
+    cudaStream_t aux = nullptr;        // the association runs here, next to the raycast (both only read the volumes)
+    cudaEvent_t fork = nullptr, join = nullptr;
     bool timed_valid = false;
 };
 
@@ -80,6 +82,9 @@ extern "C" EMF_API emf_engine* emf_engine_create(const emf_engine_config* cfg) {
     bool ok = cudaMallocHost((void**)&e->vis_host, sizeof(int32_t) * EMF_MAX_VOLUMES) == cudaSuccess;
     for (int k = 0; k < 5 && ok; ++k) ok = cudaEventCreate(&e->ev[k]) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->vis_ready, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { emf_engine_destroy(e); return nullptr; }
     for (int k = 0; k < EMF_MAX_VOLUMES; ++k) e->vis_host[k] = 0;
     return e;
@@ -91,6 +96,9 @@ extern "C" EMF_API void emf_engine_destroy(emf_engine* e) {
     if (e->vis_host) cudaFreeHost(e->vis_host);
     for (int k = 0; k < 5; ++k) if (e->ev[k]) cudaEventDestroy(e->ev[k]);
     if (e->vis_ready) cudaEventDestroy(e->vis_ready);
+    if (e->fork) cudaEventDestroy(e->fork);
+    if (e->join) cudaEventDestroy(e->join);
+    if (e->aux) cudaStreamDestroy(e->aux);
     delete e;
 }
 
@@ -159,6 +167,7 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
     cudaStream_t s = (cudaStream_t)stream;
     const bool timed = (flags & EMF_FRAME_TIMED) != 0;
     int rc = EMF_OK;
+    bool overlap = false;
     e->timed_valid = false;
     if (flags & EMF_FRAME_POINTS) {
         if (!emfb::image_ok(depth, 4) || depth->width != w || depth->height != h) return EMF_ERR_INVALID;
@@ -169,8 +178,17 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
     if ((flags & (EMF_FRAME_ASSOC | EMF_FRAME_ASSOC_PARTIAL | EMF_FRAME_ASSOC_PARTIAL_NOBG)) && n > 0) {
         if (!T_co) return EMF_ERR_INVALID;
         const int mode = (flags & EMF_FRAME_ASSOC_PARTIAL_NOBG) ? (e->has_bg ? 3 : 1) : ((flags & EMF_FRAME_ASSOC_PARTIAL) ? 1 : 0);
-        rc = emf_assoc_weights(n, e->vols.data(), T_co, &e->points, &e->cfg.params, e->a_img.data(), mode, &e->norm, stream);
+        // association and raycast of one call only read the volumes and write disjoint images: when both are asked for
+        // (and no stage timing is wanted) the association runs on a side stream and is joined before the integrate
+        overlap = mode == 0 && (flags & EMF_FRAME_RAYCAST) && !timed;
+        if (overlap) {
+            cudaEventRecord(e->fork, s);
+            cudaStreamWaitEvent(e->aux, e->fork, 0);
+        }
+        rc = emf_assoc_weights(n, e->vols.data(), T_co, &e->points, &e->cfg.params, e->a_img.data(), mode, &e->norm,
+                               overlap ? (emf_stream_t)e->aux : stream);
         if (rc != EMF_OK) return rc;
+        if (overlap) cudaEventRecord(e->join, e->aux);
     } else if ((flags & (EMF_FRAME_ASSOC_PARTIAL | EMF_FRAME_ASSOC_PARTIAL_NOBG)) && n == 0) {
         cudaMemsetAsync(e->norm.ptr, 0, e->norm.pitch * h, s);
     }
@@ -215,6 +233,7 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
             cudaEventRecord(e->vis_ready, s);
         }
     }
+    if (overlap) cudaStreamWaitEvent(s, e->join, 0);   // (also when no integrate follows: the caller sees one stream)
     if (timed) cudaEventRecord(e->ev[2], s);
     if ((flags & EMF_FRAME_INTEGRATE) && n > 0) {
         if (!T_oc || !emfb::image_ok(depth, 4)) return EMF_ERR_INVALID;
