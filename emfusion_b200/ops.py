@@ -208,6 +208,8 @@ def volumeScreenRect(volumeRes, voxelSize, rel_pose_CO: Affine, intr, width, hei
 
 
 def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out, mask_out, stream=None, stats=None):
+    if stats is not None and (stats.numel() < 4 or stats.element_size() != 8):
+        raise _lib.EmfError("raycast stats must be a tensor of at least 4 64-bit counters")
     flat = (C.c_int * (4 * len(vols)))(*[int(v) for r in rects for v in r]) if rects is not None else None
     check(_lib.lib().emf_raycast_volumes(len(vols), _vol_array(vols), poses(rel_poses_CO), _f9(intr), flat,
                                          images(ray_out), images(vert_out), images(norm_out), images(mask_out),
@@ -246,8 +248,10 @@ def integrateWorkspace(depth):
 def integrateVolumes(vols, rel_poses_OC, intr, depth, assoc, maxWeight, stream=None, gate_counts=None, gates=None,
                      gate_thresh=0, stats=None, workspace="auto"):
     """gate_counts (int32 CUDA tensor) + gates (per-volume index or -1): device-side visibility filter;
-    stats: optional uint64/int64 CUDA tensor of 5 counters (accumulated);
+    stats: optional uint64/int64 CUDA tensor of 8 counters (accumulated; see include/emf_b200.h);
     workspace: "auto" (cached depth-pyramid workspace -> segment-level kernel), None (per-voxel kernel) or a uint8 tensor."""
+    if stats is not None and (stats.numel() < 8 or stats.element_size() != 8):
+        raise _lib.EmfError("integrate stats must be a tensor of at least 8 64-bit counters")
     if workspace == "auto":
         workspace = integrateWorkspace(depth)
     if workspace is not None:

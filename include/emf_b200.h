@@ -226,9 +226,10 @@ EMF_API int emf_integrate_volumes(int n_vol, const emf_volume* vols, const emf_p
  * gate_counts[gates[i]] > gate_thresh, read ON THE DEVICE -- gate_counts is the vis_count array that
  * emf_raycast_composite wrote earlier on the same stream, so the visibility filter of
  * emf::EMFusion::integrateDepth (src/core/EMFusion.cpp:869-872) needs no device->host round trip.
- * stats (optional, 5 x uint64 on the device, accumulated): voxels updated, marked occluded-unseen (-1),
+ * stats (optional, 8 x uint64 on the device, accumulated): voxels updated, marked occluded-unseen (-1),
  * occluded but already seen, check-only (behind camera / invalid depth), projected outside the image inside
- * the culling interval -- the exact-bytes roofline numerator. */
+ * the culling interval -- the exact-bytes roofline numerator -- and, from the segment-level kernel only: voxels that took
+ * the exact per-voxel path, segments decided free, segments decided occluded. */
 EMF_API int emf_integrate_volumes_gated(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
                                 const emf_image* depth, const emf_image* assoc, float max_weight,
                                 const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,

@@ -45,7 +45,7 @@ def test_integrate_random_poses_bit_exact(oracle, cuda_dev, res):
     cbits = torch.zeros((3 * ops.bitmapWords(res),), dtype=torch.int32, device=DEV)
     ops.resetBitmaps(ops.volume(t_g, w_g, res, voxel, trunc, const_bits=cbits))
     rng = np.random.default_rng(1)
-    stats = torch.zeros(5, dtype=torch.int64, device=DEV)
+    stats = torch.zeros(8, dtype=torch.int64, device=DEV)
     tot = np.zeros(6, np.int64)
     for k, cam in enumerate(random_poses(8, 3)):
         depth, _ = scene.render(k)
