@@ -17,6 +17,7 @@ EMF_ERR_INVALID = -1
 EMF_ERR_CUDA = -2
 EMF_ERR_UNSUPPORTED = -3
 EMF_MAX_VOLUMES = 96
+EMF_TRACK_RECORD = 48
 
 
 class EmfError(RuntimeError):
@@ -87,9 +88,13 @@ _SIGS = {
                                  C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_update_brick_maps": [C.c_int, _P(Volume), C.c_void_p],
     "emf_reset_bitmaps": [_P(Volume), C.c_void_p],
+    "emf_track_workspace_init": [C.c_void_p, C.c_size_t, C.c_void_p],
+    "emf_track_linearise": [C.c_int, _P(Volume), _P(Pose), _P(C.c_int), _P(Image), _P(Image), C.c_float, C.c_float,
+                            _P(Image), _P(Image), _P(Image), _P(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    "emf_track_normalised_weights": [_P(Image), C.c_void_p, _P(Image), C.c_void_p],
     "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],
 }
-EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes", "emf_integrate_workspace_bytes", "emf_engine_create", "emf_engine_destroy",
+EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes", "emf_track_workspace_bytes", "emf_integrate_workspace_bytes", "emf_engine_create", "emf_engine_destroy",
                                 "emf_engine_vis_counts_device"])
 
 _lib = None
@@ -111,6 +116,8 @@ def lib() -> C.CDLL:
             fn.restype = C.c_int
         L.emf_integrate_workspace_bytes.argtypes = [C.c_int, C.c_int]
         L.emf_integrate_workspace_bytes.restype = C.c_size_t
+        L.emf_track_workspace_bytes.argtypes = [C.c_int]
+        L.emf_track_workspace_bytes.restype = C.c_size_t
         L.emf_brick_map_bytes.argtypes = [_P(C.c_int)]
         L.emf_brick_map_bytes.restype = C.c_size_t
         L.emf_engine_create.argtypes = [_P(EngineConfig)]

@@ -22,7 +22,7 @@ LAUNCHES = {}
 _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1, "raycastTSDF": 1, "getVolumeVals": 1,
                      "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
                      "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
-                     "updateBrickMaps": 2}
+                     "updateBrickMaps": 2, "trackLinearise": 1, "trackNormalisedWeights": 1}
 
 
 def _count(name: str) -> None:
@@ -294,3 +294,55 @@ def resetBitmaps(vol: Volume, stream=None):
 def bitmapWords(res) -> int:
     """32-bit words of ONE segment bitmap of a volume (emf_bitmap_words_per_row(Rx) * Ry * Rz)."""
     return ((int(res[0]) // 4 + 31) // 32) * int(res[1]) * int(res[2])
+
+
+# ---- tracker ----------------------------------------------------------------------------------
+_TRACK_WS = {}
+
+
+def trackWorkspace(device, n_vol: int):
+    """cached, once-zeroed device workspace of emf_track_linearise for up to n_vol volumes"""
+    key = device
+    ws = _TRACK_WS.get(key)
+    need = int(_lib.lib().emf_track_workspace_bytes(int(n_vol)))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty((int(_lib.lib().emf_track_workspace_bytes(_lib.EMF_MAX_VOLUMES)),), dtype=torch.uint8, device=device)
+        check(_lib.lib().emf_track_workspace_init(ws.data_ptr(), ws.numel(), _stream()), "trackWorkspaceInit")
+        _TRACK_WS[key] = ws
+    return ws
+
+
+def _opt_images(ts, n):
+    """array of n emf_image; entries for None tensors have ptr == NULL"""
+    if ts is None:
+        return None
+    arr = (Image * n)()
+    for i, t in enumerate(ts):
+        arr[i] = image(t) if t is not None else Image(None, 0, 0, 0)
+    return arr
+
+
+def trackLinearise(vols, rel_poses_CO, modes, points, assoc, huberThresh, maxTSDFWeight, intWeights, records,
+                   tsdfVals=None, trackWeights=None, poseGrads=None, stream=None):
+    """One launch = the device part of one tracker iteration of every volume (emf_track_linearise, include/emf_b200.h).
+    modes[i]: 0 skip / 1 linearise / 2 error only; records: (n_vol, 48) float32 CUDA tensor."""
+    n = len(vols)
+    if records.dtype != torch.float32 or records.numel() < n * _lib.EMF_TRACK_RECORD or not records.is_contiguous():
+        raise _lib.EmfError("records must be a contiguous float32 CUDA tensor of n_vol x 48")
+    ws = trackWorkspace(points.device, n)
+    m = (C.c_int * n)(*[int(x) for x in modes])
+    pg = None
+    if poseGrads is not None:
+        pg = (C.c_void_p * n)(*[(_ptr(g) if g is not None else None) for g in poseGrads])
+    check(_lib.lib().emf_track_linearise(n, _vol_array(vols), poses(rel_poses_CO), m, image(points), _opt_images(assoc, n),
+                                         float(huberThresh), float(maxTSDFWeight), _opt_images(intWeights, n),
+                                         _opt_images(tsdfVals, n), _opt_images(trackWeights, n), pg, _ptr(records),
+                                         ws.data_ptr(), ws.numel(), _stream(stream)), "trackLinearise")
+    if any(int(x) for x in modes):
+        _count("trackLinearise")
+
+
+def trackNormalisedWeights(intWeights, record, out, stream=None):
+    check(_lib.lib().emf_track_normalised_weights(image(intWeights), _ptr(record), image(out), _stream(stream)),
+          "trackNormalisedWeights")
+    _count("trackNormalisedWeights")

@@ -267,6 +267,42 @@ EMF_API int emf_volume_screen_rect(const int res[3], float voxel_size, const emf
 EMF_API int emf_fill_image_f32(const emf_image* img, float value, emf_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Tracker: the device part of one Levenberg-Marquardt iteration of
+ * emf::TSDF's SDF tracker for a batch of volumes in one launch.
+ *
+ * Replaces, per volume and iteration, TSDF::computeGradients / computeTSDFVals / computeTSDFWeights /
+ * computeHuberWeights / normalizeTSDFWeights / combineWeights / computeHessians / reduceHessians' device part /
+ * computeError (src/core/TSDF.cpp:194-265, 375-394): emf::cuda::TSDF::computePoseGradients, getVolumeVals x 2,
+ * computeAb, multSingletonCol x 2 (include/EMFusion/core/cuda/TSDF.cuh:181-253) and ~12 OpenCV-CUDA launches.
+ *
+ * modes[i]: 0 = leave volume i alone (converged), 1 = linearise at T_co[i] (evaluateGradient), 2 = error only
+ * (the trial pose of TSDF::computePoseUpdate, src/core/TSDF.cpp:312-315, or an iteration with evaluateGradient false).
+ * Per volume i:
+ *   assoc[i]        in  (mode 1)  association weights of the volume (W x H f32)
+ *   int_weights[i]  mode 1: out, mode 2: in -- Huber x min(w, max) x assoc per pixel, BEFORE the NORM_INF scale
+ *                   (the reference's intWeights = this x records[i][44]; emf_track_normalised_weights forms it)
+ *   tsdf_vals[i]    out, optional (array or entry.ptr NULL): tsdfVals
+ *   track_weights[i] out, optional, mode 1: trackWeights (Huber)
+ *   pose_grads[i]   out, optional, mode 1: `grads`, W*H x 6 floats continuous (bit-identical to the reference's)
+ *   records + i * EMF_TRACK_RECORD (device floats): [0..35] A row-major 6x6, [36..41] b, [42] error
+ *                   sum f^2 w, [43] max of the clamped integration weights, [44] the NORM_INF scale.
+ *                   Mode 1 writes all of it; mode 2 only [42], using the stored scale and int_weights.
+ * workspace: emf_track_workspace_bytes(n_vol) bytes of device memory (16-byte aligned) that was zeroed ONCE with
+ * emf_track_workspace_init; the call leaves it ready for the next one.  Sums are folded in a fixed order:
+ * the same inputs give the same bits. */
+#define EMF_TRACK_RECORD 48
+EMF_API size_t emf_track_workspace_bytes(int n_vol);
+EMF_API int emf_track_workspace_init(void* workspace, size_t workspace_bytes, emf_stream_t stream);
+EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, const emf_pose* T_co, const int* modes,
+                        const emf_image* points, const emf_image* assoc, float huber_thresh, float max_tsdf_weight,
+                        const emf_image* int_weights, const emf_image* tsdf_vals, const emf_image* track_weights,
+                        float* const* pose_grads, float* records, void* workspace, size_t workspace_bytes,
+                        emf_stream_t stream);
+/* out <- int_weights x record[44]: intWeights as emf::TSDF::getTrackingWeights sees it (src/core/TSDF.cpp:340-343). */
+EMF_API int emf_track_normalised_weights(const emf_image* int_weights, const float* record, const emf_image* out,
+                                 emf_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Level 4: the native frame engine -- one host call per frame.
  *
  * emf::EMFusion::processFrame's hot part (src/core/EMFusion.cpp:76-103 minus tracking and Mask R-CNN):

@@ -525,6 +525,86 @@ EMFO_API void emfo_raycast_weights(const float* weights, const uint8_t* fg_vol_m
     for (int64_t i = 0; i < n_vox; ++i) out[i] = fg_vol_mask[i] ? weights[i] : 0.0f;
 }
 
+/* ------------------------------------------------------------------------
+ * Tracker: the device part of one Levenberg-Marquardt iteration of emf::TSDF,
+ * op by op as the reference chains it (src/core/TSDF.cpp:194-265, 375-394):
+ *   grads        kernel_computePoseGradients  src/core/cuda/TSDF.cu:603-638 (after setTo(0); "xyz" contraction,
+ *                gradient = trilinear of the float3 tsdfGrads volume / voxelSize, [p]x g with the build's contractions)
+ *   tsdfVals     getVolumeVals(tsdfVol)       src/core/cuda/TSDF.cu:662-688
+ *   intWeights   getVolumeVals(tsdfWeights); min(., maxTSDFWeight); normalize(NORM_INF): x * (float)(1/max|x|)
+ *   trackWeights min(huberThresh / |tsdfVals|, 1) with cv::cuda::divide's x/0 = 0
+ *   intWeights   = trackWeights * intWeights * associationWeights   (two multiplies)
+ *   As, bs       kernel_computeAb :729-751, multSingletonCol by intWeights :821-853
+ *   A, b         column sums (cv::cuda::reduce; here in double -- the reference's float order is unspecified)
+ *   error        sum(tsdfVals^2 * intWeights) (cv::cuda::sum accumulates in double)
+ * Outputs: grads6 (n x 6), tsdf_vals, int_weights, track_weights (n each), A[36], b[6], err, wmax -- doubles for the sums.
+ * ---------------------------------------------------------------------- */
+EMFO_API void emfo_track_linearise(const float* tsdf, const float* grads_vol, const float* weights, const float* points,
+                                   const float* assoc, int w, int h, const float* R, const float* t, const int* res,
+                                   float voxel, float huber, float maxw, float* grads6, float* tsdf_vals,
+                                   float* int_weights, float* track_weights, double* A, double* b, double* err,
+                                   double* wmax_out) {
+    const int rx = res[0], ry = res[1], rz = res[2];
+    const float frx = (float)rx, fry = (float)ry, frz = (float)rz;
+    const int n = w * h;
+    float wmax = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        float* g = grads6 + 6 * (size_t)i;
+        for (int k = 0; k < 6; ++k) g[k] = 0.0f;
+        tsdf_vals[i] = 0.0f; int_weights[i] = 0.0f;
+        const float* p = points + 3 * (size_t)i;
+        if (!(p[2] <= 0.0f)) {
+            const float qx = t[0] + dot_xyz(R + 0, p[0], p[1], p[2]);
+            const float qy = t[1] + dot_xyz(R + 3, p[0], p[1], p[2]);
+            const float qz = t[2] + dot_xyz(R + 6, p[0], p[1], p[2]);
+            const float vx = (float)(rx - 1) * 0.5f + qx / voxel;
+            const float vy = (float)(ry - 1) * 0.5f + qy / voxel;
+            const float vz = (float)(rz - 1) * 0.5f + qz / voxel;
+            if (!out_of(vx, vy, vz, 1.0f, frx, fry, frz)) {
+                tsdf_vals[i] = trilinear(tsdf, rx, ry, vx, vy, vz);
+                int_weights[i] = trilinear(weights, rx, ry, vx, vy, vz);
+            }
+            if (!out_of(vx, vy, vz, 2.0f, frx, fry, frz)) {
+                float gi[3];
+                trilinear3(grads_vol, rx, ry, vx, vy, vz, gi);
+                g[0] = gi[0] / voxel; g[1] = gi[1] / voxel; g[2] = gi[2] / voxel;
+                g[3] = FMA(qy, g[2], -(qz * g[1]));
+                g[4] = FMA(-qx, g[2], qz * g[0]);      /* contraction as in the SASS of the reference build */
+                g[5] = FMA(qx, g[1], -(qy * g[0]));
+            }
+        }
+        const float af = fabsf(tsdf_vals[i]);
+        float tw = af != 0.0f ? huber / af : 0.0f;
+        track_weights[i] = tw < 1.0f ? tw : 1.0f;
+        int_weights[i] = int_weights[i] < maxw ? int_weights[i] : maxw;
+        if (fabsf(int_weights[i]) > wmax) wmax = fabsf(int_weights[i]);
+    }
+    const double nrm = (double)wmax;
+    const float scale = nrm > 2.220446049250313e-16 ? (float)(1.0 / nrm) : 0.0f;
+    for (int k = 0; k < 36; ++k) A[k] = 0.0;
+    for (int k = 0; k < 6; ++k) b[k] = 0.0;
+    double e = 0.0;
+    for (int i = 0; i < n; ++i) {
+        float iw = int_weights[i] * scale;
+        iw = track_weights[i] * iw;
+        iw = iw * assoc[i];
+        int_weights[i] = iw;
+        const float* g = grads6 + 6 * (size_t)i;
+        for (int a = 0; a < 6; ++a) {
+            for (int c = 0; c < 6; ++c) {
+                const float as = g[a] * g[c];
+                A[a * 6 + c] += (double)(as * iw);
+            }
+            const float bs = tsdf_vals[i] * g[a];
+            b[a] += (double)(bs * iw);
+        }
+        const float sq = tsdf_vals[i] * tsdf_vals[i];
+        e += (double)(sq * iw);
+    }
+    *err = e;
+    if (wmax_out) *wmax_out = nrm;
+}
+
 EMFO_API int emfo_uses_fma(void) {
 #ifdef EMFO_NOFMA
     return 0;

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include <set>
 #include <cvshim.hpp>
@@ -414,5 +415,169 @@ REF_API int emfref_compute_points(const float* depth, float* points, int w, int 
     dim3 threads(32, 32), blocks((w + 31) / 32, (h + 31) / 32);
     k_ref_points<<<blocks, threads>>>(depth, points, w, h, K[0], K[4], K[2], K[5]);
     cudaDeviceSynchronize();
+    return status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. tracker: the device part of one iteration of emf::TSDF's Levenberg-Marquardt loop, as
+//    emf::EMFusion::performTracking drives it (src/core/EMFusion.cpp:672-722): the reference kernels
+//    (computePoseGradients, getVolumeVals x 2, computeAb, multSingletonCol x 2) + the OpenCV-CUDA ops between them,
+//    one launch per op, on the four streams and events of src/core/TSDF.cpp:194-265,375-394.
+// ------------------------------------------------------------------------------------------------
+namespace cvk {
+#define IDX size_t i = (size_t)blockIdx.x * T + threadIdx.x; if (i >= n) return;
+__global__ void k_abs_to(const float* a, size_t n, float* d) { IDX d[i] = fabsf(a[i]); }
+// cv::cuda::divide(scalar, mat): scalar / a, 0 where a == 0
+__global__ void k_sdiv(float s, const float* a, size_t n, float* d) { IDX d[i] = a[i] != 0.f ? __fdiv_rn(s, a[i]) : 0.f; }
+__global__ void k_min_s(const float* a, size_t n, float v, float* d) { IDX d[i] = fminf(a[i], v); }
+__global__ void k_sqr(const float* a, size_t n, float* d) { IDX d[i] = __fmul_rn(a[i], a[i]); }
+__global__ void k_absmax(const float* a, size_t n, unsigned* out) {   // NORM_INF of a float image (bit pattern of |x| is monotone)
+    IDX atomicMax(out, __float_as_uint(fabsf(a[i])));
+}
+#undef IDX
+// cv::cuda::reduce(src, dst, 0, REDUCE_SUM): column sums of a rows x cols float matrix, float accumulation
+__global__ void k_colsum(const float* a, size_t rows, int cols, float* out) {
+    __shared__ float s[256];
+    const int c = blockIdx.x;
+    float acc = 0.f;
+    for (size_t r = threadIdx.x; r < rows; r += 256) acc = __fadd_rn(acc, a[r * cols + c]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) s[threadIdx.x] = __fadd_rn(s[threadIdx.x], s[threadIdx.x + o]); __syncthreads(); }
+    if (threadIdx.x == 0) out[c] = s[0];
+}
+// cv::cuda::sum: double accumulation
+__global__ void k_sum_d(const float* a, size_t n, double* out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) acc += (double)a[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) atomicAdd(out, s[0]);
+}
+}  // namespace cvk
+
+struct RefTracker {   // the tracking members of emf::TSDF (include/EMFusion/core/TSDF.h:302-326)
+    int w, h; size_t n;
+    float *grads, *tsdfVals, *intWeights, *trackWeights, *As, *bs, *A_gpu, *b_gpu, *errors;
+    unsigned* d_max; double* d_sum;
+    cudaStream_t streams[4];
+    cudaEvent_t events[5];
+};
+
+REF_API void* emfref_tracker_create(int w, int h) {
+    RefTracker* K = new RefTracker();
+    K->w = w; K->h = h; K->n = (size_t)w * h;
+    K->grads = dalloc<float>(6 * K->n); K->tsdfVals = dalloc<float>(K->n); K->intWeights = dalloc<float>(K->n);
+    K->trackWeights = dalloc<float>(K->n); K->As = dalloc<float>(36 * K->n); K->bs = dalloc<float>(6 * K->n);
+    K->A_gpu = dalloc<float>(36); K->b_gpu = dalloc<float>(6); K->errors = dalloc<float>(K->n);
+    K->d_max = dalloc<unsigned>(1); K->d_sum = dalloc<double>(1);
+    for (auto& s : K->streams) cudaStreamCreate(&s);
+    for (auto& e : K->events) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaDeviceSynchronize();
+    return K;
+}
+REF_API void emfref_tracker_destroy(void* h) {
+    RefTracker* K = (RefTracker*)h;
+    cudaFree(K->grads); cudaFree(K->tsdfVals); cudaFree(K->intWeights); cudaFree(K->trackWeights); cudaFree(K->As);
+    cudaFree(K->bs); cudaFree(K->A_gpu); cudaFree(K->b_gpu); cudaFree(K->errors); cudaFree(K->d_max); cudaFree(K->d_sum);
+    for (auto& s : K->streams) cudaStreamDestroy(s);
+    for (auto& e : K->events) cudaEventDestroy(e);
+    delete K;
+}
+REF_API float* emfref_tracker_ptr(void* h, int what) {
+    RefTracker* K = (RefTracker*)h;
+    float* p[] = {K->grads, K->tsdfVals, K->intWeights, K->trackWeights, K->As, K->bs, K->A_gpu, K->b_gpu};
+    return what >= 0 && what < 8 ? p[what] : nullptr;
+}
+
+// TSDF::computeError (src/core/TSDF.cpp:390-394): blocking
+static float ref_compute_error(RefTracker* K) {
+    using namespace cvk;
+    k_sqr<<<nb(K->n), T>>>(K->tsdfVals, K->n, K->errors);
+    k_mul<<<nb(K->n), T>>>(K->errors, K->intWeights, K->n, K->errors);
+    cudaMemsetAsync(K->d_sum, 0, 8, nullptr);
+    k_sum_d<<<296, 256>>>(K->errors, K->n, K->d_sum);
+    double s = 0;
+    cudaMemcpy(&s, K->d_sum, 8, cudaMemcpyDeviceToHost);
+    return (float)s;
+}
+
+// One gradient-evaluating iteration up to and including reduceHessians' downloads (A, b on the host) and the
+// err = computeError() of computePoseUpdate.  A_out[36], b_out[6], err_out on the host.
+REF_API int emfref_tracker_linearise(void* h, const float* tsdf, const float* grads_vol, const float* weights,
+                                     const float* points, const float* assoc, const float* R, const float* t,
+                                     const int* res, float voxel, float huber, float maxw, float* A_out, float* b_out,
+                                     float* err_out) {
+    using namespace cvk;
+    RefTracker* K = (RefTracker*)h;
+    const size_t n = K->n;
+    cudaStream_t* s = K->streams;
+    Stream st0(s[0]), st1(s[1]), st2(s[2]);
+    GpuMat tv = mat((void*)tsdf, res[1] * res[2], res[0], CV_32FC1), gv = mat((void*)grads_vol, res[1] * res[2], res[0], CV_32FC3),
+           wv = mat((void*)weights, res[1] * res[2], res[0], CV_32FC1);
+    GpuMat p = mat((void*)points, K->h, K->w, CV_32FC3);
+    GpuMat g = mat(K->grads, (int)n, 6, CV_32FC1), tvals = mat(K->tsdfVals, K->h, K->w, CV_32FC1),
+           iw = mat(K->intWeights, K->h, K->w, CV_32FC1);
+    GpuMat As = mat(K->As, (int)n, 36, CV_32FC1), bs = mat(K->bs, (int)n, 6, CV_32FC1);
+    // computeGradients / computeTSDFVals / computeTSDFWeights (src/core/TSDF.cpp:194-221)
+    emf::cuda::TSDF::computePoseGradients(gv, p, m33(R), v3(t), v3i(res), voxel, g, st0);
+    emf::cuda::TSDF::getVolumeVals(tv, p, m33(R), v3(t), v3i(res), voxel, tvals, st1);
+    cudaEventRecord(K->events[1], s[1]);
+    emf::cuda::TSDF::getVolumeVals(wv, p, m33(R), v3(t), v3i(res), voxel, iw, st2);
+    // computeHuberWeights (:223-232)
+    cudaStreamWaitEvent(s[3], K->events[1], 0);
+    k_abs_to<<<nb(n), T, 0, s[3]>>>(K->tsdfVals, n, K->trackWeights);
+    k_sdiv<<<nb(n), T, 0, s[3]>>>(huber, K->trackWeights, n, K->trackWeights);
+    k_min_s<<<nb(n), T, 0, s[3]>>>(K->trackWeights, n, 1.0f, K->trackWeights);
+    // normalizeTSDFWeights (:234-242): min, normalize(alpha = 1, NORM_INF) = norm (blocking read) + convertTo(scale)
+    k_min_s<<<nb(n), T, 0, s[2]>>>(K->intWeights, n, maxw, K->intWeights);
+    cudaMemsetAsync(K->d_max, 0, 4, s[2]);
+    k_absmax<<<nb(n), T, 0, s[2]>>>(K->intWeights, n, K->d_max);
+    unsigned mx = 0;
+    cudaMemcpyAsync(&mx, K->d_max, 4, cudaMemcpyDeviceToHost, s[2]);
+    cudaStreamSynchronize(s[2]);
+    float fmx; memcpy(&fmx, &mx, 4);
+    const double nrm = (double)fmx;
+    const float scale = nrm > 2.220446049250313e-16 ? (float)(1.0 / nrm) : 0.f;
+    k_mul_s<<<nb(n), T, 0, s[2]>>>(K->intWeights, n, scale, K->intWeights);
+    cudaEventRecord(K->events[2], s[2]);
+    // combineWeights (:244-255)
+    cudaStreamWaitEvent(s[3], K->events[2], 0);
+    k_mul<<<nb(n), T, 0, s[3]>>>(K->trackWeights, K->intWeights, n, K->intWeights);
+    k_mul<<<nb(n), T, 0, s[3]>>>(K->intWeights, assoc, n, K->intWeights);
+    cudaEventRecord(K->events[3], s[3]);
+    // computeHessians (:257-265); events[4] is never recorded in the reference, so the wait is a no-op
+    emf::cuda::TSDF::computeAb(g, tvals, As, bs, st0);
+    cudaEventRecord(K->events[0], s[0]);
+    // reduceAb (:375-388)
+    cudaStreamWaitEvent(s[0], K->events[3], 0);
+    cudaStreamWaitEvent(s[1], K->events[3], 0);
+    cudaStreamWaitEvent(s[1], K->events[0], 0);
+    GpuMat iw_col = mat(K->intWeights, (int)n, 1, CV_32FC1);
+    emf::cuda::TSDF::multSingletonCol(iw_col, As, As, st0);
+    emf::cuda::TSDF::multSingletonCol(iw_col, bs, bs, st1);
+    k_colsum<<<36, 256, 0, s[0]>>>(K->As, n, 36, K->A_gpu);
+    k_colsum<<<6, 256, 0, s[1]>>>(K->bs, n, 6, K->b_gpu);
+    // reduceHessians (:267-283): two downloads + waitForCompletion
+    cudaMemcpyAsync(A_out, K->A_gpu, 36 * 4, cudaMemcpyDeviceToHost, s[0]);
+    cudaMemcpyAsync(b_out, K->b_gpu, 6 * 4, cudaMemcpyDeviceToHost, s[1]);
+    cudaStreamSynchronize(s[0]);
+    cudaStreamSynchronize(s[1]);
+    if (err_out) *err_out = ref_compute_error(K);
+    return status();
+}
+
+// the trial pose of computePoseUpdate (src/core/TSDF.cpp:312-315): computeTSDFVals + waitForCompletion + computeError
+REF_API int emfref_tracker_error(void* h, const float* tsdf, const float* points, const float* R, const float* t,
+                                 const int* res, float voxel, float* err_out) {
+    RefTracker* K = (RefTracker*)h;
+    Stream st1(K->streams[1]);
+    GpuMat tv = mat((void*)tsdf, res[1] * res[2], res[0], CV_32FC1);
+    GpuMat p = mat((void*)points, K->h, K->w, CV_32FC3), tvals = mat(K->tsdfVals, K->h, K->w, CV_32FC1);
+    emf::cuda::TSDF::getVolumeVals(tv, p, m33(R), v3(t), v3i(res), voxel, tvals, st1);
+    cudaStreamSynchronize(K->streams[1]);
+    *err_out = ref_compute_error(K);
     return status();
 }

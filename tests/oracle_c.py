@@ -37,6 +37,10 @@ class Oracle:
         L.emfo_update_fgbg.argtypes = [_u8, _u8, C.c_int, C.c_int, _f, _f, _f, _f, _f, _f, _i32, C.c_float]
         L.emfo_compute_fg_probs.argtypes = [_f, C.c_int64, _f, _u8]
         L.emfo_raycast_weights.argtypes = [_f, _u8, C.c_int64, _f]
+        _d = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+        L.emfo_track_linearise.argtypes = [_f, _f, _f, _f, _f, C.c_int, C.c_int, _f, _f, _i32, C.c_float, C.c_float,
+                                           C.c_float, _f, _f, _f, _f, _d, _d, _d, _d]
+        L.emfo_track_linearise.restype = None
         L.emfo_uses_fma.restype = C.c_int
         for n in ("emfo_compute_points", "emfo_update_tsdf", "emfo_compute_grads", "emfo_raycast",
                   "emfo_get_volume_vals", "emfo_assoc_volume", "emfo_normalise", "emfo_composite",
@@ -140,6 +144,21 @@ class Oracle:
         out = np.empty_like(weights)
         self.L.emfo_raycast_weights(weights, fg_vol_mask, weights.size, out)
         return out
+
+    def track_linearise(self, tsdf, grads_vol, weights, points, assoc, R, t, res, voxel, huber=0.2, maxw=64.0):
+        """one tracker iteration's device part; sums in float64"""
+        h, w = points.shape[:2]
+        n = h * w
+        g6 = np.empty((n, 6), dtype=np.float32)
+        vals = np.empty((h, w), dtype=np.float32)
+        iw = np.empty((h, w), dtype=np.float32)
+        tw = np.empty((h, w), dtype=np.float32)
+        A = np.zeros(36); b = np.zeros(6); err = np.zeros(1); wmax = np.zeros(1)
+        self.L.emfo_track_linearise(tsdf, np.ascontiguousarray(grads_vol).reshape(-1), weights, np.ascontiguousarray(points),
+                                    np.ascontiguousarray(assoc), w, h, self._p(R), self._p(t), self._r(res), voxel, huber,
+                                    maxw, g6, vals, iw, tw, A, b, err, wmax)
+        return dict(grads=g6, tsdfVals=vals, intWeights=iw, trackWeights=tw, A=A.reshape(6, 6), b=b, err=float(err[0]),
+                    wmax=float(wmax[0]))
 
     def uses_fma(self) -> bool:
         return bool(self.L.emfo_uses_fma())

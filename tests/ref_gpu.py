@@ -57,6 +57,14 @@ def lib():
         L.emfref_frame_fill_assoc.argtypes = [vp, ci, cf]
         L.emfref_memcpy_d2d.argtypes = [vp, vp, C.c_size_t]
         L.emfref_compute_points.argtypes = [vp, vp, ci, ci, vp]
+        L.emfref_tracker_create.argtypes = [ci, ci]
+        L.emfref_tracker_create.restype = vp
+        L.emfref_tracker_destroy.argtypes = [vp]
+        L.emfref_tracker_destroy.restype = None
+        L.emfref_tracker_ptr.argtypes = [vp, ci]
+        L.emfref_tracker_ptr.restype = vp
+        L.emfref_tracker_linearise.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, cf, cf, cf, vp, vp, vp]
+        L.emfref_tracker_error.argtypes = [vp, vp, vp, vp, vp, vp, cf, vp]
         _lib = L
     return _lib
 
@@ -201,3 +209,40 @@ def _from_ptr(ptr, shape, dtype):
     torch.cuda.synchronize()
     _chk(lib().emfref_memcpy_d2d(out.data_ptr(), ptr, out.numel() * out.element_size()), "memcpy")
     return out
+
+
+class RefTracker:
+    """the tracking members of one emf::TSDF + the reference's launch chain of one iteration (oracle/ref_driver.cu section 4)"""
+    GRADS, TSDF_VALS, INT_WEIGHTS, TRACK_WEIGHTS, AS, BS, A_GPU, B_GPU = range(8)
+
+    def __init__(self, w, h):
+        self.w, self.h = w, h
+        self.handle = lib().emfref_tracker_create(w, h)
+
+    def close(self):
+        if self.handle:
+            lib().emfref_tracker_destroy(self.handle)
+            self.handle = None
+
+    def linearise(self, tsdf, grads_vol, weights, points, assoc, R, t, res, voxel, huber=0.2, maxw=64.0):
+        """-> (A (6,6), b (6,), err) as the reference downloads them"""
+        kr, pr = _h(R); kt, pt = _h(t); ks, ps = _h(res, np.int32)
+        A = np.zeros(36, dtype=np.float32); b = np.zeros(6, dtype=np.float32); e = np.zeros(1, dtype=np.float32)
+        _chk(lib().emfref_tracker_linearise(self.handle, tsdf.data_ptr(), grads_vol.data_ptr(), weights.data_ptr(),
+                                            points.data_ptr(), assoc.data_ptr(), pr, pt, ps, voxel, huber, maxw,
+                                            A.ctypes.data, b.ctypes.data, e.ctypes.data), "tracker linearise")
+        return A.reshape(6, 6), b, float(e[0])
+
+    def error(self, tsdf, points, R, t, res, voxel):
+        kr, pr = _h(R); kt, pt = _h(t); ks, ps = _h(res, np.int32)
+        e = np.zeros(1, dtype=np.float32)
+        _chk(lib().emfref_tracker_error(self.handle, tsdf.data_ptr(), points.data_ptr(), pr, pt, ps, voxel, e.ctypes.data),
+             "tracker error")
+        return float(e[0])
+
+    def image(self, what, shape, dtype=torch.float32):
+        """copy of one of the tracker's device buffers as a torch tensor"""
+        out = torch.empty(shape, dtype=dtype, device="cuda")
+        _chk(lib().emfref_memcpy_d2d(out.data_ptr(), lib().emfref_tracker_ptr(self.handle, what), out.numel() * out.element_size()),
+             "memcpy")
+        return out
