@@ -89,7 +89,7 @@ _SIGS = {
     "emf_update_brick_maps": [C.c_int, _P(Volume), C.c_void_p],
     "emf_reset_bitmaps": [_P(Volume), C.c_void_p],
     "emf_track_workspace_init": [C.c_void_p, C.c_size_t, C.c_void_p],
-    "emf_track_linearise": [C.c_int, _P(Volume), _P(Pose), _P(C.c_int), _P(Image), _P(Image), C.c_float, C.c_float,
+    "emf_track_linearise": [C.c_int, _P(Volume), _P(Pose), _P(C.c_int), _P(Image), _P(C.c_float), _P(Image), C.c_float, C.c_float,
                             _P(Image), _P(Image), _P(Image), _P(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_track_normalised_weights": [_P(Image), C.c_void_p, _P(Image), C.c_void_p],
     "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],

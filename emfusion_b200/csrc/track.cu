@@ -28,9 +28,11 @@
 
 namespace emfb {
 
+void box_screen_rect(const double b[3], const emf_pose* T_co, const float K[9], int width, int height, int rect_out[4]);
+
 constexpr int kTrackThreads = 256;
 constexpr int kTrackAcc = 29;        // 21 (A upper triangle) + 6 (b) + err + max
-constexpr int kTrackCtasPerVol = 74; // CTAs per volume; 74 x 2 volumes = one wave of 148 SMs
+constexpr int kTrackCtasPerVol = 296; // most CTAs (= reduction slots) one volume can use: 2 per SM
 constexpr size_t kTrackTicketBytes = 512;   // EMF_MAX_VOLUMES tickets at the head of the workspace
 
 struct TrackVol {
@@ -46,6 +48,10 @@ struct TrackVol {
     int rx, ry, rz;
     float voxel;
     int mode;                                // 0 skip, 1 linearise, 2 error only
+    int tx0, ty0, tx1, ty1;                  // tiles (32 x 8 px) with a pixel whose point can lie inside the volume (exclusive upper)
+    int lx0, ly0, ltx, ltiles;               // the tiles this launch loops over: origin, width, count (all tiles if it has
+    float inv_ltx;                           //   to write complete optional images, else the rectangle above)
+    int n_cta;                               // CTAs working on this volume (sized by the tiles inside the rectangle)
 };
 
 struct TrackParams {
@@ -75,22 +81,45 @@ __device__ __forceinline__ void track_grad_at(const TrackVol& V, int x, int y, i
     g[2] = fsub(__ldg(p + (int64_t)V.ry * V.rx), f);
 }
 
-__global__ void __launch_bounds__(kTrackThreads) k_track(const __grid_constant__ TrackParams P) {
+__global__ void __launch_bounds__(kTrackThreads, 2) k_track(const __grid_constant__ TrackParams P) {
     const int vi = blockIdx.y;
     const TrackVol& V = P.v[vi];
-    if (V.mode == 0) return;
+    if (V.mode == 0 || (int)blockIdx.x >= V.n_cta) return;
     const bool lin = V.mode == 1;
+    const unsigned n_cta = (unsigned)V.n_cta;
     float acc[kTrackAcc];
 #pragma unroll
     for (int k = 0; k < kTrackAcc; ++k) acc[k] = 0.0f;
 
-    const int tiles_x = (P.w + 31) / 32, tiles = tiles_x * ((P.h + 7) / 8);
     const float frx = (float)V.rx, fry = (float)V.ry, frz = (float)V.rz;
     const float hx = fmul((float)(V.rx - 1), 0.5f), hy = fmul((float)(V.ry - 1), 0.5f), hz = fmul((float)(V.rz - 1), 0.5f);
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    float* const out = P.out + (size_t)vi * EMF_TRACK_RECORD;
+    // error-only launches weigh with the image of the last linearisation, which is defined on ITS tile rectangle only
+    int wx0 = 0, wx1 = 0, wy0 = 0, wy1 = 0;
+    if (!lin) {
+        const unsigned a = __float_as_uint(out[45]), b = __float_as_uint(out[46]);
+        wx0 = a & 0xffff; wx1 = a >> 16; wy0 = b & 0xffff; wy1 = b >> 16;
+    }
+    for (int tile = blockIdx.x; tile < V.ltiles; tile += n_cta) {
+        const int tyl = __float2int_rz(((float)tile + 0.5f) * V.inv_ltx);   // tile / ltx (exact: tile < 2^20)
+        const int tx = V.lx0 + tile - tyl * V.ltx, ty = V.ly0 + tyl;
         const int x = tx * 32 + (threadIdx.x & 31), y = ty * 8 + (threadIdx.x >> 5);
         if (x >= P.w || y >= P.h) continue;
+        if (tx < V.tx0 || tx >= V.tx1 || ty < V.ty0 || ty >= V.ty1) {
+            // (only when complete optional images were asked for) no point of this tile can gather from the volume:
+            // every per-pixel quantity is 0 there
+            if (V.vals) *((float*)((char*)V.vals + (size_t)y * V.vals_pitch) + x) = 0.0f;
+            if (lin) {
+                *((float*)((char*)V.wimg + (size_t)y * V.wimg_pitch) + x) = 0.0f;
+                if (V.huber) *((float*)((char*)V.huber + (size_t)y * V.huber_pitch) + x) = 0.0f;
+                if (V.g6) {
+                    float* gp = V.g6 + 6 * ((size_t)y * P.w + x);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) gp[k] = 0.0f;
+                }
+            }
+            continue;
+        }
         const float* pp = (const float*)((const char*)P.points + (size_t)y * P.points_pitch) + 3 * x;
         const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
         float f = 0.0f, wint = 0.0f;
@@ -146,7 +175,7 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 6; ++i) acc[21 + i] = ffma(fmul(f, J[i]), wgt, acc[21 + i]);
         } else {
-            wgt = *wp;
+            wgt = (tx >= wx0 && tx < wx1 && ty >= wy0 && ty < wy1) ? *wp : 0.0f;
         }
         acc[27] = ffma(fmul(f, f), wgt, acc[27]);
     }
@@ -155,18 +184,31 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(const __grid_constant__
     __shared__ double s_part[kTrackThreads / 32][kTrackAcc];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp level: the 28 sums by recursive halving (at offset o a lane keeps the half of its values selected by its bit o
+    // and adds the partner's copy of that half: 16 + 8 + 4 + 2 + 1 shuffles, lane k ends up with the total of sum k), the
+    // maximum by a butterfly
+    {
+        float v[32];
 #pragma unroll
-    for (int k = 0; k < kTrackAcc; ++k) {
-        float a = acc[k];
+        for (int k = 0; k < 32; ++k) v[k] = k < 28 ? acc[k] : 0.0f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const float b = __shfl_xor_sync(0xffffffffu, a, o);
-            a = (k == 28) ? fmaxf(a, b) : fadd(a, b);
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int k = 0; k < o; ++k) {
+                const float send = up ? v[k] : v[k + o];
+                const float keep = up ? v[k + o] : v[k];
+                v[k] = fadd(keep, __shfl_xor_sync(0xffffffffu, send, o));
+            }
         }
-        if (lane == 0) s_part[warp][k] = (double)a;
+        float m = acc[28];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane < 28) s_part[warp][lane] = (double)v[0];
+        if (lane == 28) s_part[warp][28] = (double)m;
     }
     __syncthreads();
-    double* slot = P.slots + ((size_t)vi * gridDim.x + blockIdx.x) * kTrackAcc;
+    double* slot = P.slots + ((size_t)vi * kTrackCtasPerVol + blockIdx.x) * kTrackAcc;
     if (threadIdx.x < kTrackAcc) {
         double a = s_part[0][threadIdx.x];
         for (int wv = 1; wv < kTrackThreads / 32; ++wv)
@@ -175,22 +217,31 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(const __grid_constant__
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(P.tickets + vi, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(P.tickets + vi, 1u) == n_cta - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // fold the CTA slots in a fixed order: warp p sums the slots c = p (mod 8) in ascending order, then the 8 partial
+    // sums are combined in ascending order
     __shared__ double s_tot[kTrackAcc];
-    if (threadIdx.x < kTrackAcc) {
-        const double* s0 = P.slots + (size_t)vi * gridDim.x * kTrackAcc + threadIdx.x;
-        double a = s0[0];
-        for (unsigned c = 1; c < gridDim.x; ++c) {
-            const double b = s0[(size_t)c * kTrackAcc];
-            a = (threadIdx.x == 28) ? fmax(a, b) : a + b;
+    if (lane < kTrackAcc) {
+        const double* s0 = P.slots + (size_t)vi * kTrackCtasPerVol * kTrackAcc + lane;
+        double a = 0.0;   // (every accumulated quantity, the maximum included, is >= 0 or a sum)
+#pragma unroll 4
+        for (unsigned c = warp; c < n_cta; c += kTrackThreads / 32) {
+            const double b = __ldcg(s0 + (size_t)c * kTrackAcc);
+            a = (lane == 28) ? fmax(a, b) : a + b;
         }
+        s_part[warp][lane] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < kTrackAcc) {
+        double a = s_part[0][threadIdx.x];
+        for (int wv = 1; wv < kTrackThreads / 32; ++wv)
+            a = (threadIdx.x == 28) ? fmax(a, s_part[wv][threadIdx.x]) : a + s_part[wv][threadIdx.x];
         s_tot[threadIdx.x] = a;
     }
     __syncthreads();
-    float* out = P.out + (size_t)vi * EMF_TRACK_RECORD;
     if (lin) {
         // cv::cuda::normalize(NORM_INF, alpha = 1): scale = 1 / max|w| (0 when the norm vanishes), applied as a float
         const double wmax = s_tot[28];
@@ -206,6 +257,8 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(const __grid_constant__
             out[42] = (float)(s_tot[27] * (double)scale);
             out[43] = (float)wmax;
             out[44] = scale;
+            out[45] = __uint_as_float((unsigned)V.tx0 | ((unsigned)V.tx1 << 16));   // where int_weights is defined
+            out[46] = __uint_as_float((unsigned)V.ty0 | ((unsigned)V.ty1 << 16));
         }
     } else if (threadIdx.x == 0) {
         out[42] = (float)(s_tot[27] * (double)out[44]);
@@ -217,7 +270,10 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(const __grid_constant__
 __global__ void __launch_bounds__(256) k_track_scale(Img<const float> src, Img<float> dst, const float* __restrict__ rec) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x < src.w && y < src.h) dst.at(y, x) = fmul(src.at(y, x), __ldg(rec + 44));
+    if (x >= src.w || y >= src.h) return;
+    const unsigned a = __float_as_uint(__ldg(rec + 45)), b = __float_as_uint(__ldg(rec + 46));
+    const bool in = blockIdx.x >= (a & 0xffff) && blockIdx.x < (a >> 16) && blockIdx.y >= (b & 0xffff) && blockIdx.y < (b >> 16);
+    dst.at(y, x) = in ? fmul(src.at(y, x), __ldg(rec + 44)) : 0.0f;
 }
 
 }  // namespace emfb
@@ -230,7 +286,7 @@ extern "C" EMF_API size_t emf_track_workspace_bytes(int n_vol) {
 }
 
 extern "C" EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, const emf_pose* T_co, const int* modes,
-                                           const emf_image* points, const emf_image* assoc, float huber_thresh,
+                                           const emf_image* points, const float K[9], const emf_image* assoc, float huber_thresh,
                                            float max_tsdf_weight, const emf_image* int_weights, const emf_image* tsdf_vals,
                                            const emf_image* track_weights, float* const* pose_grads, float* records,
                                            void* workspace, size_t workspace_bytes, emf_stream_t stream) {
@@ -241,6 +297,7 @@ extern "C" EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, co
     TrackParams P;
     const int w = points->width, h = points->height;
     bool any = false;
+    int max_cta = 1;
     for (int i = 0; i < n_vol; ++i) {
         TrackVol& d = P.v[i];
         d.mode = modes[i];
@@ -269,6 +326,32 @@ extern "C" EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, co
         for (int k = 0; k < 3; ++k) d.t[k] = T_co[i].t[k];
         d.rx = v.res[0]; d.ry = v.res[1]; d.rz = v.res[2];
         d.voxel = v.voxel_size;
+        const int tiles_x = (w + 31) / 32, tiles_y = (h + 7) / 8;
+        if (tiles_x > 0xffff || tiles_y > 0xffff) return EMF_ERR_UNSUPPORTED;
+        d.tx0 = 0; d.ty0 = 0; d.tx1 = tiles_x; d.ty1 = tiles_y;
+        if (K) {
+            // a point gathers only if it lies inside the voxel grid, |p| < (R - 1) / 2 * voxel per axis, and it lies on its
+            // pixel's ray: outside the screen rectangle of that box (taken one voxel larger, padded by 2 px) nothing gathers
+            const double b[3] = {(0.5 * v.res[0] + 1.0) * v.voxel_size, (0.5 * v.res[1] + 1.0) * v.voxel_size,
+                                 (0.5 * v.res[2] + 1.0) * v.voxel_size};
+            int r[4];
+            box_screen_rect(b, &T_co[i], K, w, h, r);
+            d.tx0 = r[0] / 32; d.ty0 = r[1] / 8; d.tx1 = (r[2] + 31) / 32; d.ty1 = (r[3] + 7) / 8;
+            if (r[2] <= r[0] || r[3] <= r[1]) { d.tx1 = d.tx0; d.ty1 = d.ty0; }
+        }
+        // complete optional images: loop over every tile (zeros outside the rectangle); otherwise over the rectangle only
+        const bool full = d.vals || d.huber || d.g6;
+        d.lx0 = full ? 0 : d.tx0; d.ly0 = full ? 0 : d.ty0;
+        d.ltx = full ? tiles_x : d.tx1 - d.tx0;
+        d.ltiles = full ? tiles_x * tiles_y : (d.tx1 - d.tx0) * (d.ty1 - d.ty0);
+        d.inv_ltx = d.ltx > 0 ? 1.0f / (float)d.ltx : 0.0f;
+        if (d.ltiles >= (1 << 20)) return EMF_ERR_UNSUPPORTED;
+        // four tiles of real work per CTA
+        const int64_t rect_tiles = (int64_t)(d.tx1 - d.tx0) * (d.ty1 - d.ty0);
+        d.n_cta = (int)((rect_tiles + 3) / 4);
+        if (d.n_cta < 1) d.n_cta = 1;
+        if (d.n_cta > kTrackCtasPerVol) d.n_cta = kTrackCtasPerVol;
+        if (d.n_cta > max_cta) max_cta = d.n_cta;
     }
     if (!any) return EMF_OK;
     P.n_vol = n_vol; P.w = w; P.h = h;
@@ -277,7 +360,7 @@ extern "C" EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, co
     P.out = records;
     P.tickets = (unsigned*)workspace;                       // fixed place: they return to 0 after every launch
     P.slots = (double*)((char*)workspace + kTrackTicketBytes);
-    const dim3 grid(kTrackCtasPerVol, n_vol);
+    const dim3 grid(max_cta, n_vol);
     k_track<<<grid, kTrackThreads, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
 }

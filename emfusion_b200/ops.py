@@ -323,9 +323,10 @@ def _opt_images(ts, n):
 
 
 def trackLinearise(vols, rel_poses_CO, modes, points, assoc, huberThresh, maxTSDFWeight, intWeights, records,
-                   tsdfVals=None, trackWeights=None, poseGrads=None, stream=None):
+                   tsdfVals=None, trackWeights=None, poseGrads=None, stream=None, intr=None):
     """One launch = the device part of one tracker iteration of every volume (emf_track_linearise, include/emf_b200.h).
-    modes[i]: 0 skip / 1 linearise / 2 error only; records: (n_vol, 48) float32 CUDA tensor."""
+    modes[i]: 0 skip / 1 linearise / 2 error only; records: (n_vol, 48) float32 CUDA tensor; intr: the camera matrix of
+    `points` (optional: lets the kernel skip image tiles that cannot see a volume)."""
     n = len(vols)
     if records.dtype != torch.float32 or records.numel() < n * _lib.EMF_TRACK_RECORD or not records.is_contiguous():
         raise _lib.EmfError("records must be a contiguous float32 CUDA tensor of n_vol x 48")
@@ -334,7 +335,8 @@ def trackLinearise(vols, rel_poses_CO, modes, points, assoc, huberThresh, maxTSD
     pg = None
     if poseGrads is not None:
         pg = (C.c_void_p * n)(*[(_ptr(g) if g is not None else None) for g in poseGrads])
-    check(_lib.lib().emf_track_linearise(n, _vol_array(vols), poses(rel_poses_CO), m, image(points), _opt_images(assoc, n),
+    check(_lib.lib().emf_track_linearise(n, _vol_array(vols), poses(rel_poses_CO), m, image(points),
+                                         _f9(intr) if intr is not None else None, _opt_images(assoc, n),
                                          float(huberThresh), float(maxTSDFWeight), _opt_images(intWeights, n),
                                          _opt_images(tsdfVals, n), _opt_images(trackWeights, n), pg, _ptr(records),
                                          ws.data_ptr(), ws.numel(), _stream(stream)), "trackLinearise")
@@ -346,3 +348,39 @@ def trackNormalisedWeights(intWeights, record, out, stream=None):
     check(_lib.lib().emf_track_normalised_weights(image(intWeights), _ptr(record), image(out), _stream(stream)),
           "trackNormalisedWeights")
     _count("trackNormalisedWeights")
+
+
+class TrackPlan:
+    """emf_track_linearise with every argument that does not change between the iterations of one frame marshalled
+    once (volume table, image headers, workspace); per call only the poses and modes are written."""
+
+    def __init__(self, vols, points, assoc, huberThresh, maxTSDFWeight, intWeights, records, tsdfVals=None,
+                 trackWeights=None, intr=None):
+        n = self.n = len(vols)
+        if records.dtype != torch.float32 or records.numel() < n * _lib.EMF_TRACK_RECORD or not records.is_contiguous():
+            raise _lib.EmfError("records must be a contiguous float32 CUDA tensor of n_vol x 48")
+        self._keep = (vols, points, assoc, intWeights, records, tsdfVals, trackWeights)
+        self._vols = _vol_array(vols)
+        self._points = image(points)
+        self._K = _f9(intr) if intr is not None else None
+        self._assoc = _opt_images(assoc, n)
+        self._iw = _opt_images(intWeights, n)
+        self._vals = _opt_images(tsdfVals, n)
+        self._tw = _opt_images(trackWeights, n)
+        self._rec = _ptr(records)
+        self._ws = trackWorkspace(points.device, n)
+        self._poses = (Pose * n)()
+        self._modes = (C.c_int * n)()
+        self._huber, self._maxw = float(huberThresh), float(maxTSDFWeight)
+        self._fn = _lib.lib().emf_track_linearise
+
+    def launch(self, T_co: np.ndarray, modes, stream=None):
+        """T_co: (n, 12) float32 (R row-major, then t), e.g. from poses.pack_poses; modes: n ints"""
+        T_co = np.ascontiguousarray(T_co, dtype=np.float32)
+        C.memmove(self._poses, T_co.ctypes.data, 48 * self.n)
+        self._modes[:] = [int(m) for m in modes]
+        check(self._fn(self.n, self._vols, self._poses, self._modes, self._points, self._K, self._assoc, self._huber,
+                       self._maxw, self._iw, self._vals, self._tw, None, self._rec, self._ws.data_ptr(), self._ws.numel(),
+                       _stream(stream)), "trackLinearise")
+        if any(modes):
+            _count("trackLinearise")

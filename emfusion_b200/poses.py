@@ -96,3 +96,12 @@ def rel_pose_arrays(cam_pose: Affine, poses):
     T_co = np.concatenate([R_co.reshape(n, 9), t_co], axis=1).astype(np.float32)
     T_oc = np.concatenate([R_oc.reshape(n, 9), t_oc], axis=1).astype(np.float32)
     return np.ascontiguousarray(T_co), np.ascontiguousarray(T_oc)
+
+
+def pack_poses(poses) -> np.ndarray:
+    """[Affine] -> (n, 12) float32 = n packed emf_pose (R row-major, then t)"""
+    out = np.empty((len(poses), 12), dtype=np.float32)
+    for i, p in enumerate(poses):
+        out[i, :9] = p.R.reshape(9)
+        out[i, 9:] = p.t
+    return out

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .poses import Affine
+from .poses import Affine, pack_poses
 
 
 # ---- SE(3) exponential / logarithm, tangent = (upsilon, omega) as in Sophus::SE3::exp / log --------------------
@@ -122,8 +122,11 @@ class Tracker:
     """performTracking for a list of volumes that are tracked together (the background alone, then all objects:
     src/core/EMFusion.cpp:673-721)."""
 
-    def __init__(self, volumes: Sequence, frameSize, device, keep_images: bool = False):
+    def __init__(self, volumes: Sequence, frameSize, device, keep_images: bool = False, intr=None):
+        """intr: the camera matrix the points are un-projected with (optional; lets the kernel skip the image tiles
+        that cannot see a volume -- most of the frame for an object)."""
         w, h = frameSize
+        self.intr = intr
         self.device = torch.device(device)
         self.states: List[TrackState] = [TrackState(v, h, w, self.device, keep_images) for v in volumes]
         n = len(self.states)
@@ -132,13 +135,16 @@ class Tracker:
         self.keep_images = keep_images
         self.device_reads = 0
 
-    def _launch(self, modes, poses, points, assoc):
+    def _plan(self, points, assoc):
         S = self.states
         cv = [s.vol.c_volume(with_grads=True) for s in S]   # the materialised float3 gradients when they are up to date
-        ops.trackLinearise(cv, poses, modes, points, assoc, S[0].vol.params.huberThresh, S[0].vol.params.maxTSDFWeight,
-                           [s.intWeights for s in S], self.records,
-                           tsdfVals=[s.tsdfVals for s in S] if self.keep_images else None,
-                           trackWeights=[s.trackWeights for s in S] if self.keep_images else None)
+        return ops.TrackPlan(cv, points, assoc, S[0].vol.params.huberThresh, S[0].vol.params.maxTSDFWeight,
+                             [s.intWeights for s in S], self.records,
+                             tsdfVals=[s.tsdfVals for s in S] if self.keep_images else None,
+                             trackWeights=[s.trackWeights for s in S] if self.keep_images else None, intr=self.intr)
+
+    def _launch(self, plan, modes, poses):
+        plan.launch(pack_poses(poses), modes)
         self._rec_host.copy_(self.records, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self.device_reads += 1
@@ -150,12 +156,13 @@ class Tracker:
         S = self.states
         for s in S:
             s.prepareTracking(cam_pose)
+        plan = self._plan(points, assoc)
         for _ in range(maxTrackingIter):
             if all(s.trackingConverged for s in S):
                 break
             # ---- computeGradients ... reduceHessians (+ the err of computePoseUpdate) at the current poses
             modes = [0 if s.trackingConverged else (1 if s.evaluateGradient else 2) for s in S]
-            rec = self._launch(modes, [s.rel_pose_CO for s in S], points, assoc)
+            rec = self._launch(plan, modes, [s.rel_pose_CO for s in S])
             trial_modes = [0] * len(S)
             trial_poses = [s.rel_pose_CO for s in S]
             errs = [0.0] * len(S)
@@ -191,7 +198,7 @@ class Tracker:
             if not any(trial_modes):
                 continue
             # ---- computeTSDFVals at the trial poses + computeError
-            rec = self._launch(trial_modes, trial_poses, points, assoc)
+            rec = self._launch(plan, trial_modes, trial_poses)
             for i, s in enumerate(S):
                 if trial_modes[i] == 0:
                     continue

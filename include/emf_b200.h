@@ -279,14 +279,20 @@ EMF_API int emf_fill_image_f32(const emf_image* img, float value, emf_stream_t s
  * (the trial pose of TSDF::computePoseUpdate, src/core/TSDF.cpp:312-315, or an iteration with evaluateGradient false).
  * Per volume i:
  *   assoc[i]        in  (mode 1)  association weights of the volume (W x H f32)
- *   int_weights[i]  mode 1: out, mode 2: in -- Huber x min(w, max) x assoc per pixel, BEFORE the NORM_INF scale
- *                   (the reference's intWeights = this x records[i][44]; emf_track_normalised_weights forms it)
+ *   int_weights[i]  mode 1: out, mode 2: in -- Huber x min(w, max) x assoc per pixel, BEFORE the NORM_INF scale and only
+ *                   on the tile rectangle recorded in records[i][45..46] (everything outside is 0 by construction and is
+ *                   not written unless one of the optional images below is requested).  The reference's intWeights =
+ *                   this x records[i][44] inside the rectangle, 0 outside: emf_track_normalised_weights forms it.
  *   tsdf_vals[i]    out, optional (array or entry.ptr NULL): tsdfVals
  *   track_weights[i] out, optional, mode 1: trackWeights (Huber)
  *   pose_grads[i]   out, optional, mode 1: `grads`, W*H x 6 floats continuous (bit-identical to the reference's)
  *   records + i * EMF_TRACK_RECORD (device floats): [0..35] A row-major 6x6, [36..41] b, [42] error
- *                   sum f^2 w, [43] max of the clamped integration weights, [44] the NORM_INF scale.
+ *                   sum f^2 w, [43] max of the clamped integration weights, [44] the NORM_INF scale, [45], [46] (bit
+ *                   patterns of two uint32) the rectangle of 32 x 8 pixel tiles int_weights was written on:
+ *                   tx0 | tx1 << 16 and ty0 | ty1 << 16.
  *                   Mode 1 writes all of it; mode 2 only [42], using the stored scale and int_weights.
+ * K (optional): the camera matrix the points were un-projected with (emf_compute_points).  With it, image tiles whose
+ * pixels cannot see a volume's box are not gathered at all (their outputs are the zeros the reference computes there).
  * workspace: emf_track_workspace_bytes(n_vol) bytes of device memory (16-byte aligned) that was zeroed ONCE with
  * emf_track_workspace_init; the call leaves it ready for the next one.  Sums are folded in a fixed order:
  * the same inputs give the same bits. */
@@ -294,7 +300,8 @@ EMF_API int emf_fill_image_f32(const emf_image* img, float value, emf_stream_t s
 EMF_API size_t emf_track_workspace_bytes(int n_vol);
 EMF_API int emf_track_workspace_init(void* workspace, size_t workspace_bytes, emf_stream_t stream);
 EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, const emf_pose* T_co, const int* modes,
-                        const emf_image* points, const emf_image* assoc, float huber_thresh, float max_tsdf_weight,
+                        const emf_image* points, const float K[9], const emf_image* assoc, float huber_thresh,
+                        float max_tsdf_weight,
                         const emf_image* int_weights, const emf_image* tsdf_vals, const emf_image* track_weights,
                         float* const* pose_grads, float* records, void* workspace, size_t workspace_bytes,
                         emf_stream_t stream);

@@ -30,7 +30,7 @@ def _perturbed(T: Affine, k: int) -> Affine:
     return se3_exp(d) * T
 
 
-def _run_ours(v, T, pts, assoc, grads_vol=None, mode=1, rec=None, iw=None):
+def _run_ours(v, T, pts, assoc, grads_vol=None, mode=1, rec=None, iw=None, intr=None):
     n_pix = pts.shape[0] * pts.shape[1]
     t_d, w_d = cu(v.tsdf), cu(v.weights)     # (kept alive below: the descriptor only holds raw pointers)
     cv = ops.volume(t_d, w_d, v.res, v.voxel, v.trunc, grads=grads_vol, vid=v.vid)
@@ -40,7 +40,7 @@ def _run_ours(v, T, pts, assoc, grads_vol=None, mode=1, rec=None, iw=None):
     tw = torch.full(pts.shape[:2], 7.0, device=DEV)
     g6 = torch.full((n_pix, 6), 7.0, device=DEV)
     ops.trackLinearise([cv], [T], [mode], pts, [assoc], 0.2, 64.0, [iw], rec, tsdfVals=[vals], trackWeights=[tw],
-                       poseGrads=[g6])
+                       poseGrads=[g6], intr=intr)
     torch.cuda.synchronize()
     return dict(rec=rec, intWeights=iw, tsdfVals=vals, trackWeights=tw, grads=g6, keep=(cv, t_d, w_d, grads_vol))
 
@@ -125,6 +125,28 @@ def test_batch_equals_single_and_is_deterministic(scn, oracle, cuda_dev):
         assert torch.equal(g["rec"][0, :45], rec[i, :45]), f"volume {i}: batched != single"
 
 
+def test_tile_culling_changes_nothing(scn, oracle, cuda_dev):
+    """with the camera matrix the kernel skips the image tiles that cannot see the volume: same bits everywhere"""
+    pts = cu(oracle.compute_points(scn.depths[2], scn.K))
+    for k, v in enumerate(scn.vols()):
+        T = _perturbed(rel_pose_CO(scn.cam(2), v.pose), k)
+        assoc = torch.rand((scn.h, scn.w), device=DEV)
+        a = _run_ours(v, T, pts, assoc)
+        b = _run_ours(v, T, pts, assoc, intr=scn.K)
+        for key in ("grads", "tsdfVals", "trackWeights", "intWeights"):
+            assert torch.equal(a[key], b[key]), f"vol {v.vid} {key}"
+        # (the number of CTAs, hence the order of the sums, follows the rectangle: the sums agree to rounding)
+        ra, rb = a["rec"][0, :45].double().cpu().numpy(), b["rec"][0, :45].double().cpu().numpy()
+        assert np.abs(ra[:36] - rb[:36]).max() <= 1e-6 * max(np.abs(ra[:36]).max(), 1e-30)
+        assert np.abs(ra[36:42] - rb[36:42]).max() <= 1e-6 * max(np.abs(ra[36:42]).max(), 1e-30)
+        assert np.allclose(ra[42:45], rb[42:45], rtol=1e-6, atol=0)
+        T2 = _perturbed(T, 3)
+        a2 = _run_ours(v, T2, pts, assoc, mode=2, rec=a["rec"], iw=a["intWeights"])
+        b2 = _run_ours(v, T2, pts, assoc, mode=2, rec=b["rec"], iw=b["intWeights"], intr=scn.K)
+        assert torch.equal(a2["tsdfVals"], b2["tsdfVals"])
+        assert abs(float(a2["rec"][0, 42]) - float(b2["rec"][0, 42])) <= 1e-6 * abs(float(a2["rec"][0, 42]))
+
+
 @pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
 def test_linearise_vs_reference_chain(scn, oracle, cuda_dev):
     rng = np.random.default_rng(13)
@@ -185,7 +207,7 @@ def test_tracker_recovers_camera_pose(cuda_dev, oracle):
     assoc = torch.ones((sc.h, sc.w), device=DEV)
     true_cam = sc.cam(2)
     start = true_cam * se3_exp(np.array([0.01, -0.008, 0.012, 0.006, -0.005, 0.004]))
-    tr = Tracker([vol], (sc.w, sc.h), DEV)
+    tr = Tracker([vol], (sc.w, sc.h), DEV, intr=sc.K)
     st = tr.track(pts, [assoc], start, maxTrackingIter=100)[0]
     cam = tr.syncTrackCamera(0)
     d0 = np.linalg.norm(se3_log(true_cam.inv() * start))
