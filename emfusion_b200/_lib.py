@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libemf_b200.so")
+# (EMF_B200_LIB: another build of the same library, for A/B experiments -- scripts/ab_build.sh)
+LIB_PATH = os.environ.get("EMF_B200_LIB") or os.path.join(_HERE, "lib", "libemf_b200.so")
 
 EMF_OK = 0
 EMF_ERR_INVALID = -1

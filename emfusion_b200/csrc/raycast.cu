@@ -187,11 +187,101 @@ __device__ __forceinline__ bool march_step(Ray& r, const RayConst& c, const Cons
     return false;
 }
 
+// ---- two samples in flight (PAIR): the march is a chain of dependent gathers (position -> 8 loads -> 7 lerps -> decision),
+// and at 64 registers only 8 warps per scheduler hide it.  The sample after next is therefore fetched SPECULATIVELY under
+// the assumption that the next one neither ends the ray nor changes the step (true for > 95 % of the samples: free space and
+// never-observed space keep the step); its loads are issued before the first sample is resolved.  Each sample is then
+// resolved with exactly the arithmetic of march_step, in order; a speculative sample whose assumption failed is discarded.
+struct Samp {
+    float vx, vy, vz;
+    float c[8];
+    bool in;
+};
+__device__ __forceinline__ void samp_fetch(Samp& q, float t, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane) {
+    const float nx = ffma(c.dx, t, c.ox), ny = ffma(c.dy, t, c.oy), nz = ffma(c.dz, t, c.oz);
+    if (c.sane && fminf(fminf(fabsf(nx), fabsf(ny)), fabsf(nz)) > 5.5e-20f) {
+        q.vx = fadd(c.hxh, div_s.fast(nx)); q.vy = fadd(c.hyh, div_s.fast(ny)); q.vz = fadd(c.hzh, div_s.fast(nz));
+    } else {
+        q.vx = fadd(c.hxh, div_s(nx)); q.vy = fadd(c.hyh, div_s(ny)); q.vz = fadd(c.hzh, div_s(nz));
+    }
+    q.in = !out_of_thr(q.vx, q.vy, q.vz, V.thr2);
+    if (q.in) {
+        const int lx = __float2int_rz(q.vx), ly = __float2int_rz(q.vy), lz = __float2int_rz(q.vz);
+        const float* r00 = V.tsdf + (uint32_t)(lz * plane + ly * rx + lx);
+        const float* r01 = r00 + rx;
+        const float* r10 = r00 + plane;
+        const float* r11 = r10 + rx;
+        q.c[0] = __ldg(r00); q.c[1] = __ldg(r00 + 1); q.c[2] = __ldg(r01); q.c[3] = __ldg(r01 + 1);
+        q.c[4] = __ldg(r10); q.c[5] = __ldg(r10 + 1); q.c[6] = __ldg(r11); q.c[7] = __ldg(r11 + 1);
+    }
+}
+__device__ __forceinline__ float samp_value(const Samp& q) {
+    const float ax = fsub(q.vx, (float)__float2int_rz(q.vx)), ay = fsub(q.vy, (float)__float2int_rz(q.vy)),
+                az = fsub(q.vz, (float)__float2int_rz(q.vz));
+    const float bx = fsub(1.0f, ax), by = fsub(1.0f, ay), bz = fsub(1.0f, az);
+    const float c00 = lerp1(bx, q.c[0], ax, q.c[1]), c01 = lerp1(bx, q.c[2], ax, q.c[3]);
+    const float c10 = lerp1(bx, q.c[4], ax, q.c[5]), c11 = lerp1(bx, q.c[6], ax, q.c[7]);
+    return lerp1(bz, lerp1(by, c00, ay, c01), az, lerp1(by, c10, ay, c11));
+}
+// the part of march_step after the TSDF sample fn at ray parameter r.tcur / position q is known; true = ray finished
+template <bool STATS>
+__device__ __forceinline__ bool samp_resolve(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, const Samp& q, float fn,
+                                             unsigned long long* st) {
+    if (STATS) ++st[0];
+    if (r.f < 0.0f && fn > 0.0f) {
+        if (STATS) ++st[3];
+        if (trilinear_weight(V, q.vx, q.vy, q.vz) > 0.0f) return true;
+    }
+    if (fabsf(fn) < 1.0f) r.step = c.s;
+    if (fabsf(fn) < 0.8f) r.step = c.half_s;
+    if (r.f > 0.0f && fn < 0.0f) {
+        const float ts = fsub(r.tcur, fdiv(fmul(r.f, r.step), fsub(fn, r.f)));
+        const float mx = fmul(c.dx, ts), my = fmul(c.dy, ts), mz = fmul(c.dz, ts);
+        const float sx = fadd(c.hxh, div_s(fadd(c.ox, mx)));
+        const float sy = fadd(c.hyh, div_s(fadd(c.oy, my)));
+        const float sz = fadd(c.hzh, div_s(fadd(c.oz, mz)));
+        if (out_of_thr(sx, sy, sz, V.thr2)) return false;
+        if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
+            r.hit = true; r.out_t = ts;
+            r.hvx = sx; r.hvy = sy; r.hvz = sz; r.hmx = mx; r.hmy = my; r.hmz = mz;
+            return true;
+        }
+    }
+    r.f = fn;
+    return false;
+}
+template <bool STATS>
+__device__ __forceinline__ void march_pairs(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
+                                            unsigned long long* st) {
+    for (;;) {
+        const float t1 = fadd(r.tcur, r.step);
+        if (!(t1 <= c.tmax)) return;
+        const float t2 = fadd(t1, r.step);
+        const float step0 = r.step;
+        Samp a, b;
+        samp_fetch(a, t1, c, div_s, V, rx, plane);
+        const bool have2 = t2 <= c.tmax;
+        b.in = false;
+        if (have2) samp_fetch(b, t2, c, div_s, V, rx, plane);
+        r.tcur = t1;
+        if (a.in && samp_resolve<STATS>(r, c, div_s, V, a, samp_value(a), st)) return;
+        if (!have2 || r.step != step0) continue;     // the speculation failed (or there is no second sample)
+        r.tcur = t2;
+        if (b.in && samp_resolve<STATS>(r, c, div_s, V, b, samp_value(b), st)) return;
+    }
+}
+
 // JUMP = false: every lane marches its own ray (the lean default).
 // JUMP = true : the warp stays in lockstep so that jumps through certified constant regions can be agreed on with warp
 //               collectives (needs emf_volume::brick_map on at least one volume of the launch).
+#ifndef EMF_RAY_PAIR
+#define EMF_RAY_PAIR 1
+#endif
+#ifndef EMF_RAY_MINB
+#define EMF_RAY_MINB 8
+#endif
 template <bool STATS, bool JUMP>
-__global__ void __launch_bounds__(kRayThreads, 8) k_raycast(const __grid_constant__ RayParams P) {
+__global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __grid_constant__ RayParams P) {
     unsigned long long st[4] = {0, 0, 0, 0};
     int lo = 0, hi = P.n_vol - 1;
     const int b = blockIdx.x;
@@ -286,8 +376,13 @@ __global__ void __launch_bounds__(kRayThreads, 8) k_raycast(const __grid_constan
         }
     }
     if (!JUMP) {
-        if (!done)
+        if (!done) {
+#if EMF_RAY_PAIR
+            march_pairs<STATS>(r, c, div_s, V, rx, plane, st);
+#else
             while (!march_step<STATS>(r, c, div_s, V, rx, plane, st)) {}
+#endif
+        }
     } else {
         constexpr unsigned kFull = 0xffffffffu;
         const uint8_t* __restrict__ bmap = V.bmap;

@@ -149,7 +149,7 @@ class NativeEngine(EMFusionEngine):
         if flags & F_NORMALISE and n: launches += 1
         if flags & F_RAYCAST and n: launches += 1
         if flags & (F_COMPOSITE | F_COMPOSITE_NOBG): launches += 1
-        if flags & F_INTEGRATE and n: launches += 1 + (2 if any(v.constBits is not None for v in vols) else 0)
+        if flags & F_INTEGRATE and n: launches += 2 + (2 if any(v.constBits is not None for v in vols) else 0)   # pyramid + integrate
         ops.LAUNCHES["engineFrame"] = ops.LAUNCHES.get("engineFrame", 0) + launches
 
     def set_depth(self, depth: torch.Tensor):

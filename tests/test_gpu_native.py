@@ -73,3 +73,36 @@ def test_native_engine_stage_times(cuda_dev):
         nat.processFrame(cu(depth), scene.cam_pose(f), {o.id: scene.object_pose(o.id - 1, f) for o in nat.objects}, timed=True)
     ms = nat.stage_ms()
     assert len(ms) == 3 and all(m >= 0 for m in ms) and sum(ms) > 0
+
+
+def test_host_frame_pipeline_equals_direct_frames(cuda_dev):
+    """HostFramePipeline (pinned depth in, pinned composite out, copies overlapped with the kernels) returns, frame by
+    frame, exactly what processFrame on device-resident depth produces"""
+    from emfusion_b200.pipeline import HostFramePipeline
+    w, h, n_obj = 160, 120, 3
+    scene = Scene(n_objects=n_obj, width=w, height=h, seed=5)
+    a = make(NativeEngine, scene, w, h, 64, n_obj, 32)
+    b = make(NativeEngine, scene, w, h, 64, n_obj, 32)
+    pipe = HostFramePipeline(b)
+    frames = [scene.render(f) for f in range(7)]
+    pinned = [torch.from_numpy(d).pin_memory() for d, _ in frames]
+    want, tickets = [], []
+    for f in range(7):
+        poses = {o.id: scene.object_pose(o.id - 1, f) for o in a.objects}
+        a.processFrame(cu(frames[f][0]), scene.cam_pose(f), poses)
+        tickets.append(pipe.submit(pinned[f], scene.cam_pose(f), poses))
+        if f == 0:
+            zeros = torch.zeros((h, w), dtype=torch.uint8, device=DEV)
+            for eng in (a, b):
+                for o in eng.objects:
+                    o.integrateMask(cu((frames[0][1] == o.id).astype(np.uint8)), zeros, eng.pose, eng.params.intr)
+        want.append((a.modelSegmentation.cpu().numpy().copy(), a.raylengths.cpu().numpy().copy()))
+        if f >= 1:   # consume one frame behind, as a streaming host would
+            seg, ray = pipe.result(tickets[f - 1])
+            assert np.array_equal(seg.numpy(), want[f - 1][0]), f"frame {f - 1} segmentation"
+            assert_bits(torch.from_numpy(ray.numpy().copy()), want[f - 1][1], f"frame {f - 1} ray lengths")
+    seg, ray = pipe.result(tickets[-1])
+    assert np.array_equal(seg.numpy(), want[-1][0])
+    assert int((want[-1][0] > 0).sum()) > 0
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])
