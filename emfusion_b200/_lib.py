@@ -89,6 +89,9 @@ _SIGS = {
                                  C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_update_brick_maps": [C.c_int, _P(Volume), C.c_void_p],
     "emf_reset_bitmaps": [_P(Volume), C.c_void_p],
+    "emf_copy_values": [C.c_void_p, C.c_void_p, C.c_int, _P(C.c_int), _P(C.c_int), _P(C.c_int), C.c_void_p],
+    "emf_resize_volume": [C.c_void_p, C.c_void_p, C.c_void_p, _P(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p, _P(C.c_int),
+                          _P(C.c_int), C.c_void_p],
     "emf_track_workspace_init": [C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_track_linearise": [C.c_int, _P(Volume), _P(Pose), _P(C.c_int), _P(Image), _P(C.c_float), _P(Image), C.c_float, C.c_float,
                             _P(Image), _P(Image), _P(Image), _P(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],

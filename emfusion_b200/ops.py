@@ -22,7 +22,8 @@ LAUNCHES = {}
 _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1, "raycastTSDF": 1, "getVolumeVals": 1,
                      "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
                      "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
-                     "updateBrickMaps": 2, "trackLinearise": 1, "trackNormalisedWeights": 1}
+                     "updateBrickMaps": 2, "trackLinearise": 1, "trackNormalisedWeights": 1, "copyValues": 1,
+                     "resizeVolume": 1}
 
 
 def _count(name: str) -> None:
@@ -294,6 +295,22 @@ def resetBitmaps(vol: Volume, stream=None):
 def bitmapWords(res) -> int:
     """32-bit words of ONE segment bitmap of a volume (emf_bitmap_words_per_row(Rx) * Ry * Rz)."""
     return ((int(res[0]) // 4 + 31) // 32) * int(res[1]) * int(res[2])
+
+
+# ---- resize -----------------------------------------------------------------------------------
+def copyValues(src, dst, offset, srcRes, dstRes, stream=None):
+    """emf::cuda::TSDF::copyValues: dst(x - offset) = src(x) where the target exists; channels from the last dimension"""
+    ch = 1 if src.dim() == 2 else int(src.shape[-1])
+    check(_lib.lib().emf_copy_values(_ptr(src), _ptr(dst), ch, _i3(offset), _i3(srcRes), _i3(dstRes), _stream(stream)),
+          "copyValues")
+    _count("copyValues")
+
+
+def resizeVolume(srcTsdf, srcWeights, srcFgBg, srcRes, dstTsdf, dstWeights, dstFgBg, dstRes, offset, stream=None):
+    check(_lib.lib().emf_resize_volume(_ptr(srcTsdf), _ptr(srcWeights), _ptr(srcFgBg), _i3(srcRes), _ptr(dstTsdf),
+                                       _ptr(dstWeights), _ptr(dstFgBg), _i3(dstRes), _i3(offset), _stream(stream)),
+          "resizeVolume")
+    _count("resizeVolume")
 
 
 # ---- tracker ----------------------------------------------------------------------------------

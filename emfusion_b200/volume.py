@@ -229,6 +229,49 @@ class ObjTSDF(TSDF):
     def _fg_box(self):
         return self.fgBox
 
+    # -- src/core/ObjTSDF.cpp:80-165
+    def resize(self, p10, p90, volPad: float, stream=None) -> np.ndarray:
+        """Grow / recentre the grid so that the box [p10, p90] (object coordinates) fits with padding volPad.  Returns the
+        shift of the volume centre (zeros if the box was already contained).  Host arithmetic as in the reference (float32,
+        cv::Vec3i conversions round to nearest even); the device part is one launch (emf_resize_volume).  A caller that holds
+        this volume in an engine must re-submit the volume list afterwards (the arrays are new allocations)."""
+        f32 = np.float32
+        p10, p90 = np.asarray(p10, dtype=f32), np.asarray(p90, dtype=f32)
+        res = np.array(self.volumeRes, dtype=f32)
+        vs = f32(self.voxelSize)
+        high = ((res - f32(1)) / f32(2)) * vs
+        low = -high
+        if bool(np.all(p10 >= low) and np.all(p90 <= high)):
+            return np.zeros(3, dtype=f32)
+        newCenter = (p10 + p90) / f32(2)
+        pixOffset = np.rint(newCenter / vs).astype(np.int64)             # cv::Vec3i(Vec3f): saturate_cast<int> = cvRound
+        newCenter = pixOffset.astype(f32) * vs
+        self.pose = Affine(self.pose.R, self.pose.t + self.pose.R @ newCenter.astype(np.float64))   # pose.translate(R * c)
+        newDims = p90 - p10
+        newVolSize = f32(volPad) * newDims.max() / vs
+        n = (int(np.ceil(newVolSize)) + 1) // 2 * 2
+        newRes = np.array([n, n, n], dtype=np.int64)
+        pixOffset = pixOffset - np.rint((newRes - np.array(self.volumeRes, dtype=np.int64)) * 0.5).astype(np.int64)   # Vec3i / 2
+        dev = self.device
+        newVol = torch.empty((n * n, n), dtype=torch.float32, device=dev)
+        newWeights = torch.empty((n * n, n), dtype=torch.float32, device=dev)
+        newFgBg = torch.empty((n * n, n, 2), dtype=torch.float32, device=dev)
+        ops.resizeVolume(self.tsdfVol, self.tsdfWeights, self.fgBgProbs, self.volumeRes, newVol, newWeights, newFgBg,
+                         (n, n, n), [int(v) for v in pixOffset], stream)
+        self.tsdfVol, self.tsdfWeights, self.fgBgProbs = newVol, newWeights, newFgBg
+        self.fgProbs = torch.empty((n * n, n), dtype=torch.float32, device=dev)
+        self.volumeRes = (n, n, n)
+        self._grads = None            # rebuilt on demand from the new tsdf (getGrads)
+        self._grads_dirty = True
+        if self.constBits is not None:
+            if n % 4 == 0:
+                self.constBits = torch.zeros((3 * ops.bitmapWords(self.volumeRes),), dtype=torch.int32, device=dev)   # nothing certified
+                self.brickMap = torch.zeros((ops.brickMapBytes(self.volumeRes),), dtype=torch.uint8, device=dev)
+            else:
+                self.constBits = self.brickMap = None
+        self.computeFgProbs(stream)
+        return newCenter
+
     # -- src/core/ObjTSDF.cpp:167-179
     def integrateMask(self, mask, occluded_mask, cam_pose: Affine, intr, stream=None):
         ops.updateFgBgProbs(mask, occluded_mask, self.tsdfVol, self.tsdfWeights, self.fgBgProbs,

@@ -147,6 +147,12 @@ EMF_API int emf_compute_fg_probs(const float* fgbg, int64_t n_voxels, float* fg_
 EMF_API int emf_compute_fg_probs_box(const float* fgbg, const int res[3], float* fg_probs, uint8_t* fg_vol_mask,
                              int32_t* fg_box, emf_stream_t stream);
 
+/* emf::cuda::TSDF::copyValues, include/EMFusion/core/cuda/TSDF.cuh:228-230 (src/core/cuda/TSDF.cu:768-819):
+ * dst(x - offset) = src(x) for every source voxel whose target lies inside dst; the rest of dst is untouched.
+ * channels = floats per voxel (1: tsdf / weights, 2: fg/bg counts, 3: gradients). */
+EMF_API int emf_copy_values(const float* src, float* dst, int channels, const int offset[3], const int src_res[3],
+                    const int dst_res[3], emf_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Level 2: class-surface operations (one call = one reference method).
  * ------------------------------------------------------------------------- */
@@ -158,6 +164,15 @@ EMF_API int emf_compute_fg_probs_box(const float* fgbg, const int res[3], float*
 EMF_API int emf_compute_association(const emf_volume* vol, const emf_image* points, const emf_pose* T_co,
                             const emf_tsdf_params* params, const emf_image* assoc_out,
                             const emf_image* assoc_mask_out, emf_stream_t stream);
+
+/* Device part of emf::ObjTSDF::resize (src/core/ObjTSDF.cpp:116-147): the new tsdf / weights / fg-bg arrays are
+ * written completely in one launch -- copied where the old grid covers the voxel (dst(x) = src(x + offset), the
+ * reference's pixOffset), zero elsewhere -- replacing four setTo(0) and four copyValues passes.  src_fgbg / dst_fgbg
+ * are both NULL for a volume without fg/bg counts.  The gradient volume is not moved: rebuild it with
+ * emf_compute_tsdf_grads if a consumer needs it materialised. */
+EMF_API int emf_resize_volume(const float* src_tsdf, const float* src_weights, const float* src_fgbg, const int src_res[3],
+                      float* dst_tsdf, float* dst_weights, float* dst_fgbg, const int dst_res[3], const int offset[3],
+                      emf_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Level 3: frame-level batched operations (one call = one EMFusion method).

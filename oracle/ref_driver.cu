@@ -581,3 +581,14 @@ REF_API int emfref_tracker_error(void* h, const float* tsdf, const float* points
     *err_out = ref_compute_error(K);
     return status();
 }
+
+// emf::cuda::TSDF::copyValues (src/core/cuda/TSDF.cu:768-819); channels 1 / 2 / 3
+REF_API int emfref_copy_values(const float* src, float* dst, int channels, const int* offset, const int* src_res,
+                               const int* dst_res) {
+    const int type = channels == 1 ? CV_32FC1 : (channels == 2 ? CV_32FC2 : CV_32FC3);
+    GpuMat s = mat((void*)src, src_res[1] * src_res[2], src_res[0], type);
+    GpuMat d = mat(dst, dst_res[1] * dst_res[2], dst_res[0], type);
+    emf::cuda::TSDF::copyValues(s, d, v3i(offset), v3i(src_res), v3i(dst_res));
+    cudaDeviceSynchronize();
+    return status();
+}

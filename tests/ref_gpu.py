@@ -57,6 +57,7 @@ def lib():
         L.emfref_frame_fill_assoc.argtypes = [vp, ci, cf]
         L.emfref_memcpy_d2d.argtypes = [vp, vp, C.c_size_t]
         L.emfref_compute_points.argtypes = [vp, vp, ci, ci, vp]
+        L.emfref_copy_values.argtypes = [vp, vp, ci, vp, vp, vp]
         L.emfref_tracker_create.argtypes = [ci, ci]
         L.emfref_tracker_create.restype = vp
         L.emfref_tracker_destroy.argtypes = [vp]
@@ -209,6 +210,11 @@ def _from_ptr(ptr, shape, dtype):
     torch.cuda.synchronize()
     _chk(lib().emfref_memcpy_d2d(out.data_ptr(), ptr, out.numel() * out.element_size()), "memcpy")
     return out
+
+
+def copy_values(src, dst, channels, offset, src_res, dst_res):
+    ko, po = _h(offset, np.int32); ks, ps = _h(src_res, np.int32); kd, pd = _h(dst_res, np.int32)
+    _chk(lib().emfref_copy_values(src.data_ptr(), dst.data_ptr(), channels, po, ps, pd), "copyValues")
 
 
 class RefTracker:
