@@ -23,7 +23,7 @@ _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1,
                      "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
                      "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
                      "updateBrickMaps": 2, "trackLinearise": 1, "trackNormalisedWeights": 1, "copyValues": 1,
-                     "resizeVolume": 1}
+                     "resizeVolume": 1, "preprocessDepth": 1}
 
 
 def _count(name: str) -> None:
@@ -295,6 +295,14 @@ def resetBitmaps(vol: Volume, stream=None):
 def bitmapWords(res) -> int:
     """32-bit words of ONE segment bitmap of a volume (emf_bitmap_words_per_row(Rx) * Ry * Rz)."""
     return ((int(res[0]) // 4 + 31) // 32) * int(res[1]) * int(res[2])
+
+
+def preprocessDepth(depth_raw, depth, points=None, intr=None, kernel_size=7, sigma_depth=0.04, sigma_spatial=4.5, stream=None):
+    """EMFusion::preprocessDepth (+ computePoints when `points` is given) in one launch"""
+    check(_lib.lib().emf_preprocess_depth(image(depth_raw), image(depth), image(points) if points is not None else None,
+                                          _f9(intr) if intr is not None else None, int(kernel_size), float(sigma_depth),
+                                          float(sigma_spatial), _stream(stream)), "preprocessDepth")
+    _count("preprocessDepth")
 
 
 # ---- resize -----------------------------------------------------------------------------------

@@ -102,6 +102,14 @@ typedef struct emf_volume {
  * (src/core/cuda/EMFusion.cu:29-61).  depth: W x H f32; points: W x H float3. */
 EMF_API int emf_compute_points(const emf_image* depth, const emf_image* points, const float K[9], emf_stream_t stream);
 
+/* emf::EMFusion::preprocessDepth, src/core/EMFusion.cpp:294-305 (cv::cuda::bilateralFilter + NaN patch + zero patch; five
+ * launches) fused with computePoints when points_out != NULL: one launch.  depth_raw, depth_out: W x H f32 (distinct);
+ * kernel_size / sigma_depth / sigma_spatial = Params::bilateral_kernel_size / _sigma_depth / _sigma_spatial (7, 0.04 m,
+ * 4.5 px, include/EMFusion/core/data.h:92-94).  PARITY UNPINNED: the filter arithmetic is OpenCV-CUDA's (un-vendored,
+ * absent here); its published kernel is restated (csrc/preprocess.cu). */
+EMF_API int emf_preprocess_depth(const emf_image* depth_raw, const emf_image* depth_out, const emf_image* points_out,
+                         const float K[9], int kernel_size, float sigma_depth, float sigma_spatial, emf_stream_t stream);
+
 /* emf::cuda::TSDF::updateTSDF, include/EMFusion/core/cuda/TSDF.cuh:115-123
  * (src/core/cuda/TSDF.cu:327-427).  T_oc = cam_pose^-1 * pose. */
 EMF_API int emf_update_tsdf(const emf_image* depth, const emf_image* assoc_weights, float* tsdf, float* weights,

@@ -605,6 +605,48 @@ EMFO_API void emfo_track_linearise(const float* tsdf, const float* grads_vol, co
     if (wmax_out) *wmax_out = nrm;
 }
 
+/* ------------------------------------------------------------------------
+ * Depth pre-filter: emf::EMFusion::preprocessDepth, src/core/EMFusion.cpp:294-305.
+ * cv::cuda::bilateralFilter is OpenCV-CUDA code (un-vendored, version unpinned): PARITY UNPINNED -- its published kernel
+ * (opencv_contrib cudaimgproc bilateral_filter.cu) is restated: disc of radius ksize/2, float accumulation in row-major
+ * window order, exp(space2 * (-0.5/ss^2) + diff^2 * (-0.5/sc^2)), BORDER_REFLECT_101, sum1 / sum2; then NaN -> 0 and
+ * raw == 0 -> 0.
+ * ---------------------------------------------------------------------- */
+static int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+EMFO_API void emfo_preprocess_depth(const float* raw, int w, int h, int kernel_size, float sigma_depth, float sigma_spatial,
+                                    float* out) {
+    if (sigma_depth <= 0.0f) sigma_depth = 1.0f;
+    if (sigma_spatial <= 0.0f) sigma_spatial = 1.0f;
+    int r = kernel_size <= 0 ? (int)lrintf(sigma_spatial * 1.5f) : kernel_size / 2;
+    if (r < 1) r = 1;
+    const float ss = -0.5f / (sigma_spatial * sigma_spatial), sc = -0.5f / (sigma_depth * sigma_depth);
+    const float r2 = (float)(r * r);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const float centre = raw[(size_t)y * w + x];
+            float sum1 = 0.0f, sum2 = 0.0f;
+            for (int dy = -r; dy <= r; ++dy)
+                for (int dx = -r; dx <= r; ++dx) {
+                    const float space2 = (float)(dx * dx + dy * dy);
+                    if (space2 > r2) continue;
+                    const float v = raw[(size_t)reflect101(y + dy, h) * w + reflect101(x + dx, w)];
+                    const float d = v - centre;
+                    const float wgt = expf(FMA(space2, ss, (d * d) * sc));
+                    sum1 = FMA(wgt, v, sum1);
+                    sum2 = sum2 + wgt;
+                }
+            float res = sum1 / sum2;
+            if (res != res) res = 0.0f;
+            if (centre == 0.0f) res = 0.0f;
+            out[(size_t)y * w + x] = res;
+        }
+}
+
 EMFO_API int emfo_uses_fma(void) {
 #ifdef EMFO_NOFMA
     return 0;

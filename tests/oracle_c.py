@@ -41,6 +41,8 @@ class Oracle:
         L.emfo_track_linearise.argtypes = [_f, _f, _f, _f, _f, C.c_int, C.c_int, _f, _f, _i32, C.c_float, C.c_float,
                                            C.c_float, _f, _f, _f, _f, _d, _d, _d, _d]
         L.emfo_track_linearise.restype = None
+        L.emfo_preprocess_depth.argtypes = [_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _f]
+        L.emfo_preprocess_depth.restype = None
         L.emfo_uses_fma.restype = C.c_int
         for n in ("emfo_compute_points", "emfo_update_tsdf", "emfo_compute_grads", "emfo_raycast",
                   "emfo_get_volume_vals", "emfo_assoc_volume", "emfo_normalise", "emfo_composite",
@@ -159,6 +161,12 @@ class Oracle:
                                     maxw, g6, vals, iw, tw, A, b, err, wmax)
         return dict(grads=g6, tsdfVals=vals, intWeights=iw, trackWeights=tw, A=A.reshape(6, 6), b=b, err=float(err[0]),
                     wmax=float(wmax[0]))
+
+    def preprocess_depth(self, raw, kernel_size=7, sigma_depth=0.04, sigma_spatial=4.5):
+        h, w = raw.shape
+        out = np.empty((h, w), dtype=np.float32)
+        self.L.emfo_preprocess_depth(np.ascontiguousarray(raw, dtype=np.float32), w, h, kernel_size, sigma_depth, sigma_spatial, out)
+        return out
 
     def uses_fma(self) -> bool:
         return bool(self.L.emfo_uses_fma())
