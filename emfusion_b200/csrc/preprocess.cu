@@ -9,7 +9,7 @@
 // README.md:42-43).  Its published kernel is restated: window = the disc of radius ksize / 2 inside the ksize x ksize
 // square, weight = exp(space2 * (-0.5 / sigma_spatial^2) + (v - centre)^2 * (-0.5 / sigma_depth^2)), border
 // BORDER_REFLECT_101, result = sum(w v) / sum(w); rows outermost, columns innermost, float accumulation.  Checked against
-// an independent C restatement (oracle/emf_oracle.c) -- not against OpenCV itself.
+// an independent scalar C restatement under the test tree -- not against OpenCV itself.
 #include "common.cuh"
 
 namespace emfb {
