@@ -43,6 +43,11 @@ class Volume(C.Structure):
                 ("const_bits", C.c_void_p), ("brick_map", C.c_void_p), ("res", C.c_int * 3), ("voxel_size", C.c_float), ("truncdist", C.c_float), ("id", C.c_int)]
 
 
+class TrackLMParams(C.Structure):
+    _fields_ = [("tau", C.c_float), ("eps1", C.c_float), ("eps2", C.c_float), ("nu_init", C.c_float),
+                ("huber_thresh", C.c_float), ("max_tsdf_weight", C.c_float)]
+
+
 class EngineConfig(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("K", C.c_float * 9), ("params", TsdfParams),
                 ("boundary", C.c_int), ("visibility_thresh", C.c_int)]
@@ -96,6 +101,8 @@ _SIGS = {
     "emf_track_workspace_init": [C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_track_linearise": [C.c_int, _P(Volume), _P(Pose), _P(C.c_int), _P(Image), _P(C.c_float), _P(Image), C.c_float, C.c_float,
                             _P(Image), _P(Image), _P(Image), _P(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    "emf_track_iterate": [C.c_int, _P(Volume), C.c_void_p, _P(Pose), _P(Image), _P(C.c_float), _P(Image), _P(TrackLMParams),
+                          _P(Image), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p],
     "emf_track_normalised_weights": [_P(Image), C.c_void_p, _P(Image), C.c_void_p],
     "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],
 }

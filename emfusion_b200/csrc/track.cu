@@ -62,6 +62,12 @@ struct TrackParams {
     float* out;            // n_vol x EMF_TRACK_RECORD floats
     double* slots;         // n_vol x kTrackCtasPerVol x kTrackAcc
     unsigned* tickets;     // n_vol
+    // device-resident Levenberg-Marquardt loop (emf_track_iterate): poses, modes and tile rectangles come from `states`, and
+    // the last CTA of a volume runs the host part of the iteration (TSDF::reduceHessians / computePoseUpdate)
+    emf_track_state* states;   // nullptr: poses / modes from the table above (emf_track_linearise)
+    int phase;                 // 0: linearise (or error only) at the current pose, then the step; 1: the trial pose, then accept / reject
+    float K[9];
+    float tau, eps1, eps2, nu_init;
 };
 
 // gradient at an integer voxel: the materialised volume, or forward differences with a zero last plane per axis
@@ -81,11 +87,207 @@ __device__ __forceinline__ void track_grad_at(const TrackVol& V, int x, int y, i
     g[2] = fsub(__ldg(p + (int64_t)V.ry * V.rx), f);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The host part of one tracker iteration, on the device (one thread).  Statement by statement emf::TSDF::reduceHessians
+// (reference src/core/TSDF.cpp:267-283) and computePoseUpdate (:285-338); the pose algebra is Sophus' SE3 exp / log in double.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ void lm_so3_exp(const double w[3], double R[9]) {
+    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+    double a, b;
+    if (th < 1e-10) { a = 1.0; b = 0.5; } else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; }
+    const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double oo = 0;
+            for (int k = 0; k < 3; ++k) oo += O[3 * i + k] * O[3 * k + j];
+            R[3 * i + j] = (i == j ? 1.0 : 0.0) + a * O[3 * i + j] + b * oo;
+        }
+}
+__device__ void lm_se3_exp(const double x[6], double R[9], double t[3]) {
+    const double* u = x; const double* w = x + 3;
+    lm_so3_exp(w, R);
+    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+    double b, c;
+    if (th < 1e-10) { b = 0.5; c = 0.0; } else { b = (1.0 - cos(th)) / th2; c = (th - sin(th)) / (th2 * th); }
+    const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0;
+        for (int j = 0; j < 3; ++j) {
+            double oo = 0;
+            for (int k = 0; k < 3; ++k) oo += O[3 * i + k] * O[3 * k + j];
+            acc += ((i == j ? 1.0 : 0.0) + b * O[3 * i + j] + c * oo) * u[j];
+        }
+        t[i] = acc;
+    }
+}
+// |log(T)| of a rigid transform (only the norm of the twist is needed, :299)
+__device__ double lm_se3_log_norm(const double R[9], const double t[3]) {
+    double c = (R[0] + R[4] + R[8] - 1.0) * 0.5;
+    c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+    const double th = acos(c);
+    double v[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]}, w[3];
+    if (th < 1e-10) { for (int k = 0; k < 3; ++k) w[k] = 0.5 * v[k]; }
+    else if (3.14159265358979323846 - th < 1e-6) {
+        double ax[3] = {sqrt(fmax((R[0] + 1.0) * 0.5, 0.0)), sqrt(fmax((R[4] + 1.0) * 0.5, 0.0)), sqrt(fmax((R[8] + 1.0) * 0.5, 0.0))};
+        int k = ax[0] >= ax[1] ? (ax[0] >= ax[2] ? 0 : 2) : (ax[1] >= ax[2] ? 1 : 2);
+        double col[3] = {(R[k] + (k == 0)) * 0.5, (R[3 + k] + (k == 1)) * 0.5, (R[6 + k] + (k == 2)) * 0.5};
+        double n = 0; for (int i = 0; i < 3; ++i) { col[i] /= ax[k]; n += col[i] * col[i]; }
+        n = sqrt(n);
+        const double sgn = (col[0] * v[0] + col[1] * v[1] + col[2] * v[2]) < 0 ? -1.0 : 1.0;
+        for (int i = 0; i < 3; ++i) w[i] = sgn * th * col[i] / n;
+    } else { const double f = th / (2.0 * sin(th)); for (int k = 0; k < 3; ++k) w[k] = f * v[k]; }
+    const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double g;
+    if (th < 1e-10) g = 1.0 / 12.0; else { const double hf = 0.5 * th; g = (1.0 - th * cos(hf) / (2.0 * sin(hf))) / (th * th); }
+    double n2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0;
+        for (int j = 0; j < 3; ++j) {
+            double oo = 0;
+            for (int k = 0; k < 3; ++k) oo += O[3 * i + k] * O[3 * k + j];
+            acc += ((i == j ? 1.0 : 0.0) - 0.5 * O[3 * i + j] + g * oo) * t[j];
+        }
+        n2 += acc * acc;
+    }
+    return sqrt(n2);
+}
+// x = M^-1 b by LU with partial pivoting in float (cv::solve, DECOMP_LU, on a 6 x 6 float system); false if singular
+__device__ bool lm_solve6(const float A[36], float mu, const float b[6], float x[6]) {
+    float M[6][7];
+    for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) M[i][j] = A[6 * i + j] + (i == j ? mu : 0.0f); M[i][6] = b[i]; }
+    for (int c = 0; c < 6; ++c) {
+        int p = c;
+        for (int r = c + 1; r < 6; ++r) if (fabsf(M[r][c]) > fabsf(M[p][c])) p = r;
+        if (fabsf(M[p][c]) < 1.1920929e-6f) return false;        // FLT_EPSILON * 10, as cv::LU for float
+        if (p != c) for (int j = 0; j < 7; ++j) { const float tmp = M[c][j]; M[c][j] = M[p][j]; M[p][j] = tmp; }
+        const float d = -1.0f / M[c][c];
+        for (int r = c + 1; r < 6; ++r) {
+            const float f = M[r][c] * d;
+            for (int j = c + 1; j < 7; ++j) M[r][j] += f * M[c][j];
+        }
+    }
+    for (int i = 5; i >= 0; --i) {
+        float v = M[i][6];
+        for (int j = i + 1; j < 6; ++j) v -= M[i][j] * x[j];
+        x[i] = v / M[i][i];
+    }
+    return true;
+}
+// tile rectangle of the pixels whose point can lie inside the volume's grid, for pose (R, t) = T_co (as box_screen_rect)
+__device__ void lm_tile_rect(const TrackVol& V, const double R[9], const double t[3], const float K[9], int w, int h, int rect[4]) {
+    const int tiles_x = (w + 31) / 32, tiles_y = (h + 7) / 8;
+    const double b[3] = {(0.5 * V.rx + 1.0) * V.voxel, (0.5 * V.ry + 1.0) * V.voxel, (0.5 * V.rz + 1.0) * V.voxel};
+    double x0 = 1e30, y0 = 1e30, x1 = -1e30, y1 = -1e30;
+    bool full = false;
+    for (int c = 0; c < 8 && !full; ++c) {
+        const double p[3] = {(c & 1 ? b[0] : -b[0]) - t[0], (c & 2 ? b[1] : -b[1]) - t[1], (c & 4 ? b[2] : -b[2]) - t[2]};
+        double q[3];
+        for (int k = 0; k < 3; ++k) q[k] = R[k] * p[0] + R[3 + k] * p[1] + R[6 + k] * p[2];
+        if (q[2] < 1e-3) { full = true; break; }
+        const double u = K[0] * q[0] + K[1] * q[1] + K[2] * q[2], v = K[3] * q[0] + K[4] * q[1] + K[5] * q[2];
+        const double wq = K[6] * q[0] + K[7] * q[1] + K[8] * q[2];
+        if (wq < 1e-6) { full = true; break; }
+        x0 = fmin(x0, u / wq); x1 = fmax(x1, u / wq); y0 = fmin(y0, v / wq); y1 = fmax(y1, v / wq);
+    }
+    if (full) { rect[0] = 0; rect[1] = 0; rect[2] = tiles_x; rect[3] = tiles_y; return; }
+    int ix0 = (int)floor(x0) - 2, iy0 = (int)floor(y0) - 2, ix1 = (int)ceil(x1) + 3, iy1 = (int)ceil(y1) + 3;
+    ix0 = max(ix0, 0); iy0 = max(iy0, 0); ix1 = min(ix1, w); iy1 = min(iy1, h);
+    if (ix1 <= ix0 || iy1 <= iy0) { rect[0] = rect[1] = rect[2] = rect[3] = 0; return; }
+    rect[0] = ix0 / 32; rect[1] = iy0 / 8; rect[2] = (ix1 + 31) / 32; rect[3] = (iy1 + 7) / 8;
+}
+
+// after the sums of a launch are known (thread 0 of the volume's last CTA).  rec = the volume's record.
+__device__ void lm_step(const TrackParams& P, const TrackVol& V, emf_track_state& S, const float* rec, int mode) {
+    if (P.phase == 0) {
+        S.iterations += 1;
+        if (mode == 1) {
+            S.linearisations += 1;
+            float bmax = 0.0f;
+            for (int k = 0; k < 36; ++k) S.A[k] = rec[k];
+            for (int k = 0; k < 6; ++k) { S.b[k] = rec[36 + k]; bmax = fmaxf(bmax, fabsf(rec[36 + k])); }
+            if (bmax < P.eps1) { S.converged = 1; return; }                       // reduceHessians (:278-282)
+        }
+        S.err = rec[42];
+        if (S.first_iteration) {                                                   // (:290-295)
+            float dmax = S.A[0];
+            for (int k = 1; k < 6; ++k) dmax = fmaxf(dmax, S.A[7 * k]);
+            S.mu = (double)P.tau * (double)dmax;
+            S.first_iteration = 0;
+        }
+        float x[6];
+        for (int k = 0; k < 6; ++k) x[k] = S.x[k];
+        if (lm_solve6(S.A, (float)S.mu, S.b, x)) for (int k = 0; k < 6; ++k) S.x[k] = x[k];
+        float xn = 0.0f;
+        for (int k = 0; k < 6; ++k) xn += S.x[k] * S.x[k];
+        xn = sqrtf(xn);
+        if ((double)xn < (double)P.eps2 * (lm_se3_log_norm(S.R, S.t) + (double)P.eps2)) { S.converged = 1; return; }   // (:298-302)
+        double mx[6], Ri[9], ti[3];
+        for (int k = 0; k < 6; ++k) { mx[k] = -(double)S.x[k]; }
+        lm_se3_exp(mx, Ri, ti);
+        for (int k = 0; k < 9; ++k) S.R_old[k] = S.R[k];
+        for (int k = 0; k < 3; ++k) S.t_old[k] = S.t[k];
+        double Rn[9], tn[3];                                                       // pose_incr * rel_pose_CO (:308-310)
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j)
+                Rn[3 * i + j] = (Ri[3 * i] * S.R_old[j] + Ri[3 * i + 1] * S.R_old[3 + j]) + Ri[3 * i + 2] * S.R_old[6 + j];
+            tn[i] = ((Ri[3 * i] * S.t_old[0] + Ri[3 * i + 1] * S.t_old[1]) + Ri[3 * i + 2] * S.t_old[2]) + ti[i];
+        }
+        for (int k = 0; k < 9; ++k) S.R[k] = Rn[k];
+        for (int k = 0; k < 3; ++k) S.t[k] = tn[k];
+        S.trial_pending = 1;
+    } else {
+        S.err_new = rec[42];                                                       // (:312-315)
+        float g = 0.0f;
+        for (int k = 0; k < 6; ++k) g += -S.x[k] * ((float)S.mu * -S.x[k] - S.b[k]);
+        g *= 0.5f;
+        S.rho = g != 0.0f ? ((double)S.err - (double)S.err_new) / (double)g : -1.0;
+        if (S.rho > 0.0) {                                                         // (:320-326)
+            const double c = 2.0 * S.rho - 1.0;
+            S.mu *= fmax(1.0 / 3.0, 1.0 - c * c * c);
+            S.nu = (double)P.nu_init;
+            S.evaluate_gradient = 1;
+        } else {                                                                   // (:327-336)
+            for (int k = 0; k < 9; ++k) S.R[k] = S.R_old[k];
+            for (int k = 0; k < 3; ++k) S.t[k] = S.t_old[k];
+            S.mu *= S.nu;
+            S.nu *= (double)P.nu_init;
+            S.evaluate_gradient = 0;
+            }
+        S.trial_pending = 0;
+    }
+}
+
 __global__ void __launch_bounds__(kTrackThreads, 2) k_track(const __grid_constant__ TrackParams P) {
     const int vi = blockIdx.y;
     const TrackVol& V = P.v[vi];
-    if (V.mode == 0 || (int)blockIdx.x >= V.n_cta) return;
-    const bool lin = V.mode == 1;
+    int mode = V.mode;
+    float Rm[9], tm[3];
+    int tx0 = V.tx0, ty0 = V.ty0, tx1 = V.tx1, ty1 = V.ty1, lx0 = V.lx0, ly0 = V.ly0, ltx = V.ltx, ltiles = V.ltiles;
+    float inv_ltx = V.inv_ltx;
+    if (P.states) {
+        // (the last CTA of this volume rewrites the state only after every CTA of the volume has passed its ticket, i.e.
+        //  after all of them have read it here)
+        const emf_track_state& S = P.states[vi];
+        if (mode != 0) mode = P.phase == 0 ? (S.converged ? 0 : (S.evaluate_gradient ? 1 : 2)) : (S.trial_pending ? 2 : 0);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rm[k] = (float)S.R[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tm[k] = (float)S.t[k];
+        __shared__ int s_rect[4];
+        if (threadIdx.x == 0 && mode != 0) lm_tile_rect(V, S.R, S.t, P.K, P.w, P.h, s_rect);
+        __syncthreads();
+        tx0 = s_rect[0]; ty0 = s_rect[1]; tx1 = s_rect[2]; ty1 = s_rect[3];
+        lx0 = tx0; ly0 = ty0; ltx = tx1 - tx0; ltiles = ltx * (ty1 - ty0);
+        inv_ltx = ltx > 0 ? 1.0f / (float)ltx : 0.0f;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rm[k] = V.R[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tm[k] = V.t[k];
+    }
+    if (mode == 0 || (int)blockIdx.x >= V.n_cta) return;
+    const bool lin = mode == 1;
     const unsigned n_cta = (unsigned)V.n_cta;
     float acc[kTrackAcc];
 #pragma unroll
@@ -100,12 +302,12 @@ __global__ void __launch_bounds__(kTrackThreads, 2) k_track(const __grid_constan
         const unsigned a = __float_as_uint(out[45]), b = __float_as_uint(out[46]);
         wx0 = a & 0xffff; wx1 = a >> 16; wy0 = b & 0xffff; wy1 = b >> 16;
     }
-    for (int tile = blockIdx.x; tile < V.ltiles; tile += n_cta) {
-        const int tyl = __float2int_rz(((float)tile + 0.5f) * V.inv_ltx);   // tile / ltx (exact: tile < 2^20)
-        const int tx = V.lx0 + tile - tyl * V.ltx, ty = V.ly0 + tyl;
+    for (int tile = blockIdx.x; tile < ltiles; tile += n_cta) {
+        const int tyl = __float2int_rz(((float)tile + 0.5f) * inv_ltx);   // tile / ltx (exact: tile < 2^20)
+        const int tx = lx0 + tile - tyl * ltx, ty = ly0 + tyl;
         const int x = tx * 32 + (threadIdx.x & 31), y = ty * 8 + (threadIdx.x >> 5);
         if (x >= P.w || y >= P.h) continue;
-        if (tx < V.tx0 || tx >= V.tx1 || ty < V.ty0 || ty >= V.ty1) {
+        if (tx < tx0 || tx >= tx1 || ty < ty0 || ty >= ty1) {
             // (only when complete optional images were asked for) no point of this tile can gather from the volume:
             // every per-pixel quantity is 0 there
             if (V.vals) *((float*)((char*)V.vals + (size_t)y * V.vals_pitch) + x) = 0.0f;
@@ -125,9 +327,9 @@ __global__ void __launch_bounds__(kTrackThreads, 2) k_track(const __grid_constan
         float f = 0.0f, wint = 0.0f;
         float J[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (!(pz <= 0.0f)) {
-            const float qx = fadd(V.t[0], dot_xyz(V.R[0], V.R[1], V.R[2], px, py, pz));
-            const float qy = fadd(V.t[1], dot_xyz(V.R[3], V.R[4], V.R[5], px, py, pz));
-            const float qz = fadd(V.t[2], dot_xyz(V.R[6], V.R[7], V.R[8], px, py, pz));
+            const float qx = fadd(tm[0], dot_xyz(Rm[0], Rm[1], Rm[2], px, py, pz));
+            const float qy = fadd(tm[1], dot_xyz(Rm[3], Rm[4], Rm[5], px, py, pz));
+            const float qz = fadd(tm[2], dot_xyz(Rm[6], Rm[7], Rm[8], px, py, pz));
             const float vx = fadd(hx, fdiv(qx, V.voxel)), vy = fadd(hy, fdiv(qy, V.voxel)), vz = fadd(hz, fdiv(qz, V.voxel));
             if (!out_of(vx, vy, vz, 1.0f, frx, fry, frz)) {           // getVolumeVals (TSDF.cu:680-684)
                 f = trilinear(V.tsdf, V.rx, V.ry, vx, vy, vz);
@@ -257,11 +459,15 @@ __global__ void __launch_bounds__(kTrackThreads, 2) k_track(const __grid_constan
             out[42] = (float)(s_tot[27] * (double)scale);
             out[43] = (float)wmax;
             out[44] = scale;
-            out[45] = __uint_as_float((unsigned)V.tx0 | ((unsigned)V.tx1 << 16));   // where int_weights is defined
-            out[46] = __uint_as_float((unsigned)V.ty0 | ((unsigned)V.ty1 << 16));
+            out[45] = __uint_as_float((unsigned)tx0 | ((unsigned)tx1 << 16));   // where int_weights is defined
+            out[46] = __uint_as_float((unsigned)ty0 | ((unsigned)ty1 << 16));
         }
     } else if (threadIdx.x == 0) {
         out[42] = (float)(s_tot[27] * (double)out[44]);
+    }
+    if (P.states) {      // the host part of the iteration, here
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); lm_step(P, V, P.states[vi], out, mode); }
     }
     if (threadIdx.x == 0) P.tickets[vi] = 0;   // ready for the next launch on this stream
 }
@@ -360,6 +566,9 @@ extern "C" EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, co
     P.out = records;
     P.tickets = (unsigned*)workspace;                       // fixed place: they return to 0 after every launch
     P.slots = (double*)((char*)workspace + kTrackTicketBytes);
+    P.states = nullptr; P.phase = 0;
+    for (int k = 0; k < 9; ++k) P.K[k] = K ? K[k] : 0.0f;
+    P.tau = P.eps1 = P.eps2 = P.nu_init = 0.0f;
     const dim3 grid(max_cta, n_vol);
     k_track<<<grid, kTrackThreads, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
@@ -375,5 +584,64 @@ extern "C" EMF_API int emf_track_normalised_weights(const emf_image* int_weights
     if (!record || !image_ok(int_weights, 4) || !image_ok(out, 4) || !same_size(int_weights, out)) return EMF_ERR_INVALID;
     const dim3 grid((out->width + 31) / 32, (out->height + 7) / 8);
     k_track_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(view<const float>(int_weights), view<float>(out), record);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_track_iterate(int n_vol, const emf_volume* vols, emf_track_state* states, const emf_pose* T_co_hint,
+                                         const emf_image* points, const float K[9], const emf_image* assoc,
+                                         const emf_track_lm_params* lm, const emf_image* int_weights, float* records,
+                                         void* workspace, size_t workspace_bytes, int n_iterations, emf_stream_t stream) {
+    if (n_vol <= 0 || !vols || !states || !T_co_hint || !K || !assoc || !lm || !int_weights || !records || !workspace ||
+        !image_ok(points, 12) || n_iterations < 0)
+        return EMF_ERR_INVALID;
+    if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
+    if (workspace_bytes < emf_track_workspace_bytes(n_vol) || !aligned16(workspace)) return EMF_ERR_INVALID;
+    TrackParams P;
+    const int w = points->width, h = points->height;
+    const int tiles_x = (w + 31) / 32, tiles_y = (h + 7) / 8;
+    if (tiles_x > 0xffff || tiles_y > 0xffff || tiles_x * tiles_y >= (1 << 20)) return EMF_ERR_UNSUPPORTED;
+    int max_cta = 1;
+    for (int i = 0; i < n_vol; ++i) {
+        TrackVol& d = P.v[i];
+        const emf_volume& v = vols[i];
+        if (!v.tsdf || !v.weights || !res_ok(v.res)) return EMF_ERR_INVALID;
+        if (!image_ok(&int_weights[i], 4) || int_weights[i].width != w || int_weights[i].height != h) return EMF_ERR_INVALID;
+        if (!image_ok(&assoc[i], 4) || assoc[i].width != w || assoc[i].height != h) return EMF_ERR_INVALID;
+        d.mode = 1;       // the real mode of a launch is derived from the volume's state on the device
+        d.tsdf = v.tsdf; d.weights = v.weights; d.grads = v.grads;
+        d.assoc = (const float*)assoc[i].ptr; d.assoc_pitch = assoc[i].pitch;
+        d.wimg = (float*)int_weights[i].ptr; d.wimg_pitch = int_weights[i].pitch;
+        d.vals = nullptr; d.vals_pitch = 0; d.huber = nullptr; d.huber_pitch = 0; d.g6 = nullptr;
+        for (int k = 0; k < 9; ++k) d.R[k] = T_co_hint[i].R[k];
+        for (int k = 0; k < 3; ++k) d.t[k] = T_co_hint[i].t[k];
+        d.rx = v.res[0]; d.ry = v.res[1]; d.rz = v.res[2];
+        d.voxel = v.voxel_size;
+        // the grid of a volume is sized by the rectangle of its starting pose (the rectangle itself follows the pose on the device)
+        const double b[3] = {(0.5 * v.res[0] + 1.0) * v.voxel_size, (0.5 * v.res[1] + 1.0) * v.voxel_size, (0.5 * v.res[2] + 1.0) * v.voxel_size};
+        int r[4];
+        box_screen_rect(b, &T_co_hint[i], K, w, h, r);
+        d.tx0 = r[0] / 32; d.ty0 = r[1] / 8; d.tx1 = (r[2] + 31) / 32; d.ty1 = (r[3] + 7) / 8;
+        d.lx0 = d.tx0; d.ly0 = d.ty0; d.ltx = d.tx1 - d.tx0; d.ltiles = d.ltx * (d.ty1 - d.ty0); d.inv_ltx = 0.0f;
+        d.n_cta = (d.ltiles + 3) / 4;
+        if (d.n_cta < 1) d.n_cta = 1;
+        if (d.n_cta > kTrackCtasPerVol) d.n_cta = kTrackCtasPerVol;
+        if (d.n_cta > max_cta) max_cta = d.n_cta;
+    }
+    P.n_vol = n_vol; P.w = w; P.h = h;
+    P.points = (const float*)points->ptr; P.points_pitch = points->pitch;
+    P.huber_thresh = lm->huber_thresh; P.max_weight = lm->max_tsdf_weight;
+    P.out = records;
+    P.tickets = (unsigned*)workspace;
+    P.slots = (double*)((char*)workspace + kTrackTicketBytes);
+    P.states = states;
+    for (int k = 0; k < 9; ++k) P.K[k] = K[k];
+    P.tau = lm->tau; P.eps1 = lm->eps1; P.eps2 = lm->eps2; P.nu_init = lm->nu_init;
+    const dim3 grid(max_cta, n_vol);
+    for (int it = 0; it < n_iterations; ++it) {
+        P.phase = 0;
+        k_track<<<grid, kTrackThreads, 0, (cudaStream_t)stream>>>(P);
+        P.phase = 1;
+        k_track<<<grid, kTrackThreads, 0, (cudaStream_t)stream>>>(P);
+    }
     return launch_status();
 }

@@ -23,7 +23,7 @@ _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1,
                      "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
                      "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
                      "updateBrickMaps": 2, "trackLinearise": 1, "trackNormalisedWeights": 1, "copyValues": 1,
-                     "resizeVolume": 1, "preprocessDepth": 1}
+                     "resizeVolume": 1, "preprocessDepth": 1, "trackIterate": 2}
 
 
 def _count(name: str) -> None:
@@ -409,3 +409,38 @@ class TrackPlan:
                        _stream(stream)), "trackLinearise")
         if any(modes):
             _count("trackLinearise")
+
+
+# emf_track_state (include/emf_b200.h) as a numpy record: what the host initialises and reads back
+TRACK_STATE_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("R_old", "<f8", (9,)), ("t_old", "<f8", (3,)),
+                              ("mu", "<f8"), ("nu", "<f8"), ("rho", "<f8"), ("A", "<f4", (36,)), ("b", "<f4", (6,)),
+                              ("x", "<f4", (6,)), ("err", "<f4"), ("err_new", "<f4"), ("converged", "<i4"),
+                              ("first_iteration", "<i4"), ("evaluate_gradient", "<i4"), ("trial_pending", "<i4"),
+                              ("iterations", "<i4"), ("linearisations", "<i4")], align=True)
+
+
+class TrackLoopPlan:
+    """emf_track_iterate with its arguments marshalled once: the device-resident Levenberg-Marquardt loop"""
+
+    def __init__(self, vols, states, rel_poses_CO, points, intr, assoc, params, intWeights, records):
+        n = self.n = len(vols)
+        if states.dtype != torch.uint8 or states.numel() != n * TRACK_STATE_DTYPE.itemsize:
+            raise _lib.EmfError("states must be a uint8 CUDA tensor of n_vol emf_track_state records")
+        self._keep = (vols, states, points, assoc, intWeights, records)
+        self._vols = _vol_array(vols)
+        self._states = _ptr(states)
+        self._hint = poses(rel_poses_CO)
+        self._points = image(points)
+        self._K = _f9(intr)
+        self._assoc = images(assoc)
+        self._iw = images(intWeights)
+        self._rec = _ptr(records)
+        self._ws = trackWorkspace(points.device, n)
+        self._lm = _lib.TrackLMParams(params.tau, params.eps1, params.eps2, params.nu_init, params.huberThresh, params.maxTSDFWeight)
+        self._fn = _lib.lib().emf_track_iterate
+
+    def enqueue(self, n_iterations: int, stream=None):
+        check(self._fn(self.n, self._vols, self._states, self._hint, self._points, self._K, self._assoc, C.byref(self._lm),
+                       self._iw, self._rec, self._ws.data_ptr(), self._ws.numel(), int(n_iterations), _stream(stream)),
+              "trackIterate")
+        LAUNCHES["trackIterate"] = LAUNCHES.get("trackIterate", 0) + 2 * int(n_iterations)

@@ -218,6 +218,66 @@ class Tracker:
                     s.evaluateGradient = False
         return S
 
+    def track_device(self, points: torch.Tensor, assoc: Sequence[torch.Tensor], cam_pose: Affine, maxTrackingIter: int = 100,
+                     chunk: int = 4):
+        """The same loop with its host part on the device (emf_track_iterate): iterations are enqueued `chunk` at a time and
+        nothing is waited for in between -- a copy of the states follows every chunk and is looked at only once it has
+        arrived (never blocking unless four chunks are in flight), to stop enqueuing when every volume has converged.
+        Needs the camera matrix (Tracker(..., intr=K))."""
+        if self.intr is None:
+            raise _lib.EmfError("track_device needs the camera matrix: Tracker(..., intr=K)")
+        S = self.states
+        n = len(S)
+        for s in S:
+            s.prepareTracking(cam_pose)
+        prm = S[0].vol.params
+        st = np.zeros(n, dtype=ops.TRACK_STATE_DTYPE)
+        for i, s in enumerate(S):
+            st["R"][i] = s.rel_pose_CO.R.reshape(9); st["t"][i] = s.rel_pose_CO.t
+            st["nu"][i] = float(prm.nu_init)
+            st["first_iteration"][i] = 1; st["evaluate_gradient"][i] = 1
+        nbytes = st.nbytes
+        dev = torch.from_numpy(st.view(np.uint8).copy()).to(self.device)
+        cv = [s.vol.c_volume(with_grads=True) for s in S]
+        plan = ops.TrackLoopPlan(cv, dev, [s.rel_pose_CO for s in S], points, self.intr, assoc, prm,
+                                 [s.intWeights for s in S], self.records)
+        ring = [(torch.empty((nbytes,), dtype=torch.uint8).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+        pending = []          # indices into the ring, oldest first
+        issued, k_ring, all_done = 0, 0, False
+
+        def converged(buf) -> bool:
+            return bool(np.all(buf.numpy().view(ops.TRACK_STATE_DTYPE)["converged"] != 0))
+        while issued < maxTrackingIter and not all_done:
+            k = min(chunk, maxTrackingIter - issued)
+            plan.enqueue(k)
+            issued += k
+            if len(pending) == len(ring):                 # bound the run-ahead: wait for the oldest snapshot
+                j = pending.pop(0)
+                ring[j][1].synchronize()
+                self.device_reads += 1
+                all_done = converged(ring[j][0])
+            j = k_ring % len(ring); k_ring += 1
+            ring[j][0].copy_(dev, non_blocking=True)
+            ring[j][1].record()
+            pending.append(j)
+            while pending and ring[pending[0]][1].query():   # snapshots that have arrived (no waiting)
+                j0 = pending.pop(0)
+                all_done = all_done or converged(ring[j0][0])
+        final = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+        final.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.device_reads += 1
+        out = final.numpy().view(ops.TRACK_STATE_DTYPE)
+        for i, s in enumerate(S):
+            s.rel_pose_CO = Affine(out["R"][i].reshape(3, 3), out["t"][i])
+            s.mu, s.nu, s.rho = float(out["mu"][i]), float(out["nu"][i]), float(out["rho"][i])
+            s.A = out["A"][i].reshape(6, 6).copy(); s.b = out["b"][i].copy(); s.x = out["x"][i].copy()
+            s.trackingConverged = bool(out["converged"][i]); s.evaluateGradient = bool(out["evaluate_gradient"][i])
+            s.firstIteration = bool(out["first_iteration"][i])
+            s.iterations, s.linearisations = int(out["iterations"][i]), int(out["linearisations"][i])
+        self.iterations_enqueued = issued
+        return S
+
     # TSDF::syncTrack (src/core/TSDF.cpp:333-338): cam_pose = pose * rel_pose_CO
     def syncTrackCamera(self, i: int = 0) -> Affine:
         s = self.states[i]

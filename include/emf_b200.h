@@ -328,6 +328,33 @@ EMF_API int emf_track_linearise(int n_vol, const emf_volume* vols, const emf_pos
                         const emf_image* int_weights, const emf_image* tsdf_vals, const emf_image* track_weights,
                         float* const* pose_grads, float* records, void* workspace, size_t workspace_bytes,
                         emf_stream_t stream);
+/* The whole Levenberg-Marquardt loop on the device.  Per volume a state record in DEVICE memory, initialised by the host as
+ * emf::TSDF::prepareTracking does (src/core/TSDF.cpp:170-192): R, t = the orthonormalised rel_pose_CO; converged = 0,
+ * first_iteration = 1, evaluate_gradient = 1, trial_pending = 0, nu = nu_init, counters 0.  One call enqueues n_iterations
+ * iterations of every volume: per iteration two launches of the kernel behind emf_track_linearise, whose last CTA per volume
+ * also runs the host part of the iteration -- reduceHessians' convergence test, the damped 6 x 6 solve, SE(3) exp, the
+ * step-size test (launch 1: linearise or error-only at the current pose, then the trial pose) and the gain ratio with
+ * accept / reject and the damping update (launch 2: error at the trial pose), src/core/TSDF.cpp:267-338 statement by
+ * statement.  Nothing is read back in between; converged volumes cost nothing; the caller polls `converged` (e.g. with an
+ * asynchronous copy of the states every few iterations) and reads R, t when done.  T_co_hint: the starting poses on the
+ * host (only used to size each volume's grid). */
+typedef struct emf_track_state {
+    double R[9], t[3];          /* rel_pose_CO, in/out */
+    double R_old[9], t_old[3];  /* the pose a rejected trial step returns to */
+    double mu, nu, rho;
+    float A[36], b[6], x[6];
+    float err, err_new;
+    int converged, first_iteration, evaluate_gradient, trial_pending;
+    int iterations, linearisations;
+} emf_track_state;
+typedef struct emf_track_lm_params {  /* TSDFParams, include/EMFusion/core/data.h:32-71 */
+    float tau, eps1, eps2, nu_init, huber_thresh, max_tsdf_weight;
+} emf_track_lm_params;
+EMF_API int emf_track_iterate(int n_vol, const emf_volume* vols, emf_track_state* states, const emf_pose* T_co_hint,
+                      const emf_image* points, const float K[9], const emf_image* assoc, const emf_track_lm_params* lm,
+                      const emf_image* int_weights, float* records, void* workspace, size_t workspace_bytes,
+                      int n_iterations, emf_stream_t stream);
+
 /* out <- int_weights x record[44]: intWeights as emf::TSDF::getTrackingWeights sees it (src/core/TSDF.cpp:340-343). */
 EMF_API int emf_track_normalised_weights(const emf_image* int_weights, const float* record, const emf_image* out,
                                  emf_stream_t stream);

@@ -124,6 +124,32 @@ def main():
                             "pose_error_before": float(np.linalg.norm(se3_log(scene.cam_pose(f).inv() * cam))),
                             "pose_error_after": float(np.linalg.norm(se3_log(scene.cam_pose(f).inv() * tr.syncTrackCamera(0))))}
 
+    # the same run with the host part of the loop on the device (emf_track_iterate), and all 33 volumes together
+    tr2 = Tracker([eng.background], (w, h), dev, intr=scene.K)
+    tr2.track_device(points, [eng.bg_associationWeights], cam, maxTrackingIter=100)      # warm-up (allocations)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    st2 = tr2.track_device(points, [eng.bg_associationWeights], cam, maxTrackingIter=100)[0]
+    torch.cuda.synchronize()
+    res["background_lm_device_loop"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "iterations": st2.iterations,
+                                        "linearisations": st2.linearisations, "iterations_enqueued": tr2.iterations_enqueued,
+                                        "pose_error_after": float(np.linalg.norm(se3_log(scene.cam_pose(f).inv() * tr2.syncTrackCamera(0))))}
+    tr3 = Tracker(vols, (w, h), dev, intr=scene.K)
+    tr3.track_device(points, assoc, cam, maxTrackingIter=100)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    st3 = tr3.track_device(points, assoc, cam, maxTrackingIter=100)
+    torch.cuda.synchronize()
+    res["all_volumes_lm_device_loop"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "iterations_enqueued": tr3.iterations_enqueued,
+                                         "iterations_max": max(s.iterations for s in st3), "converged": sum(int(s.trackingConverged) for s in st3)}
+    tr4 = Tracker(vols, (w, h), dev, intr=scene.K)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    st4 = tr4.track(points, assoc, cam, maxTrackingIter=100)
+    torch.cuda.synchronize()
+    res["all_volumes_lm_host_loop"] = {"wall_ms": (time.perf_counter() - t0) * 1e3, "iterations_max": max(s.iterations for s in st4),
+                                       "device_reads": tr4.device_reads}
+
     out = {"what": "one tracker iteration of every volume", "config": name, "n_volumes": n, "ours": res}
     if not args.no_reference:
         from tests import ref_gpu

@@ -216,3 +216,63 @@ def test_tracker_recovers_camera_pose(cuda_dev, oracle):
     assert d1 < 0.25 * d0, f"pose error {d0:.4f} -> {d1:.4f} after {st.iterations} iterations"
     # two device reads per iteration for the whole batch, at most
     assert tr.device_reads <= 2 * st.iterations + 1
+
+
+def _bg_volume(sc):
+    prm = TSDFParams()
+    vol = TSDF(sc.bg.res, sc.bg.voxel, sc.bg.trunc, sc.bg.pose, prm, (sc.w, sc.h), device=DEV)
+    vol.tsdfVol.copy_(cu(sc.bg.tsdf).view_as(vol.tsdfVol))
+    vol.tsdfWeights.copy_(cu(sc.bg.weights).view_as(vol.tsdfWeights))
+    return vol
+
+
+def test_device_loop_equals_host_loop(cuda_dev, oracle):
+    """emf_track_iterate (the Levenberg-Marquardt loop with its host part on the device, nothing read back in between)
+    against Tracker.track (the same control flow in Python, two reads per iteration): same number of iterations and
+    linearisations, same decisions, the same pose"""
+    sc = S.make("track", oracle, 320, 240, (96, 96, 96), 2, (32, 32, 32), n_frames=3, integrate_frames=2)
+    pts = cu(oracle.compute_points(sc.depths[2], sc.K))
+    vols = [_bg_volume(sc)]
+    ObjTSDF.nextID = 0
+    for o in sc.objs:
+        v = ObjTSDF(o.res, o.voxel, o.trunc, sc.scene.object_pose(o.vid - 1, 2), TSDFParams(), (sc.w, sc.h), device=DEV)
+        v.tsdfVol.copy_(cu(o.tsdf).view_as(v.tsdfVol)); v.tsdfWeights.copy_(cu(o.weights).view_as(v.tsdfWeights))
+        vols.append(v)
+    assoc = [torch.ones((sc.h, sc.w), device=DEV) for _ in vols]
+    start = sc.cam(2) * se3_exp(np.array([0.008, -0.006, 0.01, 0.005, -0.004, 0.003]))
+    host = Tracker(vols, (sc.w, sc.h), DEV, intr=sc.K)
+    hs = [(s.rel_pose_CO, s.iterations, s.linearisations, s.trackingConverged) for s in host.track(pts, assoc, start, 40)]
+    devt = Tracker(vols, (sc.w, sc.h), DEV, intr=sc.K)
+    ds = devt.track_device(pts, assoc, start, 40)
+    for i, (s, (pose_h, it_h, lin_h, conv_h)) in enumerate(zip(ds, hs)):
+        d = np.linalg.norm(se3_log(pose_h.inv() * s.rel_pose_CO))
+        # (the background: hundreds of thousands of pixels, a well conditioned problem.  A 32^3 object seen in a few hundred
+        #  pixels amplifies the last-bit differences between LAPACK's and the device's 6 x 6 float solve over the iterations)
+        tol, dit = (2e-5, 2) if i == 0 else (1e-3, 10)
+        assert d < tol, f"volume {i}: device and host loops end {d:.2e} apart"
+        assert abs(s.iterations - it_h) <= dit and abs(s.linearisations - lin_h) <= dit, (i, s.iterations, it_h, s.linearisations, lin_h)
+        assert np.allclose(s.rel_pose_CO.R @ s.rel_pose_CO.R.T, np.eye(3), atol=1e-9)
+    # the background's pose moved towards the truth
+    true_rel = vols[0].pose.inv() * sc.cam(2)
+    d0 = np.linalg.norm(se3_log(true_rel.inv() * (vols[0].pose.inv() * start)))
+    d1 = np.linalg.norm(se3_log(true_rel.inv() * ds[0].rel_pose_CO))
+    assert d1 < d0
+    # host reads: the device loop looks at snapshots only (at most one per chunk + the final one)
+    assert devt.device_reads <= 40 // 4 + 1 < host.device_reads
+
+
+def test_device_loop_stops_on_convergence(cuda_dev, oracle):
+    """started at the optimum of a previous run the loop converges at once: converged volumes make the remaining launches
+    no-ops and the host stops enqueuing when the snapshot says so"""
+    sc = S.make("track", oracle, 160, 120, (64, 64, 64), 0, (32, 32, 32), n_frames=3, integrate_frames=2)
+    pts = cu(oracle.compute_points(sc.depths[2], sc.K))
+    vol = _bg_volume(sc)
+    assoc = [torch.ones((sc.h, sc.w), device=DEV)]
+    tr = Tracker([vol], (sc.w, sc.h), DEV, intr=sc.K)
+    s1 = tr.track_device(pts, assoc, sc.cam(2), 100)[0]
+    cam1 = tr.syncTrackCamera(0)
+    it1 = s1.iterations
+    s2 = tr.track_device(pts, assoc, cam1, 100)[0]
+    assert s2.trackingConverged or s2.iterations <= it1
+    assert tr.iterations_enqueued <= 100
+    assert np.linalg.norm(se3_log(cam1.inv() * tr.syncTrackCamera(0))) < 1e-3
