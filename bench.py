@@ -279,11 +279,11 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": "k_integrate_seg", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "peak_source": peak_src}
         try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as fh:
                 tr = json.load(fh)["k_integrate_seg"]
             if args.config == 4 and world == 1:
                 roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                roof["traffic_source"] = "profiles/r1c_ncu_full_summary.md"
+                roof["traffic_source"] = "profiles/r1e_ncu_full_summary.md"
         except Exception:
             pass
         if world == 1:
