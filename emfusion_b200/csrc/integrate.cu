@@ -29,6 +29,9 @@
 
 namespace emfb {
 
+#ifndef EMF_INT_PYR2
+#define EMF_INT_PYR2 1
+#endif
 constexpr int kPyrLevels = 6;   // depth pyramid levels 1..6 (tiles of 2..64 pixels)
 
 struct IntVol {
@@ -538,17 +541,23 @@ __global__ void __launch_bounds__(kSegThreads, 4) k_integrate_seg(const __grid_c
                     } else if (ulo >= 0.0f && vlo >= 0.0f && uhi <= fw - 1.0f && vhi <= fh - 1.0f) {
                         const int iu0 = (int)ulo, iv0 = (int)vlo, iu1 = (int)uhi + 1, iv1 = (int)vhi + 1;   // inclusive, inside the image... iu1 <= w - 1 + 1
                         const int e = max(iu1 - iu0, iv1 - iv0);
+#if EMF_INT_PYR2
+                        const int L = max(1, 32 - __clz(max(e - 1, 0)));   // tile 2^L >= e  =>  the box spans at most 2 tiles per axis
+                        constexpr int kSpan = 2;
+#else
                         const int L = 32 - __clz(e >> 1);      // tile 2^L > e / 2  =>  the box spans at most 3 tiles per axis
+                        constexpr int kSpan = 3;
+#endif
                         if (L <= kPyrLevels) {
                             const float2* __restrict__ lv = P.pyr[L];
                             const int pw = P.pyr_w[L];
                             const int a0 = iu0 >> L, a1 = min(iu1, P.w - 1) >> L, b0 = iv0 >> L, b1 = min(iv1, P.h - 1) >> L;
                             float dmin = INFINITY, dmax = -INFINITY;
 #pragma unroll
-                            for (int db = 0; db < 3; ++db) {
+                            for (int db = 0; db < kSpan; ++db) {
                                 const float2* rowp = lv + (size_t)min(b0 + db, b1) * pw;
 #pragma unroll
-                                for (int da = 0; da < 3; ++da) {
+                                for (int da = 0; da < kSpan; ++da) {
                                     const float2 mm = __ldg(rowp + min(a0 + da, a1));
                                     dmin = fminf(dmin, mm.x); dmax = fmaxf(dmax, mm.y);
                                 }
