@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--background-on-rank0", action="store_true",
                     help="multi-GPU: keep the background on GPU 0 only (BASELINE.json's layout) instead of replicating it "
                          "and sharding its raycast by image rows")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="multi-GPU: NCCL collectives (all-reduce, gather, broadcast) instead of the NVLink peer-memory exchange")
     ap.add_argument("--materialize-grads", action="store_true",
                     help="also materialise the float3 gradient volumes every frame (reference behaviour)")
     return ap.parse_args()
@@ -195,7 +197,8 @@ def run_ours(args):
                  objVolumeDims=(ob,) * 3)
     ObjTSDF.nextID = 0
     eng = NativeEngine(prm, dev, rank=rank, world_size=world, materialize_grads=args.materialize_grads,
-                       accelerate=args.brick_maps, replicate_background=False if args.background_on_rank0 else None)
+                       accelerate=args.brick_maps, replicate_background=False if args.background_on_rank0 else None,
+                       peer_exchange=False if args.nccl_exchange else None)
     for i in range(k):
         eng.add_object(scene.object_pose(i, 0), scene.object_voxel_size(i, ob))
     frames = render_stream(scene, N_STREAM_FRAMES)
@@ -320,7 +323,8 @@ def run_ours(args):
             "config": {"workload": name, "voxels_per_frame": nvox, "l2_policy": "working set (>1 GB/frame) > L2 (126 MB)",
                        "step": "one frame = computePoints + association + raycast/composite + integrate, K frames back to back",
                        "parallelism": (f"objects sharded over {world} GPU(s); background " +
-                                       ("replicated, its raycast sharded by image rows" if eng.replicate_background else "on GPU 0")),
+                                       ("replicated, its raycast sharded by image rows" if eng.replicate_background else "on GPU 0") +
+                                       ("" if world == 1 else ("; exchanges over NVLink peer memory" if eng._px is not None else "; exchanges via NCCL"))),
                        "gradients": "materialised per frame" if args.materialize_grads else "on the fly (no float3 volume)",
                        "brick_maps": bool(args.brick_maps), "visible_objects": len(eng.vis_objs)},
             "stages_ms": {"association": float(ms_stage[0]), "raycast+composite": float(ms_stage[1]),

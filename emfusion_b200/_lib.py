@@ -104,6 +104,14 @@ _SIGS = {
     "emf_track_iterate": [C.c_int, _P(Volume), C.c_void_p, _P(Pose), _P(Image), _P(C.c_float), _P(Image), _P(TrackLMParams),
                           _P(Image), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p],
     "emf_track_normalised_weights": [_P(Image), C.c_void_p, _P(Image), C.c_void_p],
+    "emf_xchg_alloc": [C.c_size_t, _P(C.c_void_p), C.c_char_p],
+    "emf_xchg_open": [C.c_char_p, _P(C.c_void_p)],
+    "emf_xchg_close": [C.c_void_p],
+    "emf_xchg_free": [C.c_void_p],
+    "emf_xchg_signal": [C.c_int, _P(C.c_void_p), C.c_uint32, C.c_void_p],
+    "emf_xchg_wait": [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_double, C.c_void_p],
+    "emf_xchg_sum_images": [C.c_int, _P(C.c_void_p), _P(Image), C.c_void_p],
+    "emf_xchg_scatter_u32": [C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p), C.c_void_p],
     "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],
 }
 EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes", "emf_track_workspace_bytes", "emf_integrate_workspace_bytes", "emf_engine_create", "emf_engine_destroy",

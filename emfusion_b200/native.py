@@ -42,13 +42,18 @@ class _DevMem:
 
 class NativeEngine(EMFusionEngine):
     def __init__(self, params: Params, device="cuda", rank: int = 0, world_size: int = 1, group=None,
-                 materialize_grads: bool = False, accelerate: bool = False, replicate_background: Optional[bool] = None):
+                 materialize_grads: bool = False, accelerate: bool = False, replicate_background: Optional[bool] = None,
+                 peer_exchange: Optional[bool] = None):
         """replicate_background (multi-GPU; default: on when the frame height divides by the world size): every rank
         keeps and integrates its own copy of the background (replicas stay bit-identical: same inputs, deterministic
         kernels) and raycasts a band of image rows of it; rank 0 gathers the bands.  Off = the background lives on
         rank 0 only (BASELINE.json's layout), which bounds the speed-up by the background's share of the frame."""
         if replicate_background is None:
             replicate_background = world_size > 1 and params.frameSize[1] % world_size == 0
+        # multi-GPU exchanges over NVLink peer memory (csrc/xchg.cu) instead of NCCL collectives; None = use it if the
+        # peers' buffers can be opened (same node, CUDA IPC), else NCCL
+        self._peer_wanted = peer_exchange
+        self._px = None
         super().__init__(params, device, rank, world_size, group, materialize_grads, accelerate,
                          replicate_background=replicate_background)
         L = _lib.lib()
@@ -164,7 +169,11 @@ class NativeEngine(EMFusionEngine):
         import torch.distributed as dist
         # (a replica of the background is left out of the partial sum: rank 0 adds the background's weight)
         self._frame(F_ASSOC_PARTIAL_NOBG if (self.replicate_background and self.rank != 0) else F_ASSOC_PARTIAL)
-        dist.all_reduce(self.associationNorm, op=dist.ReduceOp.SUM, group=self.group)
+        px = self._peer_exchange()
+        if px is not None:
+            px.all_sum_normaliser(self)
+        else:
+            dist.all_reduce(self.associationNorm, op=dist.ReduceOp.SUM, group=self.group)
         self._frame(F_NORMALISE)
 
     def raycast(self):
@@ -212,6 +221,14 @@ class NativeEngine(EMFusionEngine):
                 g["pieces"] = [packed, u8(self.bg_raylengths[y0:y0 + rows]), u8(self.bg_vertices[y0:y0 + rows]),
                                u8(self.bg_normals[y0:y0 + rows]), u8(self.bg_mask[y0:y0 + rows])]
             self._gather_bufs = g
+        px = self._peer_exchange()
+        if px is not None:
+            px.composite(self, g, packed, offs, size, total, rows, band_off, n_all)
+            if g["local"].numel():
+                self.vis_count[:g["local"].numel()] = px.counts(self)[g["local"]]
+            self._global_counts = px.counts(self)
+            self._pending_vis = True
+            return
         if rows:
             torch.cat(g["pieces"], out=g["send"])
             send = g["send"]
@@ -246,6 +263,16 @@ class NativeEngine(EMFusionEngine):
         self._global_counts = g["counts"]
         self._pending_vis = True
 
+    def _peer_exchange(self):
+        """the NVLink peer-memory exchange of this engine (created on first use; None = NCCL collectives)"""
+        if self._px is None and self._peer_wanted is not False and self.world > 1:
+            self._px = PeerExchange.create(self)
+            if self._px is None:
+                if self._peer_wanted:
+                    raise _lib.EmfError("peer_exchange=True but the peers' buffers cannot be opened (CUDA IPC)")
+                self._peer_wanted = False
+        return self._px
+
     def _resolve_visibility(self):
         """vis_objs for host-side bookkeeping (reads the asynchronously copied counters; not on the frame's path)"""
         if not getattr(self, "_pending_vis", False):
@@ -256,7 +283,7 @@ class NativeEngine(EMFusionEngine):
             check(self._L.emf_engine_vis_counts(self._e, self._counts, n), "emf_engine_vis_counts")
             self._vis_objs = {o.id for o, c in zip(self.objects, self._counts[:n]) if c > self.params.visibilityThresh}
         else:
-            cs = self._global_counts.cpu().numpy()
+            cs = self._global_counts.cpu().numpy()[:len(self.all_ids)]
             self._vis_objs = {i for i, c in zip(self.all_ids, cs) if int(c) > self.params.visibilityThresh}
 
     @property
@@ -306,3 +333,154 @@ class NativeEngine(EMFusionEngine):
         """device ms of (association, raycast + composite, integrate) of the last timed frame"""
         check(self._L.emf_engine_stage_ms(self._e, self._stage), "emf_engine_stage_ms")
         return [float(x) for x in self._stage]
+
+
+class PeerExchange:
+    """Per-rank exchange buffer + its peers' buffers (CUDA IPC), and the three exchanges of a sharded frame on top of them:
+    the sum of the partial association normalisers, the composite merge reading every rank's pre-composite in place, and
+    the visibility counters stored into every rank's buffer (csrc/xchg.cu).  All on the frame's stream, no host sync.
+
+    Buffer layout (bytes): [flags 3 kinds x 16 ranks x u32 | pad to 256] [error word | pad to 256]
+                           [counts 2 slots x 128 x i32] [normaliser 2 slots x W*H f32] [pre-composite 2 slots x `cap`]"""
+    KIND_NORM, KIND_PRE, KIND_COUNTS = 0, 1, 2
+    TIMEOUT_S = 20.0
+
+    def __init__(self):
+        pass
+
+    @staticmethod
+    def create(eng):
+        import torch.distributed as dist
+        L = _lib.lib()
+        self = PeerExchange()
+        self.L = L
+        w, h, n = eng.w, eng.h, eng.world
+        if n > 16:
+            return None
+        self.n, self.rank = n, eng.rank
+        self.off_flags, self.off_err, self.off_counts = 0, 256, 512
+        self.off_norm = 512 + 2 * 128 * 4
+        self.norm_bytes = (w * h * 4 + 255) // 256 * 256
+        self.off_pre = self.off_norm + 2 * self.norm_bytes
+        self.cap = (w * h * 29 + (h // n + 1) * w * 29 + 4096 + 255) // 256 * 256    # pre-composite + a background band
+        total = self.off_pre + 2 * self.cap
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        ok = L.emf_xchg_alloc(total, C.byref(ptr), handle) == 0
+        handles = [None] * n
+        dist.all_gather_object(handles, handle.raw if ok else None, group=eng.group)
+        if any(hd is None for hd in handles):
+            if ok:
+                L.emf_xchg_free(ptr)
+            return None
+        self.base = [0] * n
+        self.base[self.rank] = ptr.value
+        opened = True
+        for r in range(n):
+            if r == self.rank:
+                continue
+            p = C.c_void_p()
+            if L.emf_xchg_open(handles[r], C.byref(p)) != 0:
+                opened = False
+                break
+            self.base[r] = p.value
+        flags = [None] * n
+        dist.all_gather_object(flags, opened, group=eng.group)
+        if not all(flags):
+            return None
+        self.local = torch.as_tensor(_DevMem(self.base[self.rank], (total,), "|u1"), device=eng.device)
+        self.err = self.base[self.rank] + self.off_err
+        self._sig = {}
+        self._sum = {}
+        self._merge = {}
+        self.norm_seq = self.pre_seq = 0
+        return self
+
+    def _flag_ptr(self, owner, kind, src):
+        return self.base[owner] + self.off_flags + 4 * (kind * 16 + src)
+
+    def _signal(self, eng, kind, owners, epoch):
+        key = (kind, tuple(owners))
+        arr = self._sig.get(key)
+        if arr is None:
+            arr = (C.c_void_p * len(owners))(*[self._flag_ptr(o, kind, self.rank) for o in owners])
+            self._sig[key] = arr
+        check(self.L.emf_xchg_signal(len(owners), arr, epoch & 0xffffffff, torch.cuda.current_stream(eng.device).cuda_stream), "xchg_signal")
+
+    def _wait(self, eng, kind, first, count, epoch):
+        check(self.L.emf_xchg_wait(self._flag_ptr(self.rank, kind, first), count, epoch & 0xffffffff, self.err, self.TIMEOUT_S,
+                                   torch.cuda.current_stream(eng.device).cuda_stream), "xchg_wait")
+
+    def check_errors(self):
+        """0 if no wait has timed out so far (reads one word; call off the frame path)"""
+        return int(self.local[self.off_err:self.off_err + 4].view(torch.int32).item())
+
+    def all_sum_normaliser(self, eng):
+        """associationNorm <- sum over ranks (in rank order) of the partial normalisers: the all-reduce of
+        EMFusion::computeAssociationWeights' normaliser (src/core/EMFusion.cpp:653-657) as peer loads"""
+        # every rank makes the same sequence of calls: the call number is the flag value, its parity the buffer slot (a
+        # slot is rewritten two calls later, after every peer has signalled -- i.e. finished reading -- the call in between)
+        self.norm_seq += 1
+        epoch, slot = self.norm_seq, self.norm_seq & 1
+        w, h = eng.w, eng.h
+        mine = self.local[self.off_norm + slot * self.norm_bytes: self.off_norm + slot * self.norm_bytes + w * h * 4].view(torch.float32).view(h, w)
+        mine.copy_(eng.associationNorm)
+        self._signal(eng, self.KIND_NORM, list(range(self.n)), epoch)
+        self._wait(eng, self.KIND_NORM, 0, self.n, epoch)
+        arr = self._sum.get(slot)
+        if arr is None:
+            arr = (C.c_void_p * self.n)(*[self.base[r] + self.off_norm + slot * self.norm_bytes for r in range(self.n)])
+            self._sum[slot] = arr
+        check(self.L.emf_xchg_sum_images(self.n, arr, C.byref(ops.image(eng.associationNorm)),
+                                         torch.cuda.current_stream(eng.device).cuda_stream), "xchg_sum_images")
+        ops.LAUNCHES["peerExchange"] = ops.LAUNCHES.get("peerExchange", 0) + 3
+
+    def counts(self, eng):
+        slot = self.pre_seq & 1
+        o = self.off_counts + slot * 512
+        return self.local[o:o + 512].view(torch.int32)
+
+    def composite(self, eng, g, packed, offs, size, total, rows, band_off, n_all):
+        """every rank leaves [pre-composite | background band] in its own buffer; rank 0 merges straight out of the peers'
+        buffers (emf_composite_merge with peer pointers) and stores the visibility counters into every rank's buffer"""
+        if total > self.cap:
+            raise _lib.EmfError("pre-composite larger than the exchange buffer")
+        self.pre_seq += 1
+        epoch, slot = self.pre_seq, self.pre_seq & 1
+        s = torch.cuda.current_stream(eng.device).cuda_stream
+        w, h = eng.w, eng.h
+        dst = self.local[self.off_pre + slot * self.cap: self.off_pre + slot * self.cap + total]
+        if rows:
+            torch.cat(g["pieces"], out=dst)
+        else:
+            dst.copy_(packed)
+        self._signal(eng, self.KIND_PRE, [0], epoch)
+        launches = 2
+        if self.rank == 0:
+            self._wait(eng, self.KIND_PRE, 0, self.n, epoch)
+            key = (slot, total, n_all, tuple(eng.all_ids))
+            a = self._merge.get(key)
+            if a is None:
+                base = [self.base[r] + self.off_pre + slot * self.cap for r in range(self.n)]
+                mk = lambda r, o, el: Image(base[r] + o, w * el, w, h)
+                arr = lambda o, el: (Image * self.n)(*[mk(r, o, el) for r in range(self.n)])
+                ptrs = lambda o: (C.c_void_p * self.n)(*[base[r] + size + o for r in range(self.n)])
+                cnt = self.base[0] + self.off_counts + slot * 512
+                a = (self.n, arr(offs[0], 4), arr(offs[1], 12), arr(offs[2], 12), arr(offs[3], 1), n_all,
+                     (C.c_int * max(n_all, 1))(*[int(i) for i in eng.all_ids]), ops.image(eng.bg_raylengths),
+                     ops.image(eng.bg_vertices), ops.image(eng.bg_normals), ops.image(eng.bg_mask), int(eng.params.boundary),
+                     ops.image(eng.raylengths), ops.image(eng.vertices), ops.image(eng.normals), ops.image(eng.modelSegmentation),
+                     cnt, rows, ptrs(band_off[0]) if rows else None, ptrs(band_off[1]) if rows else None,
+                     ptrs(band_off[2]) if rows else None, ptrs(band_off[3]) if rows else None)
+                others = [self.base[r] + self.off_counts + slot * 512 for r in range(1, self.n)]
+                a = (a, cnt, (C.c_void_p * max(len(others), 1))(*others), len(others))
+                self._merge = {key: a}
+            args, cnt, others, n_others = a
+            check(self.L.emf_composite_merge(*args, s), "emf_composite_merge")
+            if n_others and n_all:
+                check(self.L.emf_xchg_scatter_u32(cnt, n_all, n_others, others, s), "xchg_scatter")
+            self._signal(eng, self.KIND_COUNTS, list(range(1, self.n)), epoch)
+            launches += 4
+        else:
+            self._wait(eng, self.KIND_COUNTS, 0, 1, epoch)
+            launches += 1
+        ops.LAUNCHES["peerExchange"] = ops.LAUNCHES.get("peerExchange", 0) + launches

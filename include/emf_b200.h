@@ -430,6 +430,26 @@ EMF_API int emf_engine_set_background_rows(emf_engine* e, int y0, int y1);
  * after the last composite: emf::EMFusion::createObj adds it to vis_objs, src/core/EMFusion.cpp:918). */
 EMF_API int emf_engine_force_integrate(emf_engine* e, int vol_index);
 
+/* ---------------------------------------------------------------------------
+ * Multi-GPU exchange over NVLink peer memory (csrc/xchg.cu): one process per GPU, every rank owns an exchange buffer
+ * that its peers open through CUDA IPC.  Replaces the all-reduce of the association normaliser, the gather of the
+ * pre-composites and the broadcast of the visibility counters by flags + direct peer loads / stores
+ * on the frame's stream.  Flags carry the frame number (they only grow), so nothing is ever reset.
+ * ------------------------------------------------------------------------- */
+EMF_API int emf_xchg_alloc(size_t bytes, void** ptr_out, unsigned char handle_out[64]);   /* cudaMalloc + zero + IPC handle */
+EMF_API int emf_xchg_open(const unsigned char handle[64], void** ptr_out);               /* a peer's buffer as a device pointer */
+EMF_API int emf_xchg_close(void* peer_ptr);
+EMF_API int emf_xchg_free(void* ptr);
+/* *flags[i] = value for i < n (n <= 16; local or peer pointers), after everything queued before it on the stream. */
+EMF_API int emf_xchg_signal(int n, uint32_t* const* flags, uint32_t value, emf_stream_t stream);
+/* The stream waits until flags[i] >= value (wrap-safe) for every i < n (n <= 32; LOCAL memory).  After timeout_s seconds
+ * it gives up and stores 1 + i in *err (device memory, caller-zeroed) instead of hanging. */
+EMF_API int emf_xchg_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, double timeout_s, emf_stream_t stream);
+/* out = parts[0] + parts[1] + ... in this order (W x H f32, continuous parts, 16-byte aligned; local or peer pointers). */
+EMF_API int emf_xchg_sum_images(int n_parts, const float* const* parts, const emf_image* out, emf_stream_t stream);
+/* dst[r][i] = src[i] for i < count, r < n_dst (the visibility counters into every rank's buffer). */
+EMF_API int emf_xchg_scatter_u32(const uint32_t* src, int count, int n_dst, uint32_t* const* dst, emf_stream_t stream);
+
 /* Library identification: returns a static string "emf_b200 <version> sm_100a". */
 EMF_API const char* emf_version(void);
 

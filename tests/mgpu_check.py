@@ -14,12 +14,12 @@ from emfusion_b200.synth import Scene                  # noqa: E402
 from emfusion_b200.volume import ObjTSDF, Params       # noqa: E402
 
 
-def run(out_path, world, rank, dev, n_frames=5, w=320, h=240, bg=96, n_obj=5, obj=32, group=None, replicate=None):
+def run(out_path, world, rank, dev, n_frames=5, w=320, h=240, bg=96, n_obj=5, obj=32, group=None, replicate=None, peer=None):
     scene = Scene(n_objects=n_obj, width=w, height=h, seed=11, dropout=0.01)
     prm = Params(frameSize=(w, h), intr=scene.K, globalVolumeDims=(bg,) * 3, globalVoxelSize=5.12 / bg,
                  objVolumeDims=(obj,) * 3, visibilityThresh=(40 * 40 * w * h) // (640 * 480), boundary=max(2, 20 * w // 640))
     ObjTSDF.nextID = 0
-    eng = NativeEngine(prm, dev, rank=rank, world_size=world, group=group, replicate_background=replicate)
+    eng = NativeEngine(prm, dev, rank=rank, world_size=world, group=group, replicate_background=replicate, peer_exchange=peer)
     for k in range(n_obj):
         eng.add_object(scene.object_pose(k, 0), scene.object_voxel_size(k, obj))
     res = {}
@@ -44,6 +44,14 @@ def run(out_path, world, rank, dev, n_frames=5, w=320, h=240, bg=96, n_obj=5, ob
     for o in eng.objects:
         res[f"obj{o.id}_tsdf"] = o.tsdfVol.cpu().numpy()
         res[f"obj{o.id}_assoc"] = eng.associationWeights[o.id].cpu().numpy()
+    if world > 1:
+        px = eng._px
+        res["peer_exchange"] = np.array([1 if px is not None else 0])
+        if px is not None:
+            torch.cuda.synchronize()
+            assert px.check_errors() == 0, f"rank {rank}: a peer wait timed out ({px.check_errors()})"
+        if peer:
+            assert px is not None, "peer exchange was requested but is not active"
     np.savez(out_path + f".rank{rank}.npz", **res)
 
 
@@ -52,6 +60,7 @@ if __name__ == "__main__":
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    run(sys.argv[1], world, rank, dev, replicate={"auto": None, "0": False, "1": True}[sys.argv[2] if len(sys.argv) > 2 else "auto"])
+    run(sys.argv[1], world, rank, dev, replicate={"auto": None, "0": False, "1": True}[sys.argv[2] if len(sys.argv) > 2 else "auto"],
+        peer={"auto": None, "nccl": False, "peer": True}[sys.argv[3] if len(sys.argv) > 3 else "auto"])
     dist.barrier()
     dist.destroy_process_group()

@@ -15,18 +15,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["nccl", "peer"], ids=["nccl_collectives", "nvlink_peer_memory"])
 @pytest.mark.parametrize("replicate", ["0", "1"], ids=["background_on_rank0", "background_replicated"])
-def test_two_rank_engine_equals_single_gpu(tmp_path, replicate):
+def test_two_rank_engine_equals_single_gpu(tmp_path, replicate, exchange):
     from tests import mgpu_check
     out2 = str(tmp_path / "w2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "2953" + replicate, os.path.join(ROOT, "tests", "mgpu_check.py"), out2, replicate]
+           "--master-port", "2953" + replicate, os.path.join(ROOT, "tests", "mgpu_check.py"), out2, replicate, exchange]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     out1 = str(tmp_path / "w1")
     mgpu_check.run(out1, 1, 0, torch.device("cuda", 0))
     a = np.load(out1 + ".rank0.npz")
     b0, b1 = np.load(out2 + ".rank0.npz"), np.load(out2 + ".rank1.npz")
+    assert int(b0["peer_exchange"][0]) == (1 if exchange == "peer" else 0)
     for f in range(1, 5):
         assert np.array_equal(a[f"seg{f}"], b0[f"seg{f}"]), f"frame {f}: segmentation"
         assert np.array_equal(a[f"ray{f}"], b0[f"ray{f}"]), f"frame {f}: ray lengths"
