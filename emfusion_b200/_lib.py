@@ -104,6 +104,11 @@ _SIGS = {
     "emf_track_iterate": [C.c_int, _P(Volume), C.c_void_p, _P(Pose), _P(Image), _P(C.c_float), _P(Image), _P(TrackLMParams),
                           _P(Image), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p],
     "emf_track_normalised_weights": [_P(Image), C.c_void_p, _P(Image), C.c_void_p],
+    "emf_assoc_normalise_parts": [C.c_int, _P(Image), C.c_int, _P(C.c_void_p), _P(Image), C.c_void_p, C.c_uint32, C.c_void_p,
+                                  C.c_double, C.c_void_p],
+    "emf_engine_set_partial_norm_target": [C.c_void_p, _P(Image)],
+    "emf_engine_normalise_from_parts": [C.c_void_p, C.c_int, _P(C.c_void_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_double,
+                                        C.c_void_p],
     "emf_xchg_alloc": [C.c_size_t, _P(C.c_void_p), C.c_char_p],
     "emf_xchg_open": [C.c_char_p, _P(C.c_void_p)],
     "emf_xchg_close": [C.c_void_p],

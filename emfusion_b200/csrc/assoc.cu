@@ -115,6 +115,46 @@ __global__ void __launch_bounds__(256) k_assoc_normalise(const __grid_constant__
     }
 }
 
+// Multi-GPU: the normaliser is the sum of every rank's partial sum.  The consumer kernel itself waits for the producers'
+// flags (local memory; every CTA polls them, bounded by a time-out), then reads the partial images -- this rank's own and the
+// peers', over NVLink -- adds them in rank order (the same bits on every rank), keeps the total and divides its images:
+// the all-reduce and the normalisation (reference src/core/EMFusion.cpp:653-665) in one kernel.
+struct NormPartsParams {
+    float* img[EMF_MAX_VOLUMES]; size_t pitch[EMF_MAX_VOLUMES];
+    int n_img, w, h;
+    const float* part[16]; int n_parts;
+    float* norm; size_t norm_pitch;
+    const uint32_t* flags; uint32_t value; uint32_t* err; unsigned long long timeout_ns;
+};
+__global__ void __launch_bounds__(256) k_assoc_normalise_parts(const __grid_constant__ NormPartsParams P) {
+    if (threadIdx.x < P.n_parts) {
+        const volatile uint32_t* f = P.flags + threadIdx.x;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int32_t)(*f - P.value) < 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > P.timeout_ns) { atomicExch(P.err, 1u + threadIdx.x); break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.w || y >= P.h) return;
+    const size_t i = (size_t)y * P.w + x;
+    // (plain loads: the parts were written by other GPUs / earlier kernels, never through the read-only path)
+    float n = *(const volatile float*)(P.part[0] + i);
+    for (int r = 1; r < P.n_parts; ++r) n = fadd(n, *(const volatile float*)(P.part[r] + i));
+    *((float*)((char*)P.norm + (size_t)y * P.norm_pitch) + x) = n;
+    for (int k = 0; k < P.n_img; ++k) {
+        float* o = (float*)((char*)P.img[k] + (size_t)y * P.pitch[k]) + x;
+        const float v = *o;
+        if (v != 0.0f) *o = (n != 0.0f) ? fdiv(v, n) : 0.0f;
+    }
+}
+
 // getVolumeVals<float>
 __global__ void __launch_bounds__(256) k_gather(const float* __restrict__ vol, Img<const float> points, Img<float> vals,
                                                 const __grid_constant__ Pose T, int rx, int ry, int rz, float voxel) {
@@ -234,6 +274,27 @@ extern "C" EMF_API int emf_assoc_normalise(int n_img, const emf_image* assoc_io,
     P.norm = (const float*)norm->ptr; P.norm_pitch = norm->pitch;
     const dim3 grid((P.w + 31) / 32, (P.h + 7) / 8);
     k_assoc_normalise<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_assoc_normalise_parts(int n_img, const emf_image* assoc_io, int n_parts, const float* const* parts,
+                                                 const emf_image* norm_out, const uint32_t* flags, uint32_t value, uint32_t* err,
+                                                 double timeout_s, emf_stream_t stream) {
+    if (n_img < 0 || (n_img > 0 && !assoc_io) || n_parts <= 0 || n_parts > 16 || !parts || !image_ok(norm_out, 4) || !flags || !err ||
+        !(timeout_s > 0.0))
+        return EMF_ERR_INVALID;
+    if (n_img > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
+    NormPartsParams P;
+    for (int i = 0; i < n_img; ++i) {
+        if (!image_ok(&assoc_io[i], 4) || !same_size(&assoc_io[i], norm_out)) return EMF_ERR_INVALID;
+        P.img[i] = (float*)assoc_io[i].ptr; P.pitch[i] = assoc_io[i].pitch;
+    }
+    for (int r = 0; r < n_parts; ++r) { if (!parts[r]) return EMF_ERR_INVALID; P.part[r] = parts[r]; }
+    P.n_img = n_img; P.n_parts = n_parts; P.w = norm_out->width; P.h = norm_out->height;
+    P.norm = (float*)norm_out->ptr; P.norm_pitch = norm_out->pitch;
+    P.flags = flags; P.value = value; P.err = err; P.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    const dim3 grid((P.w + 31) / 32, (P.h + 7) / 8);
+    k_assoc_normalise_parts<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
 }
 

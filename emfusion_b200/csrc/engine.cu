@@ -29,6 +29,7 @@ struct emf_engine {
     char* pool = nullptr;
     size_t pool_bytes = 0;
     emf_image points{}, norm{}, ray{}, vert{}, nrm{}, seg{}, zero_f{}, zero_f3{}, zero_u8{};
+    emf_image partial_target{};   // ptr == nullptr: partial normalisers go to `norm`
     std::vector<emf_image> a_img, v_ray, v_vert, v_norm, v_mask;
     int32_t* vis_count = nullptr;
     void* int_ws = nullptr;            // integrate workspace (depth pyramid)
@@ -185,12 +186,14 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
             cudaEventRecord(e->fork, s);
             cudaStreamWaitEvent(e->aux, e->fork, 0);
         }
-        rc = emf_assoc_weights(n, e->vols.data(), T_co, &e->points, &e->cfg.params, e->a_img.data(), mode, &e->norm,
+        rc = emf_assoc_weights(n, e->vols.data(), T_co, &e->points, &e->cfg.params, e->a_img.data(), mode,
+                               (mode != 0 && e->partial_target.ptr) ? &e->partial_target : &e->norm,
                                overlap ? (emf_stream_t)e->aux : stream);
         if (rc != EMF_OK) return rc;
         if (overlap) cudaEventRecord(e->join, e->aux);
     } else if ((flags & (EMF_FRAME_ASSOC_PARTIAL | EMF_FRAME_ASSOC_PARTIAL_NOBG)) && n == 0) {
-        cudaMemsetAsync(e->norm.ptr, 0, e->norm.pitch * h, s);
+        const emf_image& tgt = e->partial_target.ptr ? e->partial_target : e->norm;
+        cudaMemsetAsync(tgt.ptr, 0, tgt.pitch * h, s);
     }
     if ((flags & EMF_FRAME_NORMALISE) && n > 0) {
         rc = emf_assoc_normalise(n, e->a_img.data(), &e->norm, stream);
@@ -250,6 +253,20 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
     }
     if (timed) { cudaEventRecord(e->ev[3], s); e->timed_valid = true; }
     return emfb::launch_status();
+}
+
+extern "C" EMF_API int emf_engine_set_partial_norm_target(emf_engine* e, const emf_image* target) {
+    if (!e) return EMF_ERR_INVALID;
+    if (!target) { e->partial_target = emf_image{}; return EMF_OK; }
+    if (!emfb::image_ok(target, 4) || target->width != e->cfg.width || target->height != e->cfg.height) return EMF_ERR_INVALID;
+    e->partial_target = *target;
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_normalise_from_parts(emf_engine* e, int n_parts, const float* const* parts, const uint32_t* flags,
+                                                       uint32_t value, uint32_t* err, double timeout_s, emf_stream_t stream) {
+    if (!e || !e->pool) return EMF_ERR_INVALID;
+    return emf_assoc_normalise_parts(e->n_vol, e->a_img.data(), n_parts, parts, &e->norm, flags, value, err, timeout_s, stream);
 }
 
 extern "C" EMF_API int emf_engine_stage_ms(emf_engine* e, float ms[3]) {

@@ -168,12 +168,18 @@ class NativeEngine(EMFusionEngine):
             return
         import torch.distributed as dist
         # (a replica of the background is left out of the partial sum: rank 0 adds the background's weight)
-        self._frame(F_ASSOC_PARTIAL_NOBG if (self.replicate_background and self.rank != 0) else F_ASSOC_PARTIAL)
         px = self._peer_exchange()
         if px is not None:
-            px.all_sum_normaliser(self)
-        else:
-            dist.all_reduce(self.associationNorm, op=dist.ReduceOp.SUM, group=self.group)
+            # the partial normaliser is written straight into this rank's exchange slot; the normalising kernel waits
+            # for every rank's flag and sums the partial images out of the peers' memory itself (no all-reduce)
+            if self._dirty:
+                self._sync_volumes()
+            px.begin_normaliser(self)
+            self._frame(F_ASSOC_PARTIAL_NOBG if (self.replicate_background and self.rank != 0) else F_ASSOC_PARTIAL)
+            px.finish_normaliser(self)
+            return
+        self._frame(F_ASSOC_PARTIAL_NOBG if (self.replicate_background and self.rank != 0) else F_ASSOC_PARTIAL)
+        dist.all_reduce(self.associationNorm, op=dist.ReduceOp.SUM, group=self.group)
         self._frame(F_NORMALISE)
 
     def raycast(self):
@@ -414,25 +420,28 @@ class PeerExchange:
         """0 if no wait has timed out so far (reads one word; call off the frame path)"""
         return int(self.local[self.off_err:self.off_err + 4].view(torch.int32).item())
 
-    def all_sum_normaliser(self, eng):
-        """associationNorm <- sum over ranks (in rank order) of the partial normalisers: the all-reduce of
-        EMFusion::computeAssociationWeights' normaliser (src/core/EMFusion.cpp:653-657) as peer loads"""
-        # every rank makes the same sequence of calls: the call number is the flag value, its parity the buffer slot (a
-        # slot is rewritten two calls later, after every peer has signalled -- i.e. finished reading -- the call in between)
+    def begin_normaliser(self, eng):
+        """before EMF_FRAME_ASSOC_PARTIAL: its partial normaliser goes into this call's slot of the exchange buffer.
+        Every rank makes the same sequence of calls: the call number is the flag value, its parity the slot (a slot is
+        rewritten two calls later, after every peer has signalled -- i.e. finished reading -- the call in between)."""
         self.norm_seq += 1
+        slot = self.norm_seq & 1
+        img = Image(self.base[self.rank] + self.off_norm + slot * self.norm_bytes, eng.w * 4, eng.w, eng.h)
+        check(self.L.emf_engine_set_partial_norm_target(eng._e, C.byref(img)), "set_partial_norm_target")
+
+    def finish_normaliser(self, eng):
+        """associationNorm <- sum over ranks (in rank order) of the partial normalisers, every association image divided by
+        it: the all-reduce of EMFusion::computeAssociationWeights (src/core/EMFusion.cpp:653-665) inside its consumer"""
         epoch, slot = self.norm_seq, self.norm_seq & 1
-        w, h = eng.w, eng.h
-        mine = self.local[self.off_norm + slot * self.norm_bytes: self.off_norm + slot * self.norm_bytes + w * h * 4].view(torch.float32).view(h, w)
-        mine.copy_(eng.associationNorm)
         self._signal(eng, self.KIND_NORM, list(range(self.n)), epoch)
-        self._wait(eng, self.KIND_NORM, 0, self.n, epoch)
         arr = self._sum.get(slot)
         if arr is None:
             arr = (C.c_void_p * self.n)(*[self.base[r] + self.off_norm + slot * self.norm_bytes for r in range(self.n)])
             self._sum[slot] = arr
-        check(self.L.emf_xchg_sum_images(self.n, arr, C.byref(ops.image(eng.associationNorm)),
-                                         torch.cuda.current_stream(eng.device).cuda_stream), "xchg_sum_images")
-        ops.LAUNCHES["peerExchange"] = ops.LAUNCHES.get("peerExchange", 0) + 3
+        check(self.L.emf_engine_normalise_from_parts(eng._e, self.n, arr, self._flag_ptr(self.rank, self.KIND_NORM, 0),
+                                                     epoch & 0xffffffff, self.err, self.TIMEOUT_S,
+                                                     torch.cuda.current_stream(eng.device).cuda_stream), "normalise_from_parts")
+        ops.LAUNCHES["peerExchange"] = ops.LAUNCHES.get("peerExchange", 0) + 2
 
     def counts(self, eng):
         slot = self.pre_seq & 1

@@ -450,6 +450,20 @@ EMF_API int emf_xchg_sum_images(int n_parts, const float* const* parts, const em
 /* dst[r][i] = src[i] for i < count, r < n_dst (the visibility counters into every rank's buffer). */
 EMF_API int emf_xchg_scatter_u32(const uint32_t* src, int count, int n_dst, uint32_t* const* dst, emf_stream_t stream);
 
+/* The all-reduce of the association normaliser fused into its consumer: the kernel waits for flags[i] >= value, i < n_parts
+ * (local memory, polled inside the kernel by every CTA; time-out as emf_xchg_wait), sums parts[0..n_parts) (W x H f32,
+ * continuous; local or peer pointers) in this order into norm_out and divides the n_img images by it with x/0 -> 0
+ * (src/core/EMFusion.cpp:653-665). */
+EMF_API int emf_assoc_normalise_parts(int n_img, const emf_image* assoc_io, int n_parts, const float* const* parts,
+                              const emf_image* norm_out, const uint32_t* flags, uint32_t value, uint32_t* err,
+                              double timeout_s, emf_stream_t stream);
+/* Engine side of it: EMF_FRAME_ASSOC_PARTIAL* writes the partial normaliser to `target` (a slot of this rank's exchange
+ * buffer; NULL = the engine's own image again); emf_engine_normalise_from_parts = emf_assoc_normalise_parts over the
+ * engine's association images and EMF_IMG_NORM. */
+EMF_API int emf_engine_set_partial_norm_target(emf_engine* e, const emf_image* target);
+EMF_API int emf_engine_normalise_from_parts(emf_engine* e, int n_parts, const float* const* parts, const uint32_t* flags,
+                                    uint32_t value, uint32_t* err, double timeout_s, emf_stream_t stream);
+
 /* Library identification: returns a static string "emf_b200 <version> sm_100a". */
 EMF_API const char* emf_version(void);
 
