@@ -190,6 +190,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     name, bg, k, ob, w, h = CONFIGS[args.config]
     scene = Scene(n_objects=k, width=w, height=h, seed=0)

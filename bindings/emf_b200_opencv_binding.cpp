@@ -2,8 +2,8 @@
 //
 // This file is NOT part of the product library.  It is what a maintainer of EM-Fusion adds to the
 // reference build: it DEFINES the reference's own level-1 operators
-//   emf::cuda::TSDF::{updateTSDF, computeTSDFGrads, raycastTSDF, getVolumeVals}
-//       declared in  include/EMFusion/core/cuda/TSDF.cuh:115-210      (defined in src/core/cuda/TSDF.cu)
+//   emf::cuda::TSDF::{updateTSDF, computeTSDFGrads, raycastTSDF, getVolumeVals, copyValues}
+//       declared in  include/EMFusion/core/cuda/TSDF.cuh:115-230      (defined in src/core/cuda/TSDF.cu)
 //   emf::cuda::ObjTSDF::updateFgBgProbs
 //       declared in  include/EMFusion/core/cuda/ObjTSDF.cuh:49-56     (defined in src/core/cuda/ObjTSDF.cu)
 //   emf::cuda::EMFusion::computePoints
@@ -92,6 +92,15 @@ void getVolumeVals(const cv::cuda::GpuMat& vol, const cv::cuda::GpuMat& points, 
     const emf_image p = img(points), o = img(vals);
     const emf_pose T = pose(rel_rot_CO, rel_trans_CO);
     ok(emf_get_volume_vals((const float*)vol.data, &p, &T, volumeRes.val, voxelSize, &o, str(stream)));
+}
+
+// ObjTSDF::resize (src/core/ObjTSDF.cpp:139-146) calls this once per array after zero-filling the target; a maintainer who
+// edits resize() itself replaces the four fills and four calls by one emf_resize_volume.
+void copyValues(const cv::cuda::GpuMat& src, cv::cuda::GpuMat& dst, const cv::Vec3i& offset, const cv::Vec3i& srcRes,
+                const cv::Vec3i& dstRes) {
+    CV_Assert(src.depth() == CV_32F && src.type() == dst.type() && src.channels() <= 3);
+    ok(emf_copy_values((const float*)src.data, (float*)dst.data, src.channels(), offset.val, srcRes.val, dstRes.val,
+                       /*stream=*/nullptr));   // the reference launches it on the default stream
 }
 
 }  // namespace TSDF

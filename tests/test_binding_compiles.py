@@ -22,8 +22,8 @@ def test_opencv_binding_compiles_against_reference_headers(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     syms = subprocess.run(["nm", "-C", str(obj)], capture_output=True, text=True).stdout
     for name in ("emf::cuda::TSDF::updateTSDF(", "emf::cuda::TSDF::computeTSDFGrads(", "emf::cuda::TSDF::raycastTSDF(",
-                 "emf::cuda::TSDF::getVolumeVals(", "emf::cuda::ObjTSDF::updateFgBgProbs("):
+                 "emf::cuda::TSDF::getVolumeVals(", "emf::cuda::TSDF::copyValues(", "emf::cuda::ObjTSDF::updateFgBgProbs("):
         assert any(name in ln and " T " in ln for ln in syms.splitlines()), f"{name} not defined by the binding"
     for c_abi in ("emf_update_tsdf", "emf_compute_tsdf_grads", "emf_raycast_tsdf", "emf_get_volume_vals",
-                  "emf_update_fgbg_probs"):
+                  "emf_update_fgbg_probs", "emf_copy_values"):
         assert any(ln.strip().endswith("U " + c_abi) for ln in syms.splitlines()), f"{c_abi} not referenced"
