@@ -11,3 +11,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_integrate|k_raycast|k_assoc|k_composite' -s 8 -c 4 -f -o gpurun_out/prof_r1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 fi
 ls -la gpurun_out | head -30
+# the other single-GPU configurations of BASELINE.json (parity-test cases; one line each for the record) and smoke()
+if [ "$1" = "prof" ]; then
+for c in 2 3; do timeout 300 python bench.py --config $c --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg$c.json 2> gpurun_out/bench_cfg$c.err; cut -c1-200 gpurun_out/bench_cfg$c.json; done
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+fi
