@@ -190,7 +190,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     name, bg, k, ob, w, h = CONFIGS[args.config]
     scene = Scene(n_objects=k, width=w, height=h, seed=0)
@@ -341,7 +340,7 @@ def run_ours(args):
                 out["cpu_baseline"] = cpu_baseline(args.config)
             except Exception as e:  # the checker is optional for the measurement itself
                 out["cpu_baseline"] = {"error": str(e)}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -355,7 +354,7 @@ def run_reference(args):
         return
     from tests import ref_gpu
     if not ref_gpu.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libemf_ref.so not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libemf_ref.so not built (needs /root/reference at build time)"})
         return
     import torch
     from emfusion_b200.poses import Affine, rel_pose_CO, rel_pose_OC
@@ -471,12 +470,34 @@ def run_reference(args):
            "cpu_baseline": {"value": nvox / (ms_hot * 1e-3) / 1e6, "unit": "Mvoxels/s", "cores": 0, "kind": "reference",
                             "sample": "full workload on one B200 -- the reference path is CUDA-only; no host cores are used"},
            "clocks": clocks}
-    print(json.dumps(out))
+    emit(out)
     ref.close()
+
+
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: everything else a library writes there (NCCL's version banner, ...) is sent to
+    stderr until emit() restores the descriptor"""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(obj), flush=True)
+    if _STDOUT_FD is not None:
+        os.dup2(2, 1)
 
 
 if __name__ == "__main__":
     a = parse()
+    quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
