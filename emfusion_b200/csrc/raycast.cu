@@ -47,6 +47,7 @@ struct RayVol {
     int x0, y0, x1, y1;      // screen rect (exclusive upper)
     int tiles_x;             // tiles per rect row
     int first_block;
+    int tube;                // 1: tube skipping (large volume, Rx % 4 == 0, 16-byte aligned)
 };
 
 struct RayParams {
@@ -250,12 +251,13 @@ __device__ __forceinline__ bool samp_resolve(Ray& r, const RayConst& c, const Co
     r.f = fn;
     return false;
 }
+// at most max_iters pair iterations (<= 2 max_iters samples); true = the ray is finished
 template <bool STATS>
-__device__ __forceinline__ void march_pairs(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
-                                            unsigned long long* st) {
-    for (;;) {
+__device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
+                                            unsigned long long* st, int max_iters = 0x7fffffff) {
+    for (int it = 0; it < max_iters; ++it) {
         const float t1 = fadd(r.tcur, r.step);
-        if (!(t1 <= c.tmax)) return;
+        if (!(t1 <= c.tmax)) return true;
         const float t2 = fadd(t1, r.step);
         const float step0 = r.step;
         Samp a, b;
@@ -264,10 +266,92 @@ __device__ __forceinline__ void march_pairs(Ray& r, const RayConst& c, const Con
         b.in = false;
         if (have2) samp_fetch(b, t2, c, div_s, V, rx, plane);
         r.tcur = t1;
-        if (a.in && samp_resolve<STATS>(r, c, div_s, V, a, samp_value(a), st)) return;
+        if (a.in && samp_resolve<STATS>(r, c, div_s, V, a, samp_value(a), st)) return true;
         if (!have2 || r.step != step0) continue;     // the speculation failed (or there is no second sample)
         r.tcur = t2;
-        if (b.in && samp_resolve<STATS>(r, c, div_s, V, b, samp_value(b), st)) return;
+        if (b.in && samp_resolve<STATS>(r, c, div_s, V, b, samp_value(b), st)) return true;
+    }
+    return false;
+}
+
+// ---- tube skipping (large volumes; compiled in, OFF by default: EMF_RAY_TUBE -- see DESIGN.md section 4.3 for why).
+// The rays of a warp -- an 8 x 4 pixel patch -- run inside a tube a few voxels wide.  A
+// march sample whose eight corners all hold exactly +1 (observed free space) returns exactly +1 again and changes nothing
+// of the march state but the ray parameter; the same goes for exactly 0 (never observed) once the step is half a voxel.
+// When every ray of the warp carries that constant, the warp reads the voxels of the box its next n samples can touch --
+// one row of the box per lane, 128-bit loads: ~3 % of the loads and instructions those samples would cost -- and if all of
+// them hold the constant, every ray advances its parameter by the same n fp32 additions in closed form (seq_add.h) and
+// nothing else happens.  Otherwise the warp marches a round of samples and tries again later.  No auxiliary structure is
+// kept: the certificate is the volume itself, read coalesced.
+constexpr int kTubeSamples = 32;     // samples per skip (per ray)
+constexpr int kTubeRound = 8;        // pair iterations of a marching round
+template <bool STATS>
+__device__ __forceinline__ void march_tube(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
+                                           bool done, unsigned long long* st) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float inv_s = 1.0f / c.s;
+    int backoff = 0;
+    while (!__all_sync(kFull, done)) {
+        if (backoff == 0) {
+            const bool one = done || r.f == 1.0f;
+            const bool zero = done || (__float_as_uint(r.f) == 0u && r.step == c.half_s);
+            const bool all1 = __all_sync(kFull, one);
+            const bool all0 = !all1 && __all_sync(kFull, zero);
+            bool skipped = false;
+            if (all1 || all0) {
+                int n = kTubeSamples;
+                if (!done) {
+                    // samples left before the ray passes tmax, conservatively (the additions round)
+                    const float room = (c.tmax - r.tcur) / r.step * 0.999f - 1.0f;
+                    n = room >= (float)kTubeSamples ? kTubeSamples : (room > 0.0f ? (int)room : 0);
+                }
+                n = __reduce_min_sync(kFull, n);
+                if (n >= 8) {
+                    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
+                    if (!done) {
+                        const float ta = r.tcur + r.step, tb = r.tcur + r.step * (float)n;
+                        const float pa[3] = {c.hxh + (c.ox + c.dx * ta) * inv_s, c.hyh + (c.oy + c.dy * ta) * inv_s, c.hzh + (c.oz + c.dz * ta) * inv_s};
+                        const float pb[3] = {c.hxh + (c.ox + c.dx * tb) * inv_s, c.hyh + (c.oy + c.dy * tb) * inv_s, c.hzh + (c.oz + c.dz * tb) * inv_s};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {   // base voxels floor(v) .. floor(v) + 1, one voxel of slack for the approximations
+                            lo[k] = (int)floorf(fminf(pa[k], pb[k])) - 1;
+                            hi[k] = (int)floorf(fmaxf(pa[k], pb[k])) + 2;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { lo[k] = __reduce_min_sync(kFull, lo[k]); hi[k] = __reduce_max_sync(kFull, hi[k]); }
+                    // (samples outside the volume's inner bounds are skipped by the march itself: only voxels that exist matter)
+                    const int x0 = max(lo[0], 0) & ~3, x1 = min(hi[0], V.rx - 1);
+                    const int y0 = max(lo[1], 0), y1 = min(hi[1], V.ry - 1), z0 = max(lo[2], 0), z1 = min(hi[2], V.rz - 1);
+                    const int nq = x1 >= x0 ? (x1 - x0) / 4 + 1 : 0, ny = y1 - y0 + 1, rows = ny * (z1 - z0 + 1);
+                    if (nq >= 1 && nq <= 4 && ny >= 1 && rows >= 1 && rows <= 8 * 32) {
+                        const uint32_t want = all1 ? 0x3f800000u : 0u;
+                        bool ok = true;
+                        for (int rr = lane; rr < rows; rr += 32) {
+                            const int zz = z0 + rr / ny, yy = y0 + rr - (rr / ny) * ny;
+                            const uint4* p = reinterpret_cast<const uint4*>(V.tsdf + ((size_t)zz * V.ry + yy) * V.rx + x0);
+                            for (int q = 0; q < nq; ++q) {
+                                const uint4 v = __ldg(p + q);
+                                ok = ok && v.x == want && v.y == want && v.z == want && v.w == want;
+                            }
+                        }
+                        if (__all_sync(kFull, ok)) {
+                            if (!done) {
+                                r.tcur = emf_seq_add(r.tcur, r.step, n);
+                                if (STATS) { st[1] += n; ++st[2]; }
+                            }
+                            skipped = true;
+                        }
+                    }
+                }
+            }
+            if (skipped) continue;
+            backoff = (all1 || all0) ? 2 : 1;
+        } else {
+            --backoff;
+        }
+        if (!done) done = march_pairs<STATS>(r, c, div_s, V, rx, plane, st, kTubeRound);
     }
 }
 
@@ -276,6 +360,9 @@ __device__ __forceinline__ void march_pairs(Ray& r, const RayConst& c, const Con
 //               collectives (needs emf_volume::brick_map on at least one volume of the launch).
 #ifndef EMF_RAY_PAIR
 #define EMF_RAY_PAIR 1
+#endif
+#ifndef EMF_RAY_TUBE
+#define EMF_RAY_TUBE 0
 #endif
 #ifndef EMF_RAY_MINB
 #define EMF_RAY_MINB 8
@@ -297,7 +384,7 @@ __global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __g
     const int xr = V.x0 + tx * kTileW + (warp & 1) * kWarpW + (lane % kWarpW);
     const int yr = V.y0 + ty * kTileH + (warp >> 1) * kWarpH + (lane / kWarpW);
     const bool valid = xr < V.x1 && yr < V.y1;
-    if (!JUMP && !valid) return;
+    if (!JUMP && !valid && !V.tube) return;   // (tube skipping uses warp collectives: idle lanes stay)
     const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);   // (JUMP: lanes outside the rectangle idle in the loop)
 
     float* ray_px = (float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x;
@@ -376,7 +463,10 @@ __global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __g
         }
     }
     if (!JUMP) {
-        if (!done) {
+        if (V.tube) {
+            march_tube<STATS>(r, c, div_s, V, rx, plane, done, st);
+            if (!valid) return;
+        } else if (!done) {
 #if EMF_RAY_PAIR
             march_pairs<STATS>(r, c, div_s, V, rx, plane, st);
 #else
@@ -528,6 +618,12 @@ static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const
     }
     d.x0 = x0; d.y0 = y0; d.x1 = x1; d.y1 = y1;
     d.tiles_x = (x1 - x0 + kTileW - 1) / kTileW;
+#if EMF_RAY_TUBE
+    // long rays through a large grid: the background.  (Object rays are clipped to a few dozen samples: nothing to skip.)
+    d.tube = ((int64_t)v.res[0] * v.res[1] * v.res[2] >= ((int64_t)1 << 24) && v.res[0] % 4 == 0 && aligned16(v.tsdf)) ? 1 : 0;
+#else
+    d.tube = 0;
+#endif
     return EMF_OK;
 }
 
