@@ -302,8 +302,11 @@ __device__ __forceinline__ void march_tube(Ray& r, const RayConst& c, const Cons
             if (all1 || all0) {
                 int n = kTubeSamples;
                 if (!done) {
-                    // samples left before the ray passes tmax, conservatively (the additions round)
-                    const float room = (c.tmax - r.tcur) / r.step * 0.999f - 1.0f;
+                    // samples left before the ray passes tmax, conservatively (the additions round) ...
+                    float room = (c.tmax - r.tcur) / r.step * 0.999f - 1.0f;
+                    // ... and as many as keep the box of an oblique ray narrow (<= ~10 voxels in x, ~5 in y)
+                    const float per = r.step * inv_s;
+                    room = fminf(room, fminf(10.0f / fmaxf(fabsf(c.dx) * per, 1e-6f), 5.0f / fmaxf(fabsf(c.dy) * per, 1e-6f)));
                     n = room >= (float)kTubeSamples ? kTubeSamples : (room > 0.0f ? (int)room : 0);
                 }
                 n = __reduce_min_sync(kFull, n);
@@ -325,7 +328,7 @@ __device__ __forceinline__ void march_tube(Ray& r, const RayConst& c, const Cons
                     const int x0 = max(lo[0], 0) & ~3, x1 = min(hi[0], V.rx - 1);
                     const int y0 = max(lo[1], 0), y1 = min(hi[1], V.ry - 1), z0 = max(lo[2], 0), z1 = min(hi[2], V.rz - 1);
                     const int nq = x1 >= x0 ? (x1 - x0) / 4 + 1 : 0, ny = y1 - y0 + 1, rows = ny * (z1 - z0 + 1);
-                    if (nq >= 1 && nq <= 4 && ny >= 1 && rows >= 1 && rows <= 8 * 32) {
+                    if (nq >= 1 && nq <= 6 && ny >= 1 && rows >= 1 && rows <= 12 * 32) {
                         const uint32_t want = all1 ? 0x3f800000u : 0u;
                         bool ok = true;
                         for (int rr = lane; rr < rows; rr += 32) {
