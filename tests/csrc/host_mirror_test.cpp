@@ -1,0 +1,173 @@
+// GPU test of the C++ host mirror (include/emf_b200.hpp): a plane + sphere scene, two frames.  emfb::TSDF / emfb::ObjTSDF
+// integrate, raycast and associate through the C ABI; the results are compared with the C oracle (TEST INFRASTRUCTURE,
+// oracle/emf_oracle.c, linked as libemf_oracle.so) bit for bit; then the tracker pulls a perturbed camera back and an
+// object volume is resized.  Built and run by tests/test_host_mirror.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "emf_b200.hpp"
+
+extern "C" {
+void emfo_update_tsdf(const float* depth, const float* assoc, int w, int h, float* tsdf, float* weights, const float* R, const float* t,
+                      const float* K, const int* res, float voxel, float trunc, float maxw, void* counts);
+void emfo_compute_grads(const float* tsdf, float* grads, const int* res);
+void emfo_raycast(const float* tsdf, const float* grads, const float* weights, float* ray, float* vert, float* norm, unsigned char* mask,
+                  int w, int h, const float* R, const float* t, const float* K, const int* res, float voxel, float trunc, void* hit,
+                  void* steps, void* step_img);
+}
+
+using namespace emfb;
+
+static int fails = 0;
+#define CHECK(c, ...) do { if (!(c)) { ++fails; std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } } while (0)
+
+static const int W = 160, H = 120;
+static const Matx33f K{131.25f, 0, 79.5f, 0, 131.25f, 59.5f, 0, 0, 1};
+
+// z-depth of a back wall at z = 3 and a sphere (0.1, 0, 1.8) r = 0.3 seen from a camera translated by (cx, cy, 0)
+static std::vector<float> render(float cx, float cy, std::vector<unsigned char>* inst = nullptr) {
+    std::vector<float> d((size_t)W * H);
+    if (inst) inst->assign((size_t)W * H, 0);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const double dx = (x - K[2]) / K[0], dy = (y - K[5]) / K[4];
+            double best = 3.0;   // wall: z = 3 (camera z = 0)
+            const double ox = cx - 0.1, oy = cy, oz = -1.8;
+            const double a = dx * dx + dy * dy + 1, b = 2 * (dx * ox + dy * oy + oz), c = ox * ox + oy * oy + oz * oz - 0.09;
+            const double disc = b * b - 4 * a * c;
+            bool sph = false;
+            if (disc > 0) { const double l = (-b - std::sqrt(disc)) / (2 * a); if (l > 0 && l < best) { best = l; sph = true; } }
+            d[(size_t)y * W + x] = (float)best;
+            if (inst && sph) (*inst)[(size_t)y * W + x] = 255;
+        }
+    return d;
+}
+
+static bool same_bits(const std::vector<float>& a, const std::vector<float>& b) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (std::memcmp(&a[i], &b[i], 4) != 0 && !(a[i] == 0 && b[i] == 0)) return false;
+    return true;
+}
+
+int main() {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { std::printf("no CUDA device\n"); return 2; }
+    TSDFParams prm;
+    const Vec3i res{64, 64, 64};
+    const float vs = 5.12f / 64, trunc = 10.0f * vs;
+    TSDF bg(res, vs, trunc, Affine::translation(0, 0, 2.56f), prm, W, H);
+    ObjTSDF::nextID() = 0;
+    ObjTSDF obj({32, 32, 32}, 1.2f / 32, 10.0f * (1.2f / 32), Affine::translation(0.1f, 0, 1.8f), prm, W, H);
+    CHECK(obj.getID() == 1, "id %d", obj.getID());
+
+    std::vector<float> t_o(bg.numVoxels(), 0.f), w_o(bg.numVoxels(), 0.f);
+    std::vector<float> ones((size_t)W * H, 1.0f);
+    Image<float> depth(W, H), weights(W, H);
+    weights.mem.upload(ones.data(), ones.size());
+    Affine cam;
+    for (int f = 0; f < 2; ++f) {
+        cam = Affine::translation(0.02f * f, -0.01f * f, 0);
+        std::vector<unsigned char> inst;
+        const std::vector<float> d = render(cam.t[0], cam.t[1], &inst);
+        depth.mem.upload(d.data(), d.size());
+        bg.integrate(depth, weights, cam, K);
+        bg.updateGradients();
+        obj.integrate(depth, weights, cam, K);
+        Image<uint8_t> mask(W, H), occl(W, H);
+        mask.mem.upload(inst.data(), inst.size());
+        obj.integrateMask(mask, occl, cam, K);
+        const Affine T = cam.inv() * bg.getPose();
+        emfo_update_tsdf(d.data(), ones.data(), W, H, t_o.data(), w_o.data(), T.R.data(), T.t.data(), K.data(), res.data(), vs, trunc,
+                         prm.maxTSDFWeight, nullptr);
+    }
+    cu(cudaDeviceSynchronize(), "sync");
+    CHECK(same_bits(bg.getTSDF(), t_o), "integrate: tsdf differs from the oracle");
+    CHECK(same_bits(bg.getWeightsVol(), w_o), "integrate: weights differ from the oracle");
+
+    // raycast of the background against the oracle
+    Image<float> ray(W, H), vert(W, H, 3), nrm(W, H, 3);
+    Image<uint8_t> mask(W, H);
+    bg.raycast(cam, K, ray, vert, nrm, mask);
+    {
+        std::vector<float> g(3 * bg.numVoxels()), r_o((size_t)W * H, 0.f), v_o((size_t)3 * W * H, 0.f), n_o((size_t)3 * W * H, 0.f);
+        std::vector<unsigned char> m_o((size_t)W * H, 0);
+        emfo_compute_grads(t_o.data(), g.data(), res.data());
+        const Affine T = bg.getPose().inv() * cam;
+        emfo_raycast(t_o.data(), g.data(), w_o.data(), r_o.data(), v_o.data(), n_o.data(), m_o.data(), W, H, T.R.data(), T.t.data(),
+                     K.data(), res.data(), vs, trunc, nullptr, nullptr, nullptr);
+        CHECK(same_bits(ray.mem.download(), r_o), "raycast: ray lengths differ from the oracle");
+        CHECK(same_bits(nrm.mem.download(), n_o), "raycast: normals differ from the oracle");
+        const std::vector<uint8_t> m = mask.mem.download();
+        size_t hits = 0, diff = 0;
+        for (size_t i = 0; i < m.size(); ++i) { hits += m[i] != 0; diff += (m[i] != 0) != (m_o[i] != 0); }
+        CHECK(diff == 0 && hits > (size_t)W * H / 2, "raycast mask: %zu hits, %zu differ", hits, diff);
+        // the materialised gradient volume equals the oracle's
+        const float* gd = bg.getGrads();
+        std::vector<float> gh(3 * bg.numVoxels());
+        cu(cudaMemcpy(gh.data(), gd, gh.size() * 4, cudaMemcpyDeviceToHost), "grads");
+        CHECK(same_bits(gh, g), "gradients differ from the oracle");
+    }
+    // the object sees itself: raycast hits inside the sphere's silhouette only, association is high there
+    Image<float> o_ray(W, H), o_vert(W, H, 3), o_nrm(W, H, 3), points(W, H, 3), a_obj(W, H), a_bg(W, H);
+    Image<uint8_t> o_mask(W, H);
+    obj.raycast(cam, K, o_ray, o_vert, o_nrm, o_mask);
+    const emf_image dimg = depth.c(), pimg = points.c();
+    ok(emf_compute_points(&dimg, &pimg, K.data(), nullptr), "emf_compute_points");
+    obj.computeAssociation(points, cam, a_obj);
+    bg.computeAssociation(points, cam, a_bg);
+    {
+        std::vector<unsigned char> inst;
+        render(cam.t[0], cam.t[1], &inst);
+        const std::vector<uint8_t> m = o_mask.mem.download();
+        const std::vector<float> ao = a_obj.mem.download(), ab = a_bg.mem.download();
+        size_t in = 0, out = 0, hit_in = 0;
+        double sa = 0;
+        for (size_t i = 0; i < m.size(); ++i) {
+            if (inst[i]) { ++in; hit_in += m[i] != 0; sa += ao[i]; } else out += m[i] != 0;
+        }
+        CHECK(in > 500 && hit_in > in * 8 / 10 && out < in / 10, "object raycast: %zu of %zu inside, %zu outside", hit_in, in, out);
+        CHECK(sa / in > 5.0, "object association on the object: mean %.3f", sa / in);
+        CHECK(ab[(size_t)10 * W + 10] > 1.0f, "background association on the wall %.3f", ab[(size_t)10 * W + 10]);
+    }
+    // tracker: a perturbed camera is pulled back towards the true one
+    {
+        Affine start = cam;
+        start.t[0] += 0.012f; start.t[1] -= 0.009f; start.t[2] += 0.01f;
+        bg.prepareTracking(start);
+        const int it = bg.track(points, weights, K, 60);
+        Affine est;
+        bg.syncTrack(est);
+        const double e0 = std::sqrt(0.012 * 0.012 + 0.009 * 0.009 + 0.01 * 0.01);
+        const double e1 = std::sqrt(std::pow(est.t[0] - cam.t[0], 2) + std::pow(est.t[1] - cam.t[1], 2) + std::pow(est.t[2] - cam.t[2], 2));
+        // (a fronto-parallel wall and one sphere in an 8 cm grid pin the pose down only loosely: the test is that the loop
+        //  runs, terminates and moves the pose the right way, not how far)
+        CHECK(it >= 2 && e1 < 0.9 * e0, "tracker: %d iterations, translation error %.4f -> %.4f", it, e0, e1);
+    }
+    // resize: a box that sticks out makes the grid grow; kept voxels keep their values
+    {
+        const std::vector<float> before = obj.getTSDF();
+        const Vec3f c = obj.resize({-0.3f, -0.2f, -0.1f}, {0.75f, 0.4f, 0.5f}, 2.0f);
+        const Vec3i r = obj.getVolumeRes();
+        cu(cudaDeviceSynchronize(), "sync");
+        CHECK(r[0] == 56 && r[0] % 2 == 0 && (c[0] != 0 || c[1] != 0 || c[2] != 0), "resize: res %d centre %.3f %.3f %.3f", r[0], c[0], c[1], c[2]);
+        const std::vector<float> after = obj.getTSDF();
+        const float v = 1.2f / 32;
+        const int off[3] = {(int)std::nearbyint(c[0] / v) - (r[0] - 32) / 2, (int)std::nearbyint(c[1] / v) - (r[1] - 32) / 2,
+                            (int)std::nearbyint(c[2] / v) - (r[2] - 32) / 2};
+        size_t checked = 0, bad = 0;
+        for (int z = 0; z < 32; z += 3)
+            for (int y = 0; y < 32; y += 3)
+                for (int x = 0; x < 32; x += 3) {
+                    const int xn = x - off[0], yn = y - off[1], zn = z - off[2];
+                    if (xn < 0 || yn < 0 || zn < 0 || xn >= r[0] || yn >= r[1] || zn >= r[2]) continue;
+                    ++checked;
+                    bad += after[((size_t)zn * r[1] + yn) * r[0] + xn] != before[((size_t)z * 32 + y) * 32 + x];
+                }
+        CHECK(checked > 100 && bad == 0, "resize: %zu of %zu kept voxels changed", bad, checked);
+    }
+    if (fails == 0) std::printf("host mirror ok\n");
+    return fails ? 1 : 0;
+}
