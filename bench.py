@@ -332,6 +332,8 @@ def run_ours(args):
             "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h * w * 4, "d2h_bytes_per_step": h * w * 5},
             "gpu_launches": launches, "host_issue_ms_per_step": t_host,
+            # a wait of the peer-memory exchange that timed out would invalidate the run: 0 = none
+            "exchange_errors": (eng._px.check_errors() if getattr(eng, "_px", None) is not None else 0),
             "clocks": clocks,
             "roofline": roof,
         }

@@ -166,3 +166,65 @@ int main(void) {
     V = _lib.Volume
     assert [int(x) for x in b.split()] == [V.weights.offset, V.grads.offset, V.fg_probs.offset, V.res.offset,
                                            V.voxel_size.offset, V.truncdist.offset, V.id.offset]
+
+
+def test_new_entry_points_reject_invalid_arguments_without_a_device(lib):
+    """tracker, resize, pre-filter and exchange entry points: argument errors are detected on the host"""
+    img = _lib.Image(None, 0, 0, 0)
+    K = (C.c_float * 9)(525, 0, 319.5, 0, 525, 239.5, 0, 0, 1)
+    res = (C.c_int * 3)(64, 64, 64)
+    off = (C.c_int * 3)(0, 0, 0)
+    vols, poses, imgs = (_lib.Volume * 1)(), (_lib.Pose * 1)(), (_lib.Image * 1)()
+    modes = (C.c_int * 1)(1)
+    pts = _lib.Image(0x1000, 640 * 12, 640, 480)
+    assert lib.emf_track_workspace_bytes(0) == 0 and lib.emf_track_workspace_bytes(_lib.EMF_MAX_VOLUMES + 1) == 0
+    assert lib.emf_track_workspace_bytes(2) > lib.emf_track_workspace_bytes(1) > 0
+    assert lib.emf_track_linearise(0, vols, poses, modes, pts, K, imgs, 0.2, 64.0, imgs, None, None, None, 0x1000, 0x1000, 1 << 20,
+                                   None) == _lib.EMF_ERR_INVALID
+    assert lib.emf_track_linearise(1, vols, poses, modes, pts, K, imgs, 0.2, 64.0, imgs, None, None, None, 0x1000, 0x1000, 8,
+                                   None) == _lib.EMF_ERR_INVALID          # workspace too small
+    assert lib.emf_track_linearise(_lib.EMF_MAX_VOLUMES + 1, vols, poses, modes, pts, K, imgs, 0.2, 64.0, imgs, None, None, None,
+                                   0x1000, 0x1000, 1 << 30, None) == _lib.EMF_ERR_UNSUPPORTED
+    bad_mode = (C.c_int * 1)(5)
+    assert lib.emf_track_linearise(1, vols, poses, bad_mode, pts, K, imgs, 0.2, 64.0, imgs, None, None, None, 0x1000, 0x1000,
+                                   1 << 20, None) == _lib.EMF_ERR_INVALID
+    lm = _lib.TrackLMParams(1e3, 1e-8, 1e-8, 2.0, 0.2, 64.0)
+    assert lib.emf_track_iterate(1, vols, None, poses, pts, K, imgs, lm, imgs, 0x1000, 0x1000, 1 << 20, 1, None) == _lib.EMF_ERR_INVALID
+    assert lib.emf_copy_values(0x1000, 0x2000, 4, off, res, res, None) == _lib.EMF_ERR_UNSUPPORTED
+    assert lib.emf_copy_values(0x1000, 0x1000, 1, off, res, res, None) == _lib.EMF_ERR_INVALID    # in place
+    assert lib.emf_resize_volume(0x1000, 0x2000, 0x3000, res, 0x4000, 0x5000, None, res, off, None) == _lib.EMF_ERR_INVALID
+    assert lib.emf_preprocess_depth(img, img, None, K, 7, 0.04, 4.5, None) == _lib.EMF_ERR_INVALID
+    d = _lib.Image(0x1000, 640 * 4, 640, 480)
+    assert lib.emf_preprocess_depth(d, d, None, K, 7, 0.04, 4.5, None) == _lib.EMF_ERR_INVALID       # in place
+    d2 = _lib.Image(0x9000, 640 * 4, 640, 480)
+    assert lib.emf_preprocess_depth(d, d2, None, K, 31, 0.04, 4.5, None) == _lib.EMF_ERR_UNSUPPORTED  # window too large
+    assert lib.emf_xchg_signal(0, None, 1, None) == _lib.EMF_ERR_INVALID
+    assert lib.emf_xchg_wait(None, 1, 1, None, 1.0, None) == _lib.EMF_ERR_INVALID
+    assert lib.emf_xchg_sum_images(0, None, img, None) == _lib.EMF_ERR_INVALID
+    assert lib.emf_xchg_open(None, None) == _lib.EMF_ERR_INVALID
+
+
+def test_track_state_layout_matches_the_header():
+    import numpy as np
+    from emfusion_b200 import ops
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "emf_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(emf_track_state), offsetof(emf_track_state, t), offsetof(emf_track_state, R_old),
+         offsetof(emf_track_state, mu), offsetof(emf_track_state, A), offsetof(emf_track_state, x), offsetof(emf_track_state, err),
+         offsetof(emf_track_state, converged));
+  printf("%zu\n", sizeof(emf_track_lm_params));
+  return 0; }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        a, b = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    dt = ops.TRACK_STATE_DTYPE
+    assert [int(x) for x in a.split()] == [dt.itemsize, dt.fields["t"][1], dt.fields["R_old"][1], dt.fields["mu"][1], dt.fields["A"][1],
+                                           dt.fields["x"][1], dt.fields["err"][1], dt.fields["converged"][1]]
+    assert int(b) == C.sizeof(_lib.TrackLMParams)
