@@ -349,7 +349,7 @@ class PeerExchange:
     Buffer layout (bytes): [flags 3 kinds x 16 ranks x u32 | pad to 256] [error word | pad to 256]
                            [counts 2 slots x 128 x i32] [normaliser 2 slots x W*H f32] [pre-composite 2 slots x `cap`]"""
     KIND_NORM, KIND_PRE, KIND_COUNTS = 0, 1, 2
-    TIMEOUT_S = 20.0
+    TIMEOUT_S = 60.0     # a rank may lag at start-up (cold imports); a real dead peer then surfaces as an error word, not a hang
 
     def __init__(self):
         pass
