@@ -216,20 +216,7 @@ __device__ __forceinline__ void samp_fetch(Samp& q, float t, const RayConst& c, 
         q.c[4] = __ldg(r10); q.c[5] = __ldg(r10 + 1); q.c[6] = __ldg(r11); q.c[7] = __ldg(r11 + 1);
     }
 }
-#ifndef EMF_RAY_ONES
-#define EMF_RAY_ONES 0     // (not measured yet: build with -DEMF_RAY_ONES=1 through scripts/ab_build.sh to A/B it)
-#endif
 __device__ __forceinline__ float samp_value(const Samp& q) {
-#if EMF_RAY_ONES
-    // free space: eight corners that all hold exactly +1 interpolate to exactly +1 whatever the fractions are
-    // (RN(RN(1 - a) + a) == 1 for every a in [0, 1)), and ~3/4 of a background ray's samples are of this kind
-    {
-        const uint32_t c0 = __float_as_uint(q.c[0]), c1 = __float_as_uint(q.c[1]), c2 = __float_as_uint(q.c[2]), c3 = __float_as_uint(q.c[3]);
-        const uint32_t c4 = __float_as_uint(q.c[4]), c5 = __float_as_uint(q.c[5]), c6 = __float_as_uint(q.c[6]), c7 = __float_as_uint(q.c[7]);
-        const uint32_t all_and = c0 & c1 & c2 & c3 & c4 & c5 & c6 & c7, all_or = c0 | c1 | c2 | c3 | c4 | c5 | c6 | c7;
-        if (all_and == 0x3f800000u && all_or == 0x3f800000u) return 1.0f;
-    }
-#endif
     const float ax = fsub(q.vx, (float)__float2int_rz(q.vx)), ay = fsub(q.vy, (float)__float2int_rz(q.vy)),
                 az = fsub(q.vz, (float)__float2int_rz(q.vz));
     const float bx = fsub(1.0f, ax), by = fsub(1.0f, ay), bz = fsub(1.0f, az);
