@@ -22,6 +22,7 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -116,7 +117,11 @@ struct Image {
     int width = 0, height = 0, channels = 1;
     Image() = default;
     Image(int w, int h, int ch = 1) : mem((size_t)w * h * ch), width(w), height(h), channels(ch) {}
-    emf_image c() const { return emf_image{(void*)mem.data(), (size_t)width * channels * sizeof(T), width, height}; }
+    emf_image external{};    // non-owning view of somebody else's image (ptr != nullptr): c() returns it
+    emf_image c() const {
+        if (external.ptr) return external;
+        return emf_image{(void*)mem.data(), (size_t)width * channels * sizeof(T), width, height};
+    }
 };
 
 // include/EMFusion/core/data.h:32-71
@@ -221,6 +226,11 @@ public:
 
     virtual std::vector<float> getTSDF() const { return tsdfVol.download(); }
     virtual std::vector<float> getWeightsVol() const { return tsdfWeights.download(); }
+    // the volume as the C ABI sees it (for the batched / engine entry points)
+    virtual emf_volume descriptor() const { return cVolume(nullptr); }
+    void setPose(const Affine& p) { pose = p; }
+    const Affine& relPoseCO() const { return rel_pose_CO; }
+    void setRelPoseCO(const Affine& T) { rel_pose_CO = T; }
 
     TSDFParams params;
     bool trackingConverged = false;
@@ -360,6 +370,11 @@ public:
         return newCenter;
     }
     std::vector<float> getFgProbVol() const { return fgProbs.download(); }
+    emf_volume descriptor() const override {
+        emf_volume v = cVolume(fgProbs.data());
+        v.fg_box = fgBox.data();
+        return v;
+    }
 
 private:
     void resetBox() {
@@ -369,6 +384,149 @@ private:
     DeviceArray<float> fgBgProbs, fgProbs;
     DeviceArray<int32_t> fgBox;
     int exCount = 1, nonExCount = 0;
+};
+
+// include/EMFusion/core/data.h:76-199 (the fields the hot path consumes)
+struct Params {
+    int frameW = 640, frameH = 480;
+    Matx33f intr{525.f, 0, 319.5f, 0, 525.f, 239.5f, 0, 0, 1};
+    Vec3i globalVolumeDims{512, 512, 512};
+    float globalVoxelSize = 0.01f, globalRelTruncDist = 10.0f;
+    Vec3i objVolumeDims{64, 64, 64};
+    float objRelTruncDist = 10.0f;
+    Affine volumePose = Affine::translation(0, 0, 2.56f);
+    int visibilityThresh = 40 * 40, boundary = 20, maxTrackingIter = 100;
+    TSDFParams tsdfParams;
+};
+
+// The hot methods of emf::EMFusion (include/EMFusion/core/EMFusion.h, src/core/EMFusion.cpp) over the native frame engine:
+// processFrame = computePoints, computeAssociationWeights, [performTracking], raycast, integrateDepth (:70-129 minus Mask R-CNN),
+// each also callable on its own.  `background` and `objects` are the reference's members (:452-454).
+class EMFusion {
+public:
+    explicit EMFusion(const Params& p)
+        : params(p),
+          background(p.globalVolumeDims, p.globalVoxelSize, p.globalRelTruncDist * p.globalVoxelSize, p.volumePose, p.tsdfParams,
+                     p.frameW, p.frameH) {
+        emf_engine_config cfg{};
+        cfg.width = p.frameW; cfg.height = p.frameH;
+        std::memcpy(cfg.K, p.intr.data(), sizeof cfg.K);
+        cfg.params = p.tsdfParams.c();
+        cfg.boundary = p.boundary; cfg.visibility_thresh = p.visibilityThresh;
+        engine_ = emf_engine_create(&cfg);
+        if (!engine_) throw std::runtime_error("emf_engine_create failed");
+        dirty_ = true;
+    }
+    EMFusion(const EMFusion&) = delete;
+    EMFusion& operator=(const EMFusion&) = delete;
+    ~EMFusion() { if (engine_) emf_engine_destroy(engine_); }
+
+    // createObj (:908-920, the volume part): a new object volume; its association image starts at 1
+    ObjTSDF& createObj(const Affine& obj_pose, float voxelSize) {
+        objects.emplace_back(new ObjTSDF(params.objVolumeDims, voxelSize, params.objRelTruncDist * voxelSize, obj_pose, params.tsdfParams,
+                                         params.frameW, params.frameH));
+        dirty_ = true;
+        created_.push_back((int)objects.size());   // engine index (background = 0)
+        return *objects.back();
+    }
+
+    void processFrame(const Image<float>& depth, cudaStream_t stream = nullptr) {
+        depth_ = &depth;
+        frame(EMF_FRAME_POINTS, stream);
+        if (frameCount > 0) {
+            computeAssociationWeights(stream);
+            if (trackingEnabled) { performTracking(stream); computeAssociationWeights(stream); }
+            raycast(stream);
+            integrateDepth(stream);
+        } else {
+            frame(EMF_FRAME_INTEGRATE | EMF_FRAME_INTEGRATE_ALL, stream);
+        }
+        ++frameCount;
+    }
+    void computeAssociationWeights(cudaStream_t stream = nullptr) { frame(EMF_FRAME_ASSOC, stream); }          // :635-670
+    void raycast(cudaStream_t stream = nullptr) { frame(EMF_FRAME_RAYCAST | EMF_FRAME_COMPOSITE, stream); }    // :726-795
+    void integrateDepth(cudaStream_t stream = nullptr) { frame(EMF_FRAME_INTEGRATE, stream); }                 // :865-889
+    // :672-722 -- the background first, then all objects together, each as one device-resident Levenberg-Marquardt run
+    void performTracking(cudaStream_t stream = nullptr) {
+        sync(stream);
+        const Image<float> pts = view(EMF_IMG_POINTS, 0, 3);
+        {
+            const Image<float> a = view(EMF_IMG_VOL_ASSOC, 0, 1);
+            background.prepareTracking(pose);
+            background.track(pts, a, params.intr, params.maxTrackingIter, stream);
+            background.syncTrack(pose);
+        }
+        computeAssociationWeights(stream);
+        for (size_t i = 0; i < objects.size(); ++i) {
+            const Image<float> a = view(EMF_IMG_VOL_ASSOC, (int)i + 1, 1);
+            objects[i]->prepareTracking(pose);
+            objects[i]->track(pts, a, params.intr, params.maxTrackingIter, stream);
+            objects[i]->syncTrack(pose);
+        }
+    }
+    // engine-owned images (valid until the object list changes): EMF_IMG_* of include/emf_b200.h
+    std::vector<float> downloadF(int what, int index, int channels) { sync(nullptr); return view(what, index, channels).mem_download(); }
+    std::vector<uint8_t> downloadSegmentation() {
+        sync(nullptr);
+        emf_image im;
+        ok(emf_engine_image(engine_, EMF_IMG_SEG, 0, &im), "emf_engine_image");
+        std::vector<uint8_t> h((size_t)im.width * im.height);
+        cu(cudaMemcpy2D(h.data(), im.width, im.ptr, im.pitch, im.width, im.height, cudaMemcpyDeviceToHost), "download seg");
+        return h;
+    }
+    std::vector<int32_t> visibilityCounts() {
+        std::vector<int32_t> c(objects.size());
+        if (!c.empty()) ok(emf_engine_vis_counts(engine_, c.data(), (int)c.size()), "emf_engine_vis_counts");
+        return c;
+    }
+
+    Params params;
+    TSDF background;
+    std::vector<std::unique_ptr<ObjTSDF>> objects;
+    Affine pose;                 // camera pose (the caller sets it when tracking is bypassed)
+    int frameCount = 0;
+    bool trackingEnabled = false;
+
+private:
+    // a non-owning view of an engine image with the interface the volume classes take
+    struct ViewF : Image<float> {
+        emf_image im{};
+        std::vector<float> mem_download() const {
+            std::vector<float> h((size_t)im.width * im.height * channels);
+            cu(cudaMemcpy2D(h.data(), (size_t)im.width * channels * 4, im.ptr, im.pitch, (size_t)im.width * channels * 4, im.height,
+                            cudaMemcpyDeviceToHost), "download");
+            return h;
+        }
+    };
+    ViewF view(int what, int index, int channels) {
+        ViewF v;
+        ok(emf_engine_image(engine_, what, index, &v.im), "emf_engine_image");
+        v.width = v.im.width; v.height = v.im.height; v.channels = channels;
+        v.external = v.im;
+        return v;
+    }
+    void sync(cudaStream_t s) { cu(cudaStreamSynchronize(s), "sync"); }
+    void syncVolumes(cudaStream_t stream) {
+        std::vector<emf_volume> v{background.descriptor()};
+        for (auto& o : objects) v.push_back(o->descriptor());
+        ok(emf_engine_set_volumes(engine_, (int)v.size(), v.data(), 1, (emf_stream_t)stream), "emf_engine_set_volumes");
+        for (int idx : created_)
+            if (frameCount > 0) ok(emf_engine_force_integrate(engine_, idx), "emf_engine_force_integrate");   // :918
+        created_.clear();
+        dirty_ = false;
+    }
+    void frame(unsigned flags, cudaStream_t stream) {
+        if (dirty_) syncVolumes(stream);
+        if (!depth_) throw std::runtime_error("no depth frame");
+        std::vector<emf_pose> co{(background.getPose().inv() * pose).c()}, oc{(pose.inv() * background.getPose()).c()};
+        for (auto& o : objects) { co.push_back((o->getPose().inv() * pose).c()); oc.push_back((pose.inv() * o->getPose()).c()); }
+        const emf_image d = depth_->c();
+        ok(emf_engine_frame(engine_, &d, co.data(), oc.data(), flags, (emf_stream_t)stream), "emf_engine_frame");
+    }
+    emf_engine* engine_ = nullptr;
+    const Image<float>* depth_ = nullptr;
+    std::vector<int> created_;
+    bool dirty_ = true;
 };
 
 }  // namespace emfb

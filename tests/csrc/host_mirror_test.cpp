@@ -168,6 +168,67 @@ int main() {
                 }
         CHECK(checked > 100 && bad == 0, "resize: %zu of %zu kept voxels changed", bad, checked);
     }
+    // ---- emfb::EMFusion: the hot methods of the orchestrator over the native frame engine
+    {
+        Params P;
+        P.frameW = W; P.frameH = H; P.intr = K;
+        P.globalVolumeDims = {64, 64, 64}; P.globalVoxelSize = vs;
+        P.objVolumeDims = {32, 32, 32};
+        P.visibilityThresh = 50; P.boundary = 4;
+        EMFusion emf(P);
+        ObjTSDF::nextID() = 0;
+        ObjTSDF& o = emf.createObj(Affine::translation(0.1f, 0, 1.8f), 1.2f / 32);
+        std::vector<float> t_ref(emf.background.numVoxels(), 0.f), w_ref(emf.background.numVoxels(), 0.f);
+        Image<float> dimg2(W, H);
+        Image<uint8_t> m2(W, H), occ2(W, H);
+        for (int f = 0; f < 3; ++f) {
+            emf.pose = Affine::translation(0.02f * f, -0.01f * f, 0);
+            std::vector<unsigned char> inst;
+            const std::vector<float> d = render(emf.pose.t[0], emf.pose.t[1], &inst);
+            dimg2.mem.upload(d.data(), d.size());
+            emf.processFrame(dimg2);
+            if (f == 0) {   // frame 0 integrates with association == 1: the background equals the oracle's
+                m2.mem.upload(inst.data(), inst.size());
+                o.integrateMask(m2, occ2, emf.pose, K);
+                const Affine T = emf.pose.inv() * emf.background.getPose();
+                emfo_update_tsdf(d.data(), ones.data(), W, H, t_ref.data(), w_ref.data(), T.R.data(), T.t.data(), K.data(), res.data(),
+                                 vs, trunc, P.tsdfParams.maxTSDFWeight, nullptr);
+                cu(cudaDeviceSynchronize(), "sync");
+                CHECK(same_bits(emf.background.getTSDF(), t_ref), "EMFusion frame 0: background differs from the oracle");
+            }
+        }
+        cu(cudaDeviceSynchronize(), "sync");
+        std::vector<unsigned char> inst;
+        render(emf.pose.t[0], emf.pose.t[1], &inst);
+        const std::vector<uint8_t> seg = emf.downloadSegmentation();
+        const std::vector<float> a_bg2 = emf.downloadF(EMF_IMG_VOL_ASSOC, 0, 1), a_o2 = emf.downloadF(EMF_IMG_VOL_ASSOC, 1, 1);
+        const std::vector<float> ray2 = emf.downloadF(EMF_IMG_VOL_RAY, 0, 1);   // the background's own raycast (the composite ray image holds object hits only)
+        size_t obj_px = 0, obj_out = 0, sil = 0, hits = 0;
+        double worst = 0;
+        for (size_t i = 0; i < seg.size(); ++i) {
+            sil += inst[i] != 0;
+            if (seg[i]) { ++obj_px; obj_out += inst[i] == 0; CHECK(seg[i] == 1, "segmentation id %d", (int)seg[i]); }
+            hits += ray2[i] > 0;
+            const float sum = a_bg2[i] + a_o2[i];
+            if (sum != 0) worst = std::fmax(worst, std::fabs(sum - 1.0));     // normalised across the volumes
+        }
+        CHECK(obj_px > sil / 2 && obj_out < sil / 8, "EMFusion segmentation: %zu object pixels, %zu outside a silhouette of %zu", obj_px, obj_out, sil);
+        CHECK(hits > seg.size() / 2, "EMFusion raycast: %zu hits", hits);
+        CHECK(worst < 1e-5, "EMFusion association: weights sum to 1 within %.2e", worst);
+        const std::vector<int32_t> vis = emf.visibilityCounts();
+        CHECK(vis.size() == 1 && vis[0] > P.visibilityThresh, "EMFusion visibility count %d", vis.empty() ? -1 : vis[0]);
+        double wsum = 0;
+        for (float w : emf.background.getWeightsVol()) wsum += w;
+        double wref = 0;
+        for (float w : w_ref) wref += w;
+        CHECK(wsum > 1.5 * wref, "EMFusion: the background kept integrating (%.0f vs %.0f after frame 0)", wsum, wref);
+        // performTracking from a perturbed pose runs and terminates
+        emf.pose.t[2] += 0.01f;
+        emf.trackingEnabled = true;
+        emf.processFrame(dimg2);
+        cu(cudaDeviceSynchronize(), "sync");
+        CHECK(std::fabs(emf.pose.t[2]) < 0.012f && emf.frameCount == 4, "EMFusion tracking: z %.4f", emf.pose.t[2]);
+    }
     if (fails == 0) std::printf("host mirror ok\n");
     return fails ? 1 : 0;
 }
