@@ -14,6 +14,7 @@
 // the level-3 entry points of emf_b200.h.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -34,6 +35,8 @@ struct emf_engine {
     int32_t* vis_count = nullptr;
     void* int_ws = nullptr;            // integrate workspace (depth pyramid)
     size_t int_ws_bytes = 0;
+    void* ray_ws = nullptr;            // raycast workspace (ray-space certificate)
+    size_t ray_ws_bytes = 0;
     int32_t* vis_host = nullptr;       // pinned
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t vis_ready = nullptr;
@@ -70,6 +73,8 @@ void carve(emf_engine* e, char* base, size_t* total) {
     e->vis_count = (int32_t*)c.raw(sizeof(int32_t) * EMF_MAX_VOLUMES);
     e->int_ws_bytes = emf_integrate_workspace_bytes(w, h);
     e->int_ws = c.raw(e->int_ws_bytes);
+    e->ray_ws_bytes = emf_raycast_workspace_bytes(w, h);
+    e->ray_ws = c.raw(e->ray_ws_bytes);
     *total = c.off;
 }
 
@@ -213,8 +218,11 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
             e->rects[1] = std::max(e->rects[1], e->bg_y0);
             e->rects[3] = std::max(e->rects[1], std::min(e->rects[3], e->bg_y1));
         }
-        rc = emf_raycast_volumes(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), e->v_ray.data(), e->v_vert.data(),
-                                 e->v_norm.data(), e->v_mask.data(), nullptr, stream);
+        // the ray-space certificate (emf_raycast_volumes_ws) is opt-in: EMF_RAY_CERT=1 (see DESIGN.md for the measurements)
+        static const bool use_cert = [] { const char* v = getenv("EMF_RAY_CERT"); return v && v[0] == '1'; }();
+        rc = emf_raycast_volumes_ws(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), e->v_ray.data(), e->v_vert.data(),
+                                    e->v_norm.data(), e->v_mask.data(), nullptr, use_cert ? e->ray_ws : nullptr,
+                                    use_cert ? e->ray_ws_bytes : 0, stream);
         if (rc != EMF_OK) return rc;
     }
     if (flags & (EMF_FRAME_COMPOSITE | EMF_FRAME_COMPOSITE_NOBG)) {

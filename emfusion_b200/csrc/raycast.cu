@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "seq_add.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace emfb {
 
@@ -46,8 +47,15 @@ struct RayVol {
     float thr1[3], thr2[3];  // smallest v with fadd(v, pad) >= R per axis, pad = 1 / 2 (bounds tests without the addition)
     int x0, y0, x1, y1;      // screen rect (exclusive upper)
     int tiles_x;             // tiles per rect row
+    int tiles_y;             // tile rows; > 0: blocks take the tiles ring by ring from the rim of the rectangle inwards (0: row-major)
     int first_block;
     int tube;                // 1: tube skipping (large volume, Rx % 4 == 0, 16-byte aligned)
+    // ray-space certificate (k_ray_certify): bit (slab, tile) = every voxel a march sample of that 8 x 4 pixel tile can
+    // touch while its base voxel lies in that slab holds exactly +1
+    const uint32_t* cert;    // nullable: word [slab * cert_G + tile / 32], bit tile % 32
+    int cert_G, cert_txc;    // words per slab; tiles per rect row
+    int cert_axis, cert_sign, cert_L;   // slabs are ranges of 2^L voxels along this volume axis; every ray advances along it in this direction
+    int cert_nw;             // words of slab bits that k_ray_certify wrote (the others read as 0)
 };
 
 struct RayParams {
@@ -57,6 +65,7 @@ struct RayParams {
     float K[9];
     int32_t* hit_voxel;      // optional (single-volume API)
     int write_all;           // 1: batched semantics (ray/mask written for every pixel of the rect)
+    int hist;                    // diagnostics (EMF_RAY_HIST=1, needs 32 counters): stats[8 + min(15, warp iterations / 32)]++, stats[24] = max
     unsigned long long* stats;   // optional: [0] tsdf samples taken [1] samples skipped by jumps
                                  //           [2] jumps [3] weight samples
 };
@@ -81,17 +90,34 @@ __device__ __forceinline__ float trilinear32(const float* __restrict__ vol, int 
     return lerp1(bz, lerp1(by, c00, ay, c01), az, lerp1(by, c10, ay, c11));
 }
 
-__device__ __forceinline__ float weight_at(const RayVol& V, int64_t idx) {
-    float w = __ldg(V.weights + idx);
-    if (V.fg_probs) w = (__ldg(V.fg_probs + idx) > 0.5f) ? w : 0.0f;
-    return w;
+// (a real function: it is needed for a handful of samples per ray, and inlining it at every site of the march made the
+//  kernel larger than the instruction cache -- "no instruction" became the top stall reason)
+#ifndef EMF_RAY_WEIGHT_INLINE
+#define EMF_RAY_WEIGHT_INLINE 1      // measured: 0.608 ms (inline) vs 0.653 ms (call) for the frame's raycast
+#endif
+#if EMF_RAY_WEIGHT_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+float trilinear_weight_fn(const float* __restrict__ weights, const float* __restrict__ fg_probs, int rx, int ry,
+                                                  float vx, float vy, float vz) {
+    const TriSetup s(vx, vy, vz, rx, ry);
+    const int64_t b[4] = {s.base, s.base + rx, s.base + (int64_t)ry * rx, s.base + (int64_t)ry * rx + rx};
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w[2 * k] = __ldg(weights + b[k]); w[2 * k + 1] = __ldg(weights + b[k] + 1); }
+    if (fg_probs) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w[2 * k] = (__ldg(fg_probs + b[k]) > 0.5f) ? w[2 * k] : 0.0f;
+            w[2 * k + 1] = (__ldg(fg_probs + b[k] + 1) > 0.5f) ? w[2 * k + 1] : 0.0f;
+        }
+    }
+    return s.combine(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
 }
-
 __device__ __forceinline__ float trilinear_weight(const RayVol& V, float vx, float vy, float vz) {
-    const TriSetup s(vx, vy, vz, V.rx, V.ry);
-    const int64_t b00 = s.base, b01 = b00 + V.rx, b10 = b00 + (int64_t)V.ry * V.rx, b11 = b10 + V.rx;
-    return s.combine(weight_at(V, b00), weight_at(V, b00 + 1), weight_at(V, b01), weight_at(V, b01 + 1),
-                     weight_at(V, b10), weight_at(V, b10 + 1), weight_at(V, b11), weight_at(V, b11 + 1));
+    return trilinear_weight_fn(V.weights, V.fg_probs, V.rx, V.ry, vx, vy, vz);
 }
 
 // forward-difference gradient at integer voxel (x,y,z); zero on the last plane of each axis
@@ -198,14 +224,30 @@ struct Samp {
     float c[8];
     bool in;
 };
-__device__ __forceinline__ void samp_fetch(Samp& q, float t, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane) {
+// the guarded divisions (a numerator that is tiny or exactly zero, or a ray outside ConstDiv's window): rare, out of line
+#ifndef EMF_RAY_GDIV_INLINE
+#define EMF_RAY_GDIV_INLINE 0
+#endif
+#if EMF_RAY_GDIV_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+float3 guarded_div3(float nx, float ny, float nz, float s) {
+    const ConstDiv div_s(s);
+    return make_float3(div_s(nx), div_s(ny), div_s(nz));
+}
+__device__ __forceinline__ void samp_pos(Samp& q, float t, const RayConst& c, const ConstDiv& div_s, const RayVol& V) {
     const float nx = ffma(c.dx, t, c.ox), ny = ffma(c.dy, t, c.oy), nz = ffma(c.dz, t, c.oz);
     if (c.sane && fminf(fminf(fabsf(nx), fabsf(ny)), fabsf(nz)) > 5.5e-20f) {
         q.vx = fadd(c.hxh, div_s.fast(nx)); q.vy = fadd(c.hyh, div_s.fast(ny)); q.vz = fadd(c.hzh, div_s.fast(nz));
     } else {
-        q.vx = fadd(c.hxh, div_s(nx)); q.vy = fadd(c.hyh, div_s(ny)); q.vz = fadd(c.hzh, div_s(nz));
+        const float3 d = guarded_div3(nx, ny, nz, c.s);
+        q.vx = fadd(c.hxh, d.x); q.vy = fadd(c.hyh, d.y); q.vz = fadd(c.hzh, d.z);
     }
     q.in = !out_of_thr(q.vx, q.vy, q.vz, V.thr2);
+}
+__device__ __forceinline__ void samp_load(Samp& q, const RayVol& V, int rx, int plane) {
     if (q.in) {
         const int lx = __float2int_rz(q.vx), ly = __float2int_rz(q.vy), lz = __float2int_rz(q.vz);
         const float* r00 = V.tsdf + (uint32_t)(lz * plane + ly * rx + lx);
@@ -215,6 +257,10 @@ __device__ __forceinline__ void samp_fetch(Samp& q, float t, const RayConst& c, 
         q.c[0] = __ldg(r00); q.c[1] = __ldg(r00 + 1); q.c[2] = __ldg(r01); q.c[3] = __ldg(r01 + 1);
         q.c[4] = __ldg(r10); q.c[5] = __ldg(r10 + 1); q.c[6] = __ldg(r11); q.c[7] = __ldg(r11 + 1);
     }
+}
+__device__ __forceinline__ void samp_fetch(Samp& q, float t, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane) {
+    samp_pos(q, t, c, div_s, V);
+    samp_load(q, V, rx, plane);
 }
 __device__ __forceinline__ float samp_value(const Samp& q) {
     const float ax = fsub(q.vx, (float)__float2int_rz(q.vx)), ay = fsub(q.vy, (float)__float2int_rz(q.vy)),
@@ -228,7 +274,7 @@ __device__ __forceinline__ float samp_value(const Samp& q) {
 template <bool STATS>
 __device__ __forceinline__ bool samp_resolve(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, const Samp& q, float fn,
                                              unsigned long long* st) {
-    if (STATS) ++st[0];
+    if (STATS) { ++st[0]; if (r.f == 1.0f && fn == 1.0f) ++st[6]; }
     if (r.f < 0.0f && fn > 0.0f) {
         if (STATS) ++st[3];
         if (trilinear_weight(V, q.vx, q.vy, q.vz) > 0.0f) return true;
@@ -256,6 +302,7 @@ template <bool STATS>
 __device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
                                             unsigned long long* st, int max_iters = 0x7fffffff) {
     for (int it = 0; it < max_iters; ++it) {
+        if (STATS) { const unsigned am = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am) - 1) { ++st[4]; st[5] += __popc(am); } }
         const float t1 = fadd(r.tcur, r.step);
         if (!(t1 <= c.tmax)) return true;
         const float t2 = fadd(t1, r.step);
@@ -274,7 +321,56 @@ __device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const Con
     return false;
 }
 
-// ---- tube skipping (large volumes; compiled in, OFF by default: EMF_RAY_TUBE -- see DESIGN.md section 4.3 for why).
+// ---- certified skipping (k_ray_certify below).  While a ray carries exactly +1, a march sample whose eight corners all
+// hold exactly +1 returns exactly +1 again ((1 - a) + a rounds to 1 for every fraction a) and changes nothing of the march
+// state but the ray parameter.  The certificate says, per 8 x 4 pixel tile (= one warp) and per slab of 2^L voxels along
+// the volume axis the camera looks along, that EVERY voxel any sample of any ray of the tile can touch while its base
+// voxel is in that slab holds +1.  The ray position along that axis is monotone in the ray parameter (every rounded
+// operation of ray_position is), so a run of certified slabs is skipped in one go: the n additions of the ray parameter
+// in closed form (inside one binade RN(t + step) = t + inc with a constant inc: seq_add.h), then the position of the LAST
+// skipped sample is evaluated exactly as the sampler would and checked to lie in the run -- the samples before it then
+// do, too.  Bit-identical to marching through.
+// The warp works in phases, decided with ballots (its rays share the tile's bits): rays whose next sample is certified wait
+// until every ray of the warp is in that state (or finished), then all skip together; otherwise the others take samples.
+// Skipping lane by lane instead makes nearly every iteration of the warp pay for both paths (measured: no faster than marching).
+constexpr int kCertWords = 8;                      // 32-bit words of slab bits per tile
+constexpr int kCertSlabs = 32 * kCertWords;
+
+// Advances t by up to `total` executions of `t = t + step` (round to nearest even each), returns the new t and how many
+// were made in `made` (>= 1 when total >= 1).  Inside one binade every float is a multiple of u = 2^(e-23), so
+// RN(t + step) = t + inc with a constant inc once two consecutive additions agree (seq_add.h); the number of additions that
+// stay below 2^(e+1) is an exact integer quotient of bit-pattern differences.  A few rounds cover a few binades.
+__device__ __forceinline__ float cert_hop(float t, float step, int total, int& made) {
+    made = 0;
+#pragma unroll 1
+    for (int round = 0; round < 4 && made < total; ++round) {
+        const float t1 = __fadd_rn(t, step);
+        ++made;
+        const uint32_t u0 = __float_as_uint(t), u1 = __float_as_uint(t1);
+        const uint32_t b1 = u1 >> 23;
+        const int left = total - made;
+        if (left < 1 || (u0 >> 23) != b1 || b1 == 0u || b1 >= 254u || !(step > 0.0f) || !(step <= t)) { t = t1; continue; }
+        const float t2 = __fadd_rn(t1, step);
+        const uint32_t u2 = __float_as_uint(t2);
+        const uint32_t B = u1 - u0;                                  // inc in ulps of the binade
+        if ((u2 >> 23) != b1 || u2 - u1 != B || B == 0u) { t = t1; continue; }
+        const uint32_t A = ((b1 + 1u) << 23) - u1 - 1u;              // additions k after t1 stay in the binade iff k * B <= A
+        int k = (int)__fdividef((float)A, (float)B);                 // A < 2^23: both exact as floats; quotient to an ulp
+        if ((uint64_t)(uint32_t)k * B > A) --k;
+        else if ((uint64_t)(uint32_t)(k + 1) * B <= A) ++k;
+        k = min(k, left);
+        if (k < 1) { t = t1; continue; }
+        t = __uint_as_float(u1 + (uint32_t)k * B);                    // = t1 + k * inc, exactly
+        made += k;
+    }
+    return t;
+}
+
+#ifndef EMF_RAY_TUBE
+#define EMF_RAY_TUBE 0
+#endif
+#if EMF_RAY_TUBE
+// ---- tube skipping (large volumes; compiled only with -DEMF_RAY_TUBE=1 -- see DESIGN.md section 4.3 for why).
 // The rays of a warp -- an 8 x 4 pixel patch -- run inside a tube a few voxels wide.  A
 // march sample whose eight corners all hold exactly +1 (observed free space) returns exactly +1 again and changes nothing
 // of the march state but the ray parameter; the same goes for exactly 0 (never observed) once the step is half a voxel.
@@ -358,48 +454,16 @@ __device__ __forceinline__ void march_tube(Ray& r, const RayConst& c, const Cons
     }
 }
 
-// JUMP = false: every lane marches its own ray (the lean default).
-// JUMP = true : the warp stays in lockstep so that jumps through certified constant regions can be agreed on with warp
-//               collectives (needs emf_volume::brick_map on at least one volume of the launch).
-#ifndef EMF_RAY_PAIR
-#define EMF_RAY_PAIR 1
-#endif
-#ifndef EMF_RAY_TUBE
-#define EMF_RAY_TUBE 0
-#endif
-#ifndef EMF_RAY_MINB
-#define EMF_RAY_MINB 8
-#endif
-template <bool STATS, bool JUMP>
-__global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __grid_constant__ RayParams P) {
-    unsigned long long st[4] = {0, 0, 0, 0};
-    int lo = 0, hi = P.n_vol - 1;
-    const int b = blockIdx.x;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (P.v[mid].first_block <= b) lo = mid; else hi = mid - 1;
-    }
-    const RayVol& V = P.v[lo];
-    const int lb = b - V.first_block;
-    const int ty = lb / V.tiles_x, tx = lb - ty * V.tiles_x;
-    // warp = kWarpW x kWarpH pixel patch inside the CTA tile
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xr = V.x0 + tx * kTileW + (warp & 1) * kWarpW + (lane % kWarpW);
-    const int yr = V.y0 + ty * kTileH + (warp >> 1) * kWarpH + (lane / kWarpW);
-    const bool valid = xr < V.x1 && yr < V.y1;
-    if (!JUMP && !valid && !V.tube) return;   // (tube skipping uses warp collectives: idle lanes stay)
-    const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);   // (JUMP: lanes outside the rectangle idle in the loop)
+#endif   // EMF_RAY_TUBE
 
-    float* ray_px = (float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x;
-    uint8_t* mask_px = V.mask + (size_t)y * V.mask_pitch + x;
-    Ray r;
-    r.out_t = 0.0f; r.hit = false;
-    r.hvx = r.hvy = r.hvz = r.hmx = r.hmy = r.hmz = 0.f;
-    RayConst c;
+// Everything of the reference kernel before its march loop (TSDF.cu:477-521): the ray, the slab test, the coarse skip and
+// the first sample.  false = the ray has nothing to march (misses the box / the foreground box, or never gets inside).
+// the ray and its interval [t_first, c.tmax] inside the volume (TSDF.cu:477-503); false = nothing to march
+__device__ __forceinline__ bool ray_consts(const RayVol& V, const float* K, int x, int y, float old, RayConst& c, float& t_first) {
     c.s = V.voxel;
     const float s = c.s;
-    const float ux = fdiv(fsub((float)x, P.K[2]), P.K[0]);
-    const float uy = fdiv(fsub((float)y, P.K[5]), P.K[4]);
+    const float ux = fdiv(fsub((float)x, K[2]), K[0]);
+    const float uy = fdiv(fsub((float)y, K[5]), K[4]);
     // rot_CO * (ux, uy, 1)
     const float rayx = fadd(V.R[2], ffma(V.R[0], ux, fmul(V.R[1], uy)));
     const float rayy = fadd(V.R[5], ffma(V.R[3], ux, fmul(V.R[4], uy)));
@@ -415,9 +479,8 @@ __global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __g
                             fdiv(fsub(c.dz > 0.f ? -bz : bz, c.oz), c.dz));
     const float tout = fminf(fminf(fdiv(fsub(c.dx > 0.f ? bx : -bx, c.ox), c.dx), fdiv(fsub(c.dy > 0.f ? by : -by, c.oy), c.dy)),
                              fdiv(fsub(c.dz > 0.f ? bz : -bz, c.oz), c.dz));
-    r.tcur = fadd(s, tin);
+    t_first = fadd(s, tin);
     c.tmax = fsub(tout, s);
-    const float old = (P.write_all || !valid) ? 0.0f : *ray_px;   // in/out far clip (TSDF.cu:496-500)
     if (old != 0.0f) c.tmax = fminf(old, c.tmax);
 
     c.hxh = fmul((float)(V.rx - 1), 0.5f); c.hyh = fmul((float)(V.ry - 1), 0.5f); c.hzh = fmul((float)(V.rz - 1), 0.5f);
@@ -445,31 +508,93 @@ __global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __g
         else c.tmax = fminf(c.tmax, tb);
     }
     const ConstDiv div_s(s);
-    c.sane = div_s.ok && fabsf(c.ox) + fabsf(c.oy) + fabsf(c.oz) + fabsf(r.tcur) + fabsf(c.tmax) + V.trunc < 1.0e18f;
-    const int rx = V.rx, plane = V.rx * V.ry;
+    c.sane = div_s.ok && fabsf(c.ox) + fabsf(c.oy) + fabsf(c.oz) + fabsf(t_first) + fabsf(c.tmax) + V.trunc < 1.0e18f;
+    return !(culled || t_first >= c.tmax);
+}
+__device__ __forceinline__ bool ray_begin(const RayVol& V, const float* K, int x, int y, float old, Ray& r, RayConst& c) {
+    r.out_t = 0.0f; r.hit = false;
+    r.hvx = r.hvy = r.hvz = r.hmx = r.hmy = r.hmz = 0.f;
     r.step = V.trunc;
     r.vx = r.vy = r.vz = r.f = 0.f;
-    bool done = !valid || culled || r.tcur >= c.tmax;
-    if (!done) {
-        for (;;) {   // coarse skip (TSDF.cu:509-515)
-            ray_position(r, c, div_s);
-            if (out_of_thr(r.vx, r.vy, r.vz, V.thr1) && r.tcur < c.tmax) r.tcur = fadd(r.step, r.tcur);
-            else break;
-        }
-        // still outside => the reference's march loop cannot run (tcur >= tmax): defined as no hit
-        if (!out_of_thr(r.vx, r.vy, r.vz, V.thr1) && r.vx == r.vx && r.vy == r.vy && r.vz == r.vz) {
-            r.f = trilinear(V.tsdf, V.rx, V.ry, r.vx, r.vy, r.vz);
-            if (fabsf(r.f) < 1.0f) r.step = s;
-            if (fabsf(r.f) < 0.8f) r.step = c.half_s;
-        } else {
-            done = true;
-        }
+    r.tcur = 0.f;
+    if (!ray_consts(V, K, x, y, old, c, r.tcur)) return false;
+    const float s = c.s;
+    const ConstDiv div_s(s);
+    for (;;) {   // coarse skip (TSDF.cu:509-515)
+        ray_position(r, c, div_s);
+        if (out_of_thr(r.vx, r.vy, r.vz, V.thr1) && r.tcur < c.tmax) r.tcur = fadd(r.step, r.tcur);
+        else break;
     }
-    if (!JUMP) {
+    // still outside => the reference's march loop cannot run (tcur >= tmax): defined as no hit
+    if (!out_of_thr(r.vx, r.vy, r.vz, V.thr1) && r.vx == r.vx && r.vy == r.vy && r.vz == r.vz) {
+        r.f = trilinear(V.tsdf, V.rx, V.ry, r.vx, r.vy, r.vz);
+        if (fabsf(r.f) < 1.0f) r.step = s;
+        if (fabsf(r.f) < 0.8f) r.step = c.half_s;
+        return true;
+    }
+    return false;
+}
+
+// MODE 0: every lane marches its own ray, two samples in flight (objects; volumes without a certificate).
+// (certified skipping -- the volume carries RayVol::cert -- has its own kernel: k_raycast_cert)
+// MODE 2: the warp stays in lockstep so that jumps through certified constant regions can be agreed on with warp
+//         collectives (needs emf_volume::brick_map on at least one volume of the launch).
+// One loop per kernel: with all of them inlined into one kernel the code outgrew the instruction cache.
+#ifndef EMF_RAY_PAIR
+#define EMF_RAY_PAIR 1
+#endif
+#ifndef EMF_RAY_TUBE
+#define EMF_RAY_TUBE 0
+#endif
+#ifndef EMF_CERT_L
+#define EMF_CERT_L 2      // log2 of the smallest slab thickness (voxels)
+#endif
+#ifndef EMF_RAY_MINB
+#define EMF_RAY_MINB 8
+#endif
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+template <bool STATS, int MODE>
+__global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __grid_constant__ RayParams P) {
+    constexpr bool JUMP = MODE == 2;
+    unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [4], [5]: warp iterations of the march loop and the lanes active in them
+    const unsigned long long t_begin = (STATS && P.hist == 2) ? global_ns() : 0ull;
+    int lo = 0, hi = P.n_vol - 1;
+    const int b = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (P.v[mid].first_block <= b) lo = mid; else hi = mid - 1;
+    }
+    const RayVol& V = P.v[lo];
+    const int lb = b - V.first_block;
+    int ty = lb / V.tiles_x, tx = lb - ty * V.tiles_x;
+    // warp = kWarpW x kWarpH pixel patch inside the CTA tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xr = V.x0 + tx * kTileW + (warp & 1) * kWarpW + (lane % kWarpW);
+    const int yr = V.y0 + ty * kTileH + (warp >> 1) * kWarpH + (lane / kWarpW);
+    const bool valid = xr < V.x1 && yr < V.y1;
+    if (MODE == 0 && !valid && !(EMF_RAY_TUBE && V.tube)) return;   // (the other modes use warp collectives: idle lanes stay)
+    const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);   // (JUMP: lanes outside the rectangle idle in the loop)
+
+    float* ray_px = (float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x;
+    uint8_t* mask_px = V.mask + (size_t)y * V.mask_pitch + x;
+    Ray r;
+    RayConst c;
+    const float old = (P.write_all || !valid) ? 0.0f : *ray_px;   // in/out far clip (TSDF.cu:496-500)
+    bool done = !ray_begin(V, P.K, x, y, old, r, c) || !valid;
+    const ConstDiv div_s(c.s);
+    const int rx = V.rx, plane = V.rx * V.ry;
+    if (MODE == 0) {
+#if EMF_RAY_TUBE
         if (V.tube) {
             march_tube<STATS>(r, c, div_s, V, rx, plane, done, st);
             if (!valid) return;
-        } else if (!done) {
+        } else
+#endif
+        if (!done) {
 #if EMF_RAY_PAIR
             march_pairs<STATS>(r, c, div_s, V, rx, plane, st);
 #else
@@ -481,6 +606,7 @@ __global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __g
         const uint8_t* __restrict__ bmap = V.bmap;
         const float frx = (float)V.rx, fry = (float)V.ry, frz = (float)V.rz;
         // jump geometry: voxels advanced per metre of ray parameter along each axis (and the largest of them)
+        const float s = c.s;
         const float ax_m = fdiv(fabsf(c.dx), s), ay_m = fdiv(fabsf(c.dy), s), az_m = fdiv(fabsf(c.dz), s);
         const float vox_per_m = fmaxf(ax_m, fmaxf(ay_m, az_m));
         int wait = 0;   // (warp-uniform) march steps to take before the brick map is consulted again after a failed attempt
@@ -570,8 +696,482 @@ __global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __g
     }
     if (STATS && P.stats) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (st[k]) atomicAdd(P.stats + k, st[k]);
+        for (int k = 0; k < 8; ++k) if (st[k]) atomicAdd(P.stats + k, st[k]);
+        if (P.hist && V.cert && (threadIdx.x & 31) == 0) {
+            atomicAdd(P.stats + 8 + min(15ull, st[4] / 32ull), 1ull);
+            atomicMax(P.stats + 24, st[4]);
+        }
+        if (P.hist == 2 && (threadIdx.x & 31) == 0) {   // timeline: 4 words per warp after the 32 counters
+            unsigned smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            unsigned long long* rec = P.stats + 32 + 4 * ((size_t)blockIdx.x * (kRayThreads / 32) + (threadIdx.x >> 5));
+            rec[0] = t_begin; rec[1] = global_ns(); rec[2] = st[4]; rec[3] = ((unsigned long long)smid << 32) | (unsigned)lo;
+        }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_raycast_cert: the certified march of one volume (the background), FOUR LANES PER RAY.
+//
+// What bounds the background's raycast is not its number of samples but its longest DEPENDENT CHAIN: rays along the rim of
+// the frustum and along the shadow volumes of objects run through seams of observed / never observed / occluded space for
+// up to ~1200 samples that are no no-ops, and a sample is position -> 8 gathers -> 7 lerps -> decision.  One ray per
+// lane marches that chain two samples at a time (0.7 us per pair on an otherwise idle SM: the whole launch waits for it).
+// Here the four lanes of a group take the ray's next EIGHT samples at once, two each (lane j: samples 2j and 2j + 1, at t
+// after 2j + 1 / 2j + 2 additions of the step), under the assumption that the step does not change.  The first sample
+// that changes the march state otherwise than by f = fn -- a different step, a sign change that ends the ray or keeps f,
+// a sample outside the march bounds, the end of the ray -- is the "stop": the samples before it are accepted wholesale
+// (state after them: t and f of the last one), the stop sample is resolved by the sequential rule by all lanes of the
+// group in step (they hold the same state), what lies behind it is discarded.  Same samples, same arithmetic, same order
+// as the reference loop (TSDF.cu:523-572): bit-identical, the chain per sample four times shorter, and as many warp
+// instructions per accepted sample as with one ray per lane.
+// A CTA is one 8 x 4 pixel tile of the certificate (k_ray_certify below), a warp one row of it.  Skipping: see cert_hop
+// above -- the warp works in phases decided with ballots: rays whose next sample is certified wait until every ray of
+// the warp is in that state (or finished), then all skip together.  Tiles are handed out rim first.
+// ---------------------------------------------------------------------------------------------
+struct CertRayParams {
+    RayVol v;
+    float K[9];
+    int w, h;
+    int hist;
+    unsigned long long* stats;
+};
+
+
+struct RayEvent { int code; float ts, sx, sy, sz; };   // 0: go on, f = fn; 1: finished (back face); 2: go on, f unchanged; 3: hit
+
+// a sign change between the previous sample f and this one fn (TSDF.cu:532, 540-566); `step` is the step AFTER its update
+__device__ __noinline__ RayEvent ray_event(const RayVol& V, float f, float fn, float tcur, float step, float vx, float vy, float vz,
+                                           float dx, float dy, float dz) {
+    RayEvent e;
+    e.code = 0; e.ts = e.sx = e.sy = e.sz = 0.0f;
+    if (f < 0.0f && fn > 0.0f) {     // back face: ends the ray if the weight there is positive
+        if (trilinear_weight_fn(V.weights, V.fg_probs, V.rx, V.ry, vx, vy, vz) > 0.0f) e.code = 1;
+        return e;
+    }
+    const ConstDiv div_s(V.voxel);
+    const float hxh = fmul((float)(V.rx - 1), 0.5f), hyh = fmul((float)(V.ry - 1), 0.5f), hzh = fmul((float)(V.rz - 1), 0.5f);
+    const float ts = fsub(tcur, fdiv(fmul(f, step), fsub(fn, f)));
+    const float sx = fadd(hxh, div_s(fadd(V.t[0], fmul(dx, ts))));
+    const float sy = fadd(hyh, div_s(fadd(V.t[1], fmul(dy, ts))));
+    const float sz = fadd(hzh, div_s(fadd(V.t[2], fmul(dz, ts))));
+    if (out_of_thr(sx, sy, sz, V.thr2)) { e.code = 2; return e; }     // reference `continue`: f keeps its old value
+    if (trilinear_weight_fn(V.weights, V.fg_probs, V.rx, V.ry, sx, sy, sz) > 0.0f) {
+        e.code = 3; e.ts = ts; e.sx = sx; e.sy = sy; e.sz = sz;
+    }
+    return e;
+}
+
+// vertex, normal, ray length and mask of a hit (TSDF.cu:552-566)
+__device__ __noinline__ void ray_emit_hit(const RayVol& V, int x, int y, float ts, float sx, float sy, float sz, float dx, float dy, float dz,
+                                          int32_t* hit_voxel, int w) {
+    float g[3];
+    trilinear_grad(V, sx, sy, sz, g);
+    const float mx = fmul(dx, ts), my = fmul(dy, ts), mz = fmul(dz, ts);
+    float* vp = (float*)((char*)V.vert + (size_t)y * V.vert_pitch) + 3 * x;
+    float* np = (float*)((char*)V.norm + (size_t)y * V.norm_pitch) + 3 * x;
+    // transpose(rot_CO) * (t* dir)
+    vp[0] = dot_yxz(V.R[0], V.R[3], V.R[6], mx, my, mz);
+    vp[1] = dot_yxz(V.R[1], V.R[4], V.R[7], mx, my, mz);
+    vp[2] = dot_yxz(V.R[2], V.R[5], V.R[8], mx, my, mz);
+    const float gn = norm3(g[0], g[1], g[2]);
+    const float nx = fdiv(g[0], gn), ny = fdiv(g[1], gn), nz = fdiv(g[2], gn);
+    np[0] = dot_yxz(V.R[0], V.R[3], V.R[6], nx, ny, nz);
+    np[1] = dot_yxz(V.R[1], V.R[4], V.R[7], nx, ny, nz);
+    np[2] = dot_yxz(V.R[2], V.R[5], V.R[8], nx, ny, nz);
+    *((float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x) = ts;
+    V.mask[(size_t)y * V.mask_pitch + x] = 1;
+    if (hit_voxel) {
+        int32_t* hv = hit_voxel + 3 * ((size_t)y * w + x);
+        hv[0] = __float2int_rz(sx); hv[1] = __float2int_rz(sy); hv[2] = __float2int_rz(sz);
+    }
+}
+
+constexpr int kGrpLanes = 4;         // lanes per ray
+constexpr int kGrpSamples = 2 * kGrpLanes;   // samples per ray and iteration
+#ifndef EMF_CERT_MINB
+#define EMF_CERT_MINB 6
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(kRayThreads, EMF_CERT_MINB) k_raycast_cert(const __grid_constant__ CertRayParams P) {
+    constexpr unsigned kFull = 0xffffffffu;
+    unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long t_begin = (STATS && P.hist == 2) ? global_ns() : 0ull;
+    const RayVol& V = P.v;
+    // the CTA's tile (8 x 4 pixels), rim of the rectangle first
+    const int n_tx = V.cert_txc, n_ty = 2 * V.tiles_y;
+    int ty, tx;
+    {
+        int r = 0, rest = blockIdx.x, wr = n_tx, hr = n_ty;
+        for (;;) {
+            const int cnt = hr == 1 ? wr : (wr == 1 ? hr : 2 * wr + 2 * hr - 4);
+            if (rest < cnt || wr <= 2 || hr <= 2) break;
+            rest -= cnt; ++r; wr -= 2; hr -= 2;
+        }
+        if (wr <= 2 || hr <= 2) { ty = r + rest / wr; tx = r + rest - (rest / wr) * wr; }      // the core that is left: row-major
+        else if (rest < wr) { ty = r; tx = r + rest; }
+        else if (rest < 2 * wr) { ty = r + hr - 1; tx = r + rest - wr; }
+        else if (rest < 2 * wr + hr - 2) { tx = r; ty = r + 1 + rest - 2 * wr; }
+        else { tx = r + wr - 1; ty = r + 1 + rest - 2 * wr - (hr - 2); }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane & (kGrpLanes - 1), gl0 = lane & ~(kGrpLanes - 1);     // lane inside the group, first lane of the group
+    const int xr = V.x0 + tx * kWarpW + (lane / kGrpLanes);
+    const int yr = V.y0 + ty * kWarpH + warp;
+    const bool valid = xr < V.x1 && yr < V.y1;
+    __shared__ uint32_t s_cert[2 * kCertWords];   // [0, kCertWords): all +1 ; [kCertWords, 2 kCertWords): all 0
+    if (warp == 0) {
+        // the tile's slab bits, one word per 32 slabs (lane = slab of the word, bit = the tile inside its group of 32)
+        const int ti = ty * V.cert_txc + tx;
+        const int g = ti >> 5, tb = ti & 31;
+#pragma unroll
+        for (int k = 0; k < 2 * kCertWords; ++k) {
+            const int kk = k & (kCertWords - 1);
+            const uint32_t* tab = V.cert + (k < kCertWords ? (size_t)0 : (size_t)kCertSlabs * V.cert_G);
+            const uint32_t wd = kk < V.cert_nw ? __ldg(tab + (size_t)(32 * kk + lane) * V.cert_G + g) : 0u;
+            const uint32_t col = __ballot_sync(kFull, (wd >> tb) & 1u);
+            if (lane == 0) s_cert[k] = col;
+        }
+    }
+    __syncthreads();
+    const uint32_t* __restrict__ bits = s_cert;
+    const int x = min(xr, V.x1 - 1), y = min(yr, V.y1 - 1);   // (lanes outside the rectangle idle in the loop)
+    Ray r;
+    RayConst c;
+    bool done = !ray_begin(V, P.K, x, y, 0.0f, r, c) || !valid;
+    bool hit = false;
+    const ConstDiv div_s(c.s);
+    const int rx = V.rx, plane = V.rx * V.ry;
+    const int axis = V.cert_axis, L = V.cert_L;
+    const float d_a = axis == 0 ? c.dx : (axis == 1 ? c.dy : c.dz);
+    const float o_a = axis == 0 ? c.ox : (axis == 1 ? c.oy : c.oz);
+    const float h_a = axis == 0 ? c.hxh : (axis == 1 ? c.hyh : c.hzh);
+    const bool fwd = V.cert_sign > 0;
+    const bool can = fwd ? d_a > 0.04f : d_a < -0.04f;
+    const float inv_da = __fdividef(1.0f, d_a);
+    float f = r.f, tcur = r.tcur, step = r.step;      // the ray's state: identical in the lanes of its group
+
+    for (;;) {
+        if (STATS) { if (lane == 0) ++st[4]; if (!done) ++st[5]; }
+        // ---- this lane's two samples: 2 sub + 1 and 2 sub + 2 additions of the step; t1 = the ray's next sample
+        const float t1 = fadd(tcur, step);
+        float ta = t1, tb = t1;
+        {
+            float tk = t1;
+#pragma unroll
+            for (int i = 1; i < kGrpSamples; ++i) {
+                tk = fadd(tk, step);
+                if (i == 2 * sub) ta = tk;
+                if (i == 2 * sub + 1) tb = tk;
+            }
+            if (sub == 0) ta = t1;
+        }
+        Samp qa, qb;
+        qa.in = qb.in = false; qa.vx = qa.vy = qa.vz = qb.vx = qb.vy = qb.vz = 0.0f;
+        bool ready = false;
+        int j = 0;
+        const uint32_t* tab = bits;
+        bool have_a = false, have_b = false;
+        if (!done) {
+            if (!(t1 <= c.tmax)) done = true;
+            else {
+                have_a = ta <= c.tmax; have_b = tb <= c.tmax;
+                if (have_a) samp_pos(qa, ta, c, div_s, V);
+                if (have_b) samp_pos(qb, tb, c, div_s, V);
+                // a ray that carries exactly +1 passes all-(+1) slabs unchanged; one that carries 0 at the half-voxel step
+                // passes all-0 slabs unchanged (|0| < 0.8 keeps the step, no sign change, f stays 0)
+                const bool one = f == 1.0f, zero = f == 0.0f && step == c.half_s;
+                if (sub == 0 && can && qa.in && (one || zero)) {
+                    const float va = axis == 0 ? qa.vx : (axis == 1 ? qa.vy : qa.vz);
+                    j = __float2int_rz(va) >> L;                 // (va >= 0: the sample is inside the march bounds)
+                    tab = one ? bits : bits + kCertWords;
+                    ready = (j >> 5) < kCertWords && ((tab[j >> 5] >> (j & 31)) & 1u);
+                }
+            }
+        }
+        ready = __shfl_sync(kFull, (int)ready, gl0) != 0;
+        if (__all_sync(kFull, done)) break;
+        if (__all_sync(kFull, done || ready)) {
+            // ---- skip phase: every ray still marching stands before a run of certified slabs
+            j = __shfl_sync(kFull, j, gl0);
+            if (!done) {
+                tab = (f == 1.0f) ? bits : bits + kCertWords;
+                int k = j >> 5;
+                const uint32_t w = tab[k];
+                float bound;
+                if (fwd) {
+                    uint32_t inv = ~w & (0xffffffffu << (j & 31));
+                    while (inv == 0u && k + 1 < kCertWords) { ++k; inv = ~tab[k]; }
+                    const int je = inv ? 32 * k + __ffs(inv) - 1 : kCertSlabs;      // first slab that is not certified
+                    bound = (float)(je << L);                                        // samples with va < bound are no-ops
+                } else {
+                    uint32_t inv = ~w & (0xffffffffu >> (31 - (j & 31)));
+                    while (inv == 0u && k > 0) { --k; inv = ~tab[k]; }
+                    const int je = inv ? 32 * k + 31 - __clz(inv) : -1;             // last slab (below) that is not certified
+                    bound = (float)((je + 1) << L);                                  // samples with va >= bound are no-ops
+                }
+                // ray parameter at which the ray leaves the run (plain arithmetic: an estimate, verified below)
+                const float t_end = fminf(((bound - h_a) * c.s - o_a) * inv_da, c.tmax);
+                const float nf = __fdividef(t_end - t1, step);
+                const int n = (nf < 1.0e6f ? (int)nf : 1000000);                     // samples, t1 included, up to the end of the run (estimate)
+                int made = 1;
+                float t2 = t1;
+                if (n >= 2) {
+                    t2 = cert_hop(tcur, step, n, made);          // (one short of the estimate: the last sample before the bound is taken next)
+                    Samp b;
+                    samp_pos(b, t2, c, div_s, V);
+                    const float vb = axis == 0 ? b.vx : (axis == 1 ? b.vy : b.vz);
+                    if (!(t2 <= c.tmax && b.in && (fwd ? vb < bound : vb >= bound))) { t2 = t1; made = 1; }   // (the estimate is conservative: rare)
+                }
+                if (STATS && sub == 0) { ++st[2]; st[1] += made; }
+                tcur = t2;
+            }
+            continue;
+        }
+        // ---- sample phase (rays standing before a certified run wait)
+        const bool act = !done && !ready;
+        if (!act) { qa.in = false; qb.in = false; }
+        samp_load(qa, V, rx, plane);          // (predicated on .in, which is false for lanes that do not take part)
+        samp_load(qb, V, rx, plane);
+        float va = 0.0f, vb = 0.0f;
+        if (qa.in) va = samp_value(qa);
+        if (qb.in) vb = samp_value(qb);
+        float nsa = step, nsb = step;
+        if (fabsf(va) < 1.0f) nsa = c.s;
+        if (fabsf(va) < 0.8f) nsa = c.half_s;
+        if (fabsf(vb) < 1.0f) nsb = c.s;
+        if (fabsf(vb) < 0.8f) nsb = c.half_s;
+        float prev = __shfl_up_sync(kFull, vb, 1, kGrpLanes);
+        if (sub == 0) prev = f;
+        // a sign change against the predecessor is looked into right here, by its own lane, under the assumption that
+        // everything before it is accepted: along the shadow volume of an object nearly every sample is such a candidate
+        // and nearly none ends the ray (no weight there)
+        bool stop_a = !have_a || !qa.in || nsa != step;
+        if (!stop_a && ((prev < 0.0f && va > 0.0f) || (prev > 0.0f && va < 0.0f)))
+            stop_a = ray_event(V, prev, va, ta, step, qa.vx, qa.vy, qa.vz, c.dx, c.dy, c.dz).code != 0;
+        bool stop_b = stop_a || !have_b || !qb.in || nsb != step;
+        if (!stop_b && ((va < 0.0f && vb > 0.0f) || (va > 0.0f && vb < 0.0f)))
+            stop_b = ray_event(V, va, vb, tb, step, qb.vx, qb.vy, qb.vz, c.dx, c.dy, c.dz).code != 0;
+        const unsigned ma = (__ballot_sync(kFull, stop_a) >> gl0) & ((1u << kGrpLanes) - 1u);
+        const unsigned mb = (__ballot_sync(kFull, stop_b) >> gl0) & ((1u << kGrpLanes) - 1u);
+        const int first = min(ma ? 2 * (__ffs(ma) - 1) : kGrpSamples, mb ? 2 * (__ffs(mb) - 1) + 1 : kGrpSamples);   // index of the stop sample
+        // the samples before the stop: f = fn each, nothing else
+        {
+            const int a = max(first - 1, 0);
+            const float t_acc = __shfl_sync(kFull, (a & 1) ? tb : ta, gl0 + (a >> 1));
+            const float f_acc = __shfl_sync(kFull, (a & 1) ? vb : va, gl0 + (a >> 1));
+            if (act && first > 0) { tcur = t_acc; f = f_acc; if (STATS && sub == 0) st[0] += first; }
+        }
+        // the stop sample, by the sequential rule
+        {
+            const int sidx = min(first, kGrpSamples - 1), sl = gl0 + (sidx >> 1);
+            const bool sb = (sidx & 1) != 0;
+            const float tS = __shfl_sync(kFull, sb ? tb : ta, sl), vS = __shfl_sync(kFull, sb ? vb : va, sl);
+            const float sx = __shfl_sync(kFull, sb ? qb.vx : qa.vx, sl), sy = __shfl_sync(kFull, sb ? qb.vy : qa.vy, sl),
+                        sz = __shfl_sync(kFull, sb ? qb.vz : qa.vz, sl);
+            const int fl = __shfl_sync(kFull, (int)(sb ? have_b : have_a) | ((int)(sb ? qb.in : qa.in) << 1), sl);
+            if (act && first < kGrpSamples) {
+                if (!(fl & 1)) {
+                    done = true;                         // t > t_max: the ray ends without a hit
+                } else {
+                    tcur = tS;
+                    if (fl & 2) {
+                        if (STATS && sub == 0) { ++st[0]; if (f == 1.0f && vS == 1.0f) ++st[6]; }
+                        if (fabsf(vS) < 1.0f) step = c.s;
+                        if (fabsf(vS) < 0.8f) step = c.half_s;
+                        if ((f < 0.0f && vS > 0.0f) || (f > 0.0f && vS < 0.0f)) {
+                            if (STATS && sub == 0 && f < 0.0f) ++st[3];
+                            const RayEvent e = ray_event(V, f, vS, tcur, step, sx, sy, sz, c.dx, c.dy, c.dz);
+                            if (e.code == 3) {
+                                if (sub == 0) ray_emit_hit(V, x, y, e.ts, e.sx, e.sy, e.sz, c.dx, c.dy, c.dz, nullptr, P.w);
+                                hit = true;
+                            }
+                            if (e.code == 1 || e.code == 3) done = true;
+                            else if (e.code == 0) f = vS;
+                        } else {
+                            f = vS;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (valid && !hit && sub == 0) {
+        *((float*)((char*)V.ray + (size_t)y * V.ray_pitch) + x) = 0.0f;
+        V.mask[(size_t)y * V.mask_pitch + x] = 0;
+    }
+    if (STATS && P.stats) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (st[k]) atomicAdd(P.stats + k, st[k]);
+        if (P.hist && lane == 0) {
+            atomicAdd(P.stats + 8 + min(15ull, st[4] / 32ull), 1ull);
+            atomicMax(P.stats + 24, st[4]);
+        }
+        if (P.hist == 2 && lane == 0) {   // timeline: 4 words per warp after the 32 counters
+            unsigned smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            unsigned long long* rec = P.stats + 32 + 4 * ((size_t)blockIdx.x * (kRayThreads / 32) + warp);
+            rec[0] = t_begin; rec[1] = global_ns(); rec[2] = st[4]; rec[3] = ((unsigned long long)smid << 32);
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_ray_certify: the ray-space certificate of k_raycast_cert.
+// One thread per (8 x 4 pixel tile, slab); the lanes of a warp are 32 consecutive tiles of one slab (neighbouring tiles
+// read neighbouring voxels of the same rows), the ballot of their verdicts is one word of the bit table.
+// The box of a (tile, slab): the slab's planes along the dominant axis (a sample whose base voxel is in the slab has its
+// corners in planes [j 2^L, (j + 1) 2^L]), and across it the bounding box of the tile's four corner rays between the two
+// faces of the slab (the position on a ray at a given coordinate along the axis is a linear-fractional function of the
+// pixel: over a pixel rectangle its extremes are at the corners; along the slab it is linear), widened by margins a
+// hundred times the rounding error of the sampler's own arithmetic.  Every voxel of the box must hold exactly +1.
+// ---------------------------------------------------------------------------------------------
+struct CertParams {
+    const float* tsdf;
+    int rx, ry, rz;
+    float R[9], t[3];
+    float fx, fy, cx, cy, voxel;
+    int x0, y0, x1, y1;
+    int txc, n_tiles, G;
+    int axis, sgn, L, n_slabs;
+    uint32_t* table;
+};
+constexpr int kCertWarps = 8;        // warps per CTA
+constexpr int kCertPerWarp = 4;      // consecutive slabs a warp certifies for its 32 tiles (the per-tile set-up is shared)
+
+__global__ void __launch_bounds__(32 * kCertWarps) k_ray_certify(const __grid_constant__ CertParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x, j0 = (blockIdx.y * kCertWarps + warp) * kCertPerWarp;
+    const int ti = g * 32 + lane;
+    const int a = P.axis, b = a == 2 ? 0 : a + 1, c = a == 0 ? 2 : (a == 1 ? 0 : 1);   // (a, b, c) = (0,1,2), (1,2,0), (2,0,1)
+    const int ra = a == 0 ? P.rx : (a == 1 ? P.ry : P.rz);
+    const int rb = b == 0 ? P.rx : (b == 1 ? P.ry : P.rz);
+    const int rc = c == 0 ? P.rx : (c == 1 ? P.ry : P.rz);
+    // ---- per tile: position across the axis as a function of the coordinate along it, for the four corner rays:
+    //      v_b = ib + v_a * mb, v_c = ic + v_a * mc (voxel coordinates)
+    bool tile_ok = ti < P.n_tiles;
+    float mb[4], mc[4], ib[4], ic[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mb[q] = mc[q] = ib[q] = ic[q] = 0.0f;
+    const float inv_s = 1.0f / P.voxel;
+    const float cam_a = 0.5f * (float)(ra - 1) + P.t[a] * inv_s;       // the camera centre along the axis
+    if (tile_ok) {
+        const int wy = ti / P.txc, wx = ti - wy * P.txc;
+        const int X0 = P.x0 + 8 * wx, Y0 = P.y0 + 4 * wy;
+        tile_ok = X0 < P.x1 && Y0 < P.y1;
+        if (tile_ok) {
+            const int X1 = min(X0 + 7, P.x1 - 1), Y1 = min(Y0 + 3, P.y1 - 1);
+            const float cam_b = 0.5f * (float)(rb - 1) + P.t[b] * inv_s, cam_c = 0.5f * (float)(rc - 1) + P.t[c] * inv_s;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float ux = ((float)((q & 1) ? X1 : X0) - P.cx) / P.fx, uy = ((float)((q & 2) ? Y1 : Y0) - P.cy) / P.fy;
+                const float Da = P.R[3 * a] * ux + P.R[3 * a + 1] * uy + P.R[3 * a + 2];
+                const float Db = P.R[3 * b] * ux + P.R[3 * b + 1] * uy + P.R[3 * b + 2];
+                const float Dc = P.R[3 * c] * ux + P.R[3 * c + 1] * uy + P.R[3 * c + 2];
+                if (!((float)P.sgn * Da > 0.05f * sqrtf(Da * Da + Db * Db + Dc * Dc))) tile_ok = false;
+                mb[q] = Db / Da; mc[q] = Dc / Da;
+                ib[q] = cam_b - cam_a * mb[q]; ic[q] = cam_c - cam_a * mc[q];
+            }
+        }
+    }
+    const uint32_t* __restrict__ vol = reinterpret_cast<const uint32_t*>(P.tsdf);
+    const size_t sy = (size_t)P.rx, sz = (size_t)P.rx * P.ry;
+#pragma unroll 1
+    for (int s = 0; s < kCertPerWarp; ++s) {
+        const int j = j0 + s;
+        if (j >= P.n_slabs) break;                                   // (warp-uniform)
+        const int a0 = j << P.L, a1 = min((j + 1) << P.L, ra - 1);   // planes along the axis that corners of the slab's samples lie in
+        bool ok = tile_ok && a0 <= ra - 1;
+        // the slab is cut off at the camera centre (no sample lies behind it)
+        if (P.sgn > 0) ok = ok && (float)((j + 1) << P.L) + 0.02f > cam_a;
+        else ok = ok && (float)a0 - 0.02f < cam_a;
+        uint32_t acc = 0u, acz = 0u;         // some voxel is not +1 / not (+-)0
+#pragma unroll 1
+        for (int pl = a0; pl <= a1 && ok && (acc == 0u || acz == 0u); ++pl) {
+            // samples with a corner in plane pl have their base in {pl - 1, pl}: coordinate along the axis in [pl - 1, pl + 1),
+            // inside the slab, widened
+            float c0 = (float)max(pl - 1, a0) - 0.02f, c1 = (float)min(pl + 1, (j + 1) << P.L) + 0.02f;
+            if (P.sgn > 0) { c0 = fmaxf(c0, cam_a); c1 = fmaxf(c1, cam_a); }
+            else { c0 = fminf(c0, cam_a); c1 = fminf(c1, cam_a); }
+            float mnb = INFINITY, mxb = -INFINITY, mnc = INFINITY, mxc = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float b0 = fmaf(c0, mb[q], ib[q]), b1 = fmaf(c1, mb[q], ib[q]);
+                const float e0 = fmaf(c0, mc[q], ic[q]), e1 = fmaf(c1, mc[q], ic[q]);
+                mnb = fminf(mnb, fminf(b0, b1)); mxb = fmaxf(mxb, fmaxf(b0, b1));
+                mnc = fminf(mnc, fminf(e0, e1)); mxc = fmaxf(mxc, fmaxf(e0, e1));
+            }
+            if (!(fabsf(mnb) < 1.0e6f && fabsf(mxb) < 1.0e6f && fabsf(mnc) < 1.0e6f && fabsf(mxc) < 1.0e6f)) { ok = false; break; }   // (or NaN)
+            const int blo = max((int)floorf(mnb - 0.05f), 0), bhi = min((int)floorf(mxb + 0.05f) + 1, rb - 1);
+            const int clo = max((int)floorf(mnc - 0.05f), 0), chi = min((int)floorf(mxc + 0.05f) + 1, rc - 1);
+            // (a rectangle wholly outside the volume belongs to samples outside the march bounds: never consulted)
+            if (blo > bhi || clo > chi || (bhi - blo + 1) * (chi - clo + 1) > 400) { ok = false; break; }
+            // rectangle in (x, y, z)
+            const int xlo = a == 0 ? pl : (b == 0 ? blo : clo), xhi = a == 0 ? pl : (b == 0 ? bhi : chi);
+            const int ylo = a == 1 ? pl : (b == 1 ? blo : clo), yhi = a == 1 ? pl : (b == 1 ? bhi : chi);
+            const int zlo = a == 2 ? pl : (b == 2 ? blo : clo), zhi = a == 2 ? pl : (b == 2 ? bhi : chi);
+            const int nx = xhi - xlo;
+            for (int z = zlo; z <= zhi; ++z) {
+                const uint32_t* row = vol + (size_t)z * sz + (size_t)ylo * sy + xlo;
+                for (int y = ylo; y <= yhi; ++y, row += sy) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (i <= nx) { const uint32_t v = __ldg(row + i); acc |= v ^ 0x3f800000u; acz |= v << 1; }
+                    for (int i = 8; i <= nx; ++i) { const uint32_t v = __ldg(row + i); acc |= v ^ 0x3f800000u; acz |= v << 1; }
+                }
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, ok && acc == 0u);
+        const uint32_t wordz = __ballot_sync(0xffffffffu, ok && acz == 0u);
+        if (lane == 0) {
+            P.table[(size_t)j * P.G + g] = word;
+            P.table[(size_t)(kCertSlabs + j) * P.G + g] = wordz;
+        }
+    }
+}
+
+static int cert_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EMF_RAY_CERT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+static size_t cert_table_bytes(int tiles_x, int tiles_y) {   // CTA tiles of the raycast (kTileW x kTileH pixels)
+    const int n_tiles = 4 * tiles_x * tiles_y;
+    return (size_t)2 * kCertSlabs * ((n_tiles + 31) / 32) * sizeof(uint32_t);      // all-(+1) table, all-0 table
+}
+
+// certify volume d (rays as fill_ray_vol prepared them) into the workspace and point the raycast at it; false = not applicable
+static bool launch_certify(RayVol& d, const float* K, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!cert_enabled() || !workspace || d.fg_probs || d.bmap || d.tube) return false;
+    if (d.x1 <= d.x0 || d.y1 <= d.y0) return false;
+    if (!(K[0] != 0.0f && K[4] != 0.0f)) return false;
+    const int tiles_y = (d.y1 - d.y0 + kTileH - 1) / kTileH;
+    if (cert_table_bytes(d.tiles_x, tiles_y) > workspace_bytes) return false;
+    uint32_t* table = (uint32_t*)workspace;
+    CertParams C;
+    C.tsdf = d.tsdf; C.rx = d.rx; C.ry = d.ry; C.rz = d.rz;
+    for (int k = 0; k < 9; ++k) C.R[k] = d.R[k];
+    for (int k = 0; k < 3; ++k) C.t[k] = d.t[k];
+    C.fx = K[0]; C.fy = K[4]; C.cx = K[2]; C.cy = K[5]; C.voxel = d.voxel;
+    C.x0 = d.x0; C.y0 = d.y0; C.x1 = d.x1; C.y1 = d.y1;
+    C.txc = 2 * d.tiles_x; C.n_tiles = 4 * d.tiles_x * tiles_y; C.G = (C.n_tiles + 31) / 32;
+    // the volume axis the optical axis (third column of rot_CO) is closest to
+    int axis = 0;
+    for (int k = 1; k < 3; ++k) if (fabsf(d.R[3 * k + 2]) > fabsf(d.R[3 * axis + 2])) axis = k;
+    C.axis = axis; C.sgn = d.R[3 * axis + 2] > 0.0f ? 1 : -1;
+    const int ra = axis == 0 ? d.rx : (axis == 1 ? d.ry : d.rz);
+    int L = EMF_CERT_L;
+    while ((kCertSlabs << L) < ra) ++L;
+    C.L = L;
+    const int n_slabs = min(kCertSlabs, (((ra + (1 << L) - 1) >> L) + 31) & ~31);     // whole words of slab bits
+    C.n_slabs = n_slabs;
+    C.table = table;
+    const int per_cta = kCertWarps * kCertPerWarp;
+    k_ray_certify<<<dim3((unsigned)C.G, (unsigned)((n_slabs + per_cta - 1) / per_cta)), 32 * kCertWarps, 0, stream>>>(C);
+    d.tiles_y = tiles_y;
+    d.cert = table; d.cert_G = C.G; d.cert_txc = C.txc; d.cert_axis = axis; d.cert_sign = C.sgn; d.cert_L = L;
+    d.cert_nw = n_slabs / 32;
+    return true;
 }
 
 // smallest float v with fl(v + pad) >= R: `v + pad >= R` (reference bounds tests, TSDF.cu:510,526,547) <=> v >= threshold,
@@ -627,6 +1227,8 @@ static int fill_ray_vol(RayVol& d, const emf_volume& v, const emf_pose& T, const
 #else
     d.tube = 0;
 #endif
+    d.tiles_y = 0;
+    d.cert = nullptr; d.cert_G = 0; d.cert_txc = 0; d.cert_axis = 2; d.cert_sign = 1; d.cert_L = 1; d.cert_nw = 0;
     return EMF_OK;
 }
 
@@ -836,41 +1438,80 @@ extern "C" EMF_API int emf_raycast_tsdf(const float* tsdf, const float* grads, c
     P.v[0].first_block = 0;
     P.n_vol = 1; P.w = w; P.h = h;
     for (int k = 0; k < 9; ++k) P.K[k] = K[k];
-    P.hit_voxel = hit_voxel; P.write_all = 0; P.stats = nullptr;
+    P.hit_voxel = hit_voxel; P.write_all = 0; P.stats = nullptr; P.hist = 0;
     const int blocks = P.v[0].tiles_x * ((h + kTileH - 1) / kTileH);
-    k_raycast<false, false><<<blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
+    k_raycast<false, 0><<<blocks, kRayThreads, 0, (cudaStream_t)stream>>>(P);
     return launch_status();
+}
+
+extern "C" EMF_API size_t emf_raycast_workspace_bytes(int width, int height) {
+    if (width <= 0 || height <= 0) return 0;
+    return cert_table_bytes((width + kTileW - 1) / kTileW, (height + kTileH - 1) / kTileH) + 256;
 }
 
 extern "C" EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
                                    const int* rects, const emf_image* ray_out, const emf_image* vert_out,
                                    const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
                                    emf_stream_t stream) {
+    return emf_raycast_volumes_ws(n_vol, vols, T_co, K, rects, ray_out, vert_out, norm_out, mask_out, stats, nullptr, 0, stream);
+}
+
+extern "C" EMF_API int emf_raycast_volumes_ws(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
+                                      const int* rects, const emf_image* ray_out, const emf_image* vert_out,
+                                      const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
+                                      void* workspace, size_t workspace_bytes, emf_stream_t stream) {
     if (n_vol <= 0 || !vols || !T_co || !K || !ray_out || !vert_out || !norm_out || !mask_out) return EMF_ERR_INVALID;
     if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
-    RayParams P;
+    static RayParams P;          // (tens of kilobytes: not on the stack; the ABI is single-threaded per process like the reference)
     const int w = ray_out[0].width, h = ray_out[0].height;
-    int64_t blocks = 0;
     for (int i = 0; i < n_vol; ++i) {
         const int rc = fill_ray_vol(P.v[i], vols[i], T_co[i], &ray_out[i], &vert_out[i], &norm_out[i], &mask_out[i],
                                     rects ? rects + 4 * i : nullptr, w, h);
         if (rc != EMF_OK) return rc;
-        P.v[i].first_block = (int)blocks;
-        blocks += (int64_t)P.v[i].tiles_x * ((P.v[i].y1 - P.v[i].y0 + kTileH - 1) / kTileH);
     }
-    if (blocks == 0) return EMF_OK;
-    P.n_vol = n_vol; P.w = w; P.h = h;
+    P.w = w; P.h = h;
     for (int k = 0; k < 9; ++k) P.K[k] = K[k];
     P.hit_voxel = nullptr; P.write_all = 1; P.stats = (unsigned long long*)stats;
+    { const char* e = getenv("EMF_RAY_HIST"); P.hist = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0); }
     bool jump = false;
     for (int i = 0; i < n_vol; ++i) jump = jump || P.v[i].bmap != nullptr;
     const cudaStream_t cs = (cudaStream_t)stream;
-    if (jump) {
-        if (stats) k_raycast<true, true><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
-        else k_raycast<false, true><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
-    } else {
-        if (stats) k_raycast<true, false><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
-        else k_raycast<false, false><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+    int n_rest = n_vol;
+    if (!jump && workspace && ((uintptr_t)workspace & 15) == 0) {
+        // ray-space certificate for the first volume without a foreground mask (the background: long rays through free
+        // space); that volume gets its own launch of the certified march, the others follow in the plain one
+        for (int i = 0; i < n_vol; ++i) {
+            if (P.v[i].fg_probs) continue;
+            if (launch_certify(P.v[i], K, workspace, workspace_bytes, cs)) {
+                static CertRayParams Pc;
+                Pc.v = P.v[i];
+                Pc.v.first_block = 0;
+                Pc.w = w; Pc.h = h;
+                for (int k = 0; k < 9; ++k) Pc.K[k] = K[k];
+                Pc.stats = P.stats; Pc.hist = P.hist;
+                const unsigned cb = (unsigned)(4 * Pc.v.tiles_x * Pc.v.tiles_y);      // one CTA per 8 x 4 pixel tile
+                if (stats) k_raycast_cert<true><<<cb, kRayThreads, 0, cs>>>(Pc);
+                else k_raycast_cert<false><<<cb, kRayThreads, 0, cs>>>(Pc);
+                for (int k = i; k + 1 < n_vol; ++k) P.v[k] = P.v[k + 1];
+                --n_rest;
+            }
+            break;
+        }
+    }
+    int64_t blocks = 0;
+    for (int i = 0; i < n_rest; ++i) {
+        P.v[i].first_block = (int)blocks;
+        blocks += (int64_t)P.v[i].tiles_x * ((P.v[i].y1 - P.v[i].y0 + kTileH - 1) / kTileH);
+    }
+    P.n_vol = n_rest;
+    if (blocks > 0) {
+        if (jump) {
+            if (stats) k_raycast<true, 2><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+            else k_raycast<false, 2><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+        } else {
+            if (stats) k_raycast<true, 0><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+            else k_raycast<false, 0><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
+        }
     }
     return launch_status();
 }

@@ -11,6 +11,7 @@ of the per-rank pre-composited raycast to rank 0 -- both through torch.distribut
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -152,7 +153,8 @@ class NativeEngine(EMFusionEngine):
         if flags & F_POINTS: launches += 1
         if flags & (F_ASSOC | F_ASSOC_PARTIAL | F_ASSOC_PARTIAL_NOBG) and n: launches += 1
         if flags & F_NORMALISE and n: launches += 1
-        if flags & F_RAYCAST and n: launches += 1
+        if flags & F_RAYCAST and n:   # (+ k_ray_certify and k_raycast_cert when the opt-in ray-space certificate is on)
+            launches += 3 if (os.environ.get("EMF_RAY_CERT") == "1" and self.background is not None and n > 1) else (2 if os.environ.get("EMF_RAY_CERT") == "1" and self.background is not None else 1)
         if flags & (F_COMPOSITE | F_COMPOSITE_NOBG): launches += 1
         if flags & F_INTEGRATE and n: launches += 2 + (2 if any(v.constBits is not None for v in vols) else 0)   # pyramid + integrate
         ops.LAUNCHES["engineFrame"] = ops.LAUNCHES.get("engineFrame", 0) + launches

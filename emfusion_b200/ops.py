@@ -26,8 +26,8 @@ _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1,
                      "resizeVolume": 1, "preprocessDepth": 1, "trackIterate": 2}
 
 
-def _count(name: str) -> None:
-    LAUNCHES[name] = LAUNCHES.get(name, 0) + _KERNELS_PER_CALL[name]
+def _count(name: str, kernels: Optional[int] = None) -> None:
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + (_KERNELS_PER_CALL[name] if kernels is None else kernels)
 
 
 def launches_total() -> int:
@@ -208,14 +208,23 @@ def volumeScreenRect(volumeRes, voxelSize, rel_pose_CO: Affine, intr, width, hei
     return list(out)
 
 
-def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out, mask_out, stream=None, stats=None):
-    if stats is not None and (stats.numel() < 4 or stats.element_size() != 8):
-        raise _lib.EmfError("raycast stats must be a tensor of at least 4 64-bit counters")
+def raycastWorkspace(width, height, device):
+    """device scratch for raycastVolumes(workspace=...): the ray-space certificate table (csrc/raycast.cu, k_ray_certify)"""
+    n = int(_lib.lib().emf_raycast_workspace_bytes(int(width), int(height)))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out, mask_out, stream=None, stats=None,
+                   workspace=None):
+    """workspace (raycastWorkspace): lets the background's rays skip certified free-space samples (same results)."""
+    if stats is not None and (stats.numel() < 8 or stats.element_size() != 8):
+        raise _lib.EmfError("raycast stats must be a tensor of at least 8 64-bit counters")
     flat = (C.c_int * (4 * len(vols)))(*[int(v) for r in rects for v in r]) if rects is not None else None
-    check(_lib.lib().emf_raycast_volumes(len(vols), _vol_array(vols), poses(rel_poses_CO), _f9(intr), flat,
-                                         images(ray_out), images(vert_out), images(norm_out), images(mask_out),
-                                         _ptr(stats), _stream(stream)), "raycastVolumes")
-    _count("raycastVolumes")
+    check(_lib.lib().emf_raycast_volumes_ws(len(vols), _vol_array(vols), poses(rel_poses_CO), _f9(intr), flat,
+                                            images(ray_out), images(vert_out), images(norm_out), images(mask_out),
+                                            _ptr(stats), _ptr(workspace), workspace.numel() if workspace is not None else 0,
+                                            _stream(stream)), "raycastVolumes")
+    _count("raycastVolumes", 1 if workspace is None else 2)
 
 
 def raycastComposite(ids, rects, obj_ray, obj_vert, obj_norm, obj_mask, bg_ray, bg_vert, bg_norm, bg_mask, boundary,

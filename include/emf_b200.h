@@ -207,12 +207,25 @@ EMF_API int emf_assoc_normalise(int n_img, const emf_image* assoc_io, const emf_
  * mask_out[i] (u8), vert_out[i]/norm_out[i] (float3, hit pixels only).  rects (n_vol x 4 ints:
  * x0, y0, x1, y1, exclusive upper) bound the pixels each volume can cover; pixels outside a
  * volume's rect are not touched and must be treated as "no hit" by the consumer.
- * stats (optional, 4 x uint64 on the device, accumulated): TSDF samples taken, march samples skipped by jumps
- * through constant bricks, jumps, weight samples -- the raycast's roofline numerator. */
+ * stats (optional, 8 x uint64 on the device, accumulated): TSDF samples taken, march samples skipped by jumps
+ * (constant bricks / certified slabs), jumps, weight samples -- the raycast's roofline numerator --, then warp iterations
+ * of the march loop and the lanes active in them, for certified ([4], [5]) and plain ([6], [7]) rays. */
 EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
                         const int* rects, const emf_image* ray_out, const emf_image* vert_out,
                         const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
                         emf_stream_t stream);
+
+/* emf_raycast_volumes with a workspace of emf_raycast_workspace_bytes(W, H) bytes (device memory, 16-byte aligned,
+ * contents irrelevant).  With it, a pre-pass (k_ray_certify) certifies, per 8 x 4 pixel tile and per slab of voxels along
+ * the volume axis the camera looks along, that every voxel a march sample of the tile can touch there holds exactly +1;
+ * rays of the first volume without fg_probs (the background) then skip those samples -- no-ops of the reference's march
+ * loop, src/core/cuda/TSDF.cu:523-572 -- in closed form.  Same results, bit for bit (stats[1], [2] count what was skipped);
+ * the environment variable EMF_RAY_CERT=0 turns the pre-pass off for A/B measurements. */
+EMF_API int emf_raycast_volumes_ws(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
+                           const int* rects, const emf_image* ray_out, const emf_image* vert_out,
+                           const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
+                           void* workspace, size_t workspace_bytes, emf_stream_t stream);
+EMF_API size_t emf_raycast_workspace_bytes(int width, int height);
 
 /* Compositing of emf::EMFusion::raycast, src/core/EMFusion.cpp:760-794, in one launch.
  * Objects i = 0..n_obj-1 in list order with ids[i]; background images bg_*.
