@@ -31,6 +31,36 @@ def random_poses(n, seed):
     return out
 
 
+@pytest.mark.parametrize("res", [(64, 64, 64), (128, 40, 72), (96, 128, 64)], ids=["64", "128x40x72", "96x128x64"])
+def test_integrate_bricks_random_poses_bit_exact(oracle, cuda_dev, res):
+    """brick-level classification (k_brick_classify + k_integrate_bricks: no bitmaps => the brick path) vs the straight oracle
+    loop under random camera poses (rotated, inside the volume, looking away, grazing), accumulated over all poses; the
+    kernel's own counters agree with the oracle's"""
+    w, h = 320, 240
+    scene = Scene(n_objects=3, width=w, height=h, seed=7, dropout=0.03)
+    n = int(np.prod(res))
+    voxel = float(np.float32(5.12 / res[0]))
+    trunc = float(np.float32(10.0) * np.float32(voxel))
+    vol_pose = Affine.translation([0, 0, 2.56])
+    t_o, w_o = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    t_g, w_g = cu(t_o), cu(w_o)
+    rng = np.random.default_rng(1)
+    stats = torch.zeros(8, dtype=torch.int64, device=DEV)
+    tot = np.zeros(6, np.int64)
+    for k, cam in enumerate(random_poses(8, 3)):
+        depth, _ = scene.render(k)
+        assoc = rng.random((h, w), dtype=np.float32)
+        T = rel_pose_OC(cam, vol_pose)
+        tot += oracle.update_tsdf(depth, assoc, t_o, w_o, S.R9(T), S.T3(T), scene.K, res, voxel, trunc, 64.0, counts=True)
+        v = ops.volume(t_g, w_g, res, voxel, trunc)
+        ops.integrateVolumes([v], [T], scene.K, cu(depth), [cu(assoc)], 64.0, stats=stats)
+        assert_bits(t_g, t_o, f"tsdf after pose {k}")
+        assert_bits(w_g, w_o, f"weights after pose {k}")
+    st = stats.cpu().numpy()
+    assert st[0] == tot[0] and st[1] == tot[1] and st[2] == tot[2] and st[3] == tot[3], (st, tot)
+    assert st[6] + st[7] > 0        # segments were decided wholesale
+
+
 @pytest.mark.parametrize("res", [(64, 64, 64), (128, 40, 72)], ids=["64", "128x40x72"])
 def test_integrate_random_poses_bit_exact(oracle, cuda_dev, res):
     """frustum culling + approximate classification vs the straight oracle loop, accumulated over all poses"""
