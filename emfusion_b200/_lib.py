@@ -94,6 +94,8 @@ _SIGS = {
                                     C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p],
     "emf_integrate_volumes_ws": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(Image), _P(Image), C.c_float,
                                  C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    "emf_integrate_volumes_phase": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(Image), _P(Image), C.c_float,
+                                    C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p],
     "emf_update_brick_maps": [C.c_int, _P(Volume), C.c_void_p],
     "emf_reset_bitmaps": [_P(Volume), C.c_void_p],
     "emf_preprocess_depth": [_P(Image), _P(Image), _P(Image), _P(C.c_float), C.c_int, C.c_float, C.c_float, C.c_void_p],

@@ -42,6 +42,8 @@ struct emf_engine {
     cudaEvent_t vis_ready = nullptr;
     cudaStream_t aux = nullptr;        // the association runs here, next to the raycast (both only read the volumes)
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t aux2 = nullptr;       // the integrate's preparation (depth pyramid, brick classification)
+    cudaEvent_t fork2 = nullptr, join2 = nullptr;
     bool timed_valid = false;
 };
 
@@ -91,6 +93,9 @@ extern "C" EMF_API emf_engine* emf_engine_create(const emf_engine_config* cfg) {
     ok = ok && cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&e->aux2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->fork2, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->join2, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { emf_engine_destroy(e); return nullptr; }
     for (int k = 0; k < EMF_MAX_VOLUMES; ++k) e->vis_host[k] = 0;
     return e;
@@ -105,6 +110,9 @@ extern "C" EMF_API void emf_engine_destroy(emf_engine* e) {
     if (e->fork) cudaEventDestroy(e->fork);
     if (e->join) cudaEventDestroy(e->join);
     if (e->aux) cudaStreamDestroy(e->aux);
+    if (e->fork2) cudaEventDestroy(e->fork2);
+    if (e->join2) cudaEventDestroy(e->join2);
+    if (e->aux2) cudaStreamDestroy(e->aux2);
     delete e;
 }
 
@@ -112,7 +120,11 @@ extern "C" EMF_API int emf_engine_set_volumes(emf_engine* e, int n_vol, const em
                                       emf_stream_t stream) {
     if (!e || n_vol < 0 || (n_vol > 0 && !vols)) return EMF_ERR_INVALID;
     if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
-    const bool realloc = n_vol != e->n_vol || !e->pool;
+    bool same_ids = n_vol == e->n_vol && (has_background ? 1 : 0) == e->has_bg;
+    for (int i = 0; i < n_vol && same_ids; ++i) same_ids = vols[i].id == e->vols[i].id;
+    // (a list that changed at equal length -- one object removed, one created -- is re-matched by id like any other change)
+    const bool realloc = !same_ids || !e->pool;
+    const std::vector<char> old_force = e->force;
     // what the engine held so far: per-volume images survive a change of the volume list (matched by id)
     const std::vector<emf_volume> old_vols = e->vols;
     const int old_has_bg = e->has_bg;
@@ -128,6 +140,9 @@ extern "C" EMF_API int emf_engine_set_volumes(emf_engine* e, int n_vol, const em
         e->gates.push_back(bg ? -1 : (int)e->ids.size() - 1);
     }
     e->force.assign(n_vol, 0);
+    for (int i = 0; i < n_vol; ++i)       // pending force flags follow their volume
+        for (int k = 0; k < (int)old_vols.size() && k < (int)old_force.size(); ++k)
+            if (old_vols[k].id == vols[i].id && ((old_has_bg && k == 0) == (e->has_bg && i == 0))) { e->force[i] = old_force[k]; break; }
     e->rects.assign((size_t)4 * (n_vol > 0 ? n_vol : 1), 0);
     cudaStream_t s = (cudaStream_t)stream;
     if (realloc) {
@@ -181,6 +196,18 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         if (rc != EMF_OK) return rc;
     }
     if (timed) cudaEventRecord(e->ev[0], s);
+    // what the integrate needs from the depth image and the poses alone (depth pyramid, brick classification) runs on a side
+    // stream next to the association and the raycast
+    bool prepared = false;
+    if ((flags & EMF_FRAME_INTEGRATE) && (flags & EMF_FRAME_RAYCAST) && n > 0 && T_oc && emfb::image_ok(depth, 4) && !timed) {
+        cudaEventRecord(e->fork2, s);
+        cudaStreamWaitEvent(e->aux2, e->fork2, 0);
+        rc = emf_integrate_volumes_phase(n, e->vols.data(), T_oc, e->cfg.K, depth, e->a_img.data(), e->cfg.params.max_tsdf_weight,
+                                         nullptr, nullptr, 0, nullptr, e->int_ws, e->int_ws_bytes, 1, (emf_stream_t)e->aux2);
+        if (rc != EMF_OK) return rc;
+        cudaEventRecord(e->join2, e->aux2);
+        prepared = true;
+    }
     if ((flags & (EMF_FRAME_ASSOC | EMF_FRAME_ASSOC_PARTIAL | EMF_FRAME_ASSOC_PARTIAL_NOBG)) && n > 0) {
         if (!T_co) return EMF_ERR_INVALID;
         const int mode = (flags & EMF_FRAME_ASSOC_PARTIAL_NOBG) ? (e->has_bg ? 3 : 1) : ((flags & EMF_FRAME_ASSOC_PARTIAL) ? 1 : 0);
@@ -226,9 +253,9 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         if (rc != EMF_OK) return rc;
     }
     if (flags & (EMF_FRAME_COMPOSITE | EMF_FRAME_COMPOSITE_NOBG)) {
-        // visibility is re-derived by every raycast (vis_objs.clear(), reference src/core/EMFusion.cpp:745): objects
-        // created before it are gated like all others; only objects created after it (:550) are integrated unseen
-        std::fill(e->force.begin(), e->force.end(), (char)0);
+        // (force flags -- objects created since the last integrate, reference src/core/EMFusion.cpp:550,918: createObj puts
+        //  them into vis_objs after the raycast -- stay set until an integrate consumes them: a frame driven through one
+        //  emf_engine_frame call creates its objects before the raycast, and the composite must not drop them)
         const int o0 = e->has_bg ? 1 : 0, n_obj = n - o0;
         const bool with_bg = e->has_bg && !(flags & EMF_FRAME_COMPOSITE_NOBG);
         const emf_image* bg_ray = with_bg ? &e->v_ray[0] : &e->zero_f;
@@ -252,9 +279,10 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         const bool gate = (flags & EMF_FRAME_INTEGRATE_ALL) == 0;
         std::vector<int> g(e->gates);
         for (int i = 0; i < n; ++i) if (e->force[i]) { g[i] = -1; e->force[i] = 0; }
-        rc = emf_integrate_volumes_ws(n, e->vols.data(), T_oc, e->cfg.K, depth, assoc, e->cfg.params.max_tsdf_weight,
-                                      gate ? e->vis_count : nullptr, gate ? g.data() : nullptr,
-                                      e->cfg.visibility_thresh, nullptr, e->int_ws, e->int_ws_bytes, stream);
+        if (prepared) cudaStreamWaitEvent(s, e->join2, 0);
+        rc = emf_integrate_volumes_phase(n, e->vols.data(), T_oc, e->cfg.K, depth, assoc, e->cfg.params.max_tsdf_weight,
+                                         gate ? e->vis_count : nullptr, gate ? g.data() : nullptr,
+                                         e->cfg.visibility_thresh, nullptr, e->int_ws, e->int_ws_bytes, prepared ? 2 : 0, stream);
         if (rc != EMF_OK) return rc;
         rc = emf_update_brick_maps(n, e->vols.data(), stream);
         if (rc != EMF_OK) return rc;

@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(kClassifyThreads) k_brick_classify(const __gri
             if (P.v[mid].first_brick <= gb) lo = mid; else hi = mid - 1;
         }
         const IntVol& V = P.v[lo];
-        const bool gated_out = V.gate >= 0 && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh);   // not visible: not integrated
+        const bool gated_out = V.gate >= 0 && P.gate_counts && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh);   // not visible: not integrated
         if (!gated_out) {
             const int b = gb - V.first_brick;
             const int bz = b / (V.nbx * V.nby), brem = b - bz * V.nbx * V.nby;
@@ -907,6 +907,7 @@ __global__ void __launch_bounds__(kBrickThreads, 4) k_integrate_bricks(const __g
         const uint2 item = i < n_m ? __ldg(P.list_mixed + i) : __ldg(P.list_whole + (i - n_m));
         const int cls = (int)((item.y >> (3 * (seg >> 1))) & 7u);      // class of this lane's sub-brick
         const IntVol& V = P.v[(item.x >> kBrickVolShift) & 127u];
+        if (V.gate >= 0 && P.gate_counts && !(__ldg(P.gate_counts + V.gate) > P.gate_thresh)) continue;   // (classified before the gate was known)
         const int b = (int)(item.x & ((1u << kBrickVolShift) - 1u));
         const int rx = V.rx, ry = V.ry;
         const int bz = b / (V.nbx * V.nby), brem = b - bz * V.nbx * V.nby;
@@ -1271,7 +1272,9 @@ size_t pyramid_layout(int w, int h, size_t off[kPyrLevels + 1], int lw[kPyrLevel
 int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float* K, const emf_image* depth,
                      const emf_image* assoc, float max_weight, const int32_t* gate_counts, const int* gates,
                      int gate_thresh, unsigned long long* stats, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int phase = 0) {
+    // phase 0: everything; 1: only what depends on the depth image and the poses alone (depth pyramid, brick classification
+    // of EVERY volume: the visibility gate is applied by the integrate kernel) -- can run next to the raycast; 2: the rest
     if (n_vol <= 0 || !vols || !T_oc || !K || !assoc) return EMF_ERR_INVALID;
     if (n_vol > EMF_MAX_VOLUMES) return EMF_ERR_UNSUPPORTED;
     if (!image_ok(depth, 4)) return EMF_ERR_INVALID;
@@ -1316,6 +1319,7 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
     P.g_rel = pin ? 1.25f * 0.25f * (1.0f / fabsf(K[0]) + 1.0f / fabsf(K[4])) + 4.0e-6f : INFINITY;
     P.g_abs = 1.0e-4f;
     if (!rows_ok) {
+        if (phase == 1) return EMF_OK;
         if (pin) k_integrate_simple<true><<<(unsigned)items, kSimpleThreads, 0, stream>>>(P);
         else k_integrate_simple<false><<<(unsigned)items, kSimpleThreads, 0, stream>>>(P);
         return launch_status();
@@ -1356,13 +1360,18 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
             P.inv_lambda = Q.inv_lambda;
             Q.fx = K[0]; Q.fy = K[4]; Q.cx = K[2]; Q.cy = K[5];
             const dim3 pgrid((P.w + 63) / 64, (P.h + 63) / 64);
-            k_depth_pyramid<<<pgrid, 256, 0, stream>>>(Q);
+            if (phase != 2) k_depth_pyramid<<<pgrid, 256, 0, stream>>>(Q);
             if (bricks_ok) {
                 P.total_bricks = (int)n_bricks;
                 P.brick_counters = Q.brick_counters;
                 P.list_mixed = (uint2*)((char*)workspace + need + 256);
                 P.list_whole = P.list_mixed + list_cap;
-                k_brick_classify<<<(unsigned)((n_bricks + kClassifyThreads - 1) / kClassifyThreads), kClassifyThreads, 0, stream>>>(P);
+                if (phase != 2) {
+                    IntParams C = P;
+                    if (phase == 1) C.gate_counts = nullptr;      // classify everything: the gate is not known yet
+                    k_brick_classify<<<(unsigned)((n_bricks + kClassifyThreads - 1) / kClassifyThreads), kClassifyThreads, 0, stream>>>(C);
+                }
+                if (phase == 1) return launch_status();
                 static int bocc_s = 0, bocc_n = 0;
                 int& bocc = stats ? bocc_s : bocc_n;
                 if (bocc == 0) {
@@ -1375,6 +1384,7 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
                 else k_integrate_bricks<false><<<bblocks, kBrickThreads, 0, stream>>>(P);
                 return launch_status();
             }
+            if (phase == 1) return launch_status();
             static int occ_s = 0, occ_n = 0;
             int& occ = stats ? occ_s : occ_n;
             if (occ == 0) {
@@ -1390,6 +1400,7 @@ int launch_integrate(int n_vol, const emf_volume* vols, const emf_pose* T_oc, co
             return launch_status();
         }
     }
+    if (phase == 1) return EMF_OK;
     for (int l = 0; l <= kPyrLevels; ++l) { P.pyr[l] = nullptr; P.pyr_w[l] = 0; }
     P.work_counter = nullptr; P.inv_lambda = nullptr;
     const dim3 block(kIntThreads);
@@ -1445,6 +1456,15 @@ extern "C" EMF_API int emf_integrate_volumes_ws(int n_vol, const emf_volume* vol
                                         void* workspace, size_t workspace_bytes, emf_stream_t stream) {
     return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, gate_counts, gates, gate_thresh,
                                   (unsigned long long*)stats, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" EMF_API int emf_integrate_volumes_phase(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
+                                           const emf_image* depth, const emf_image* assoc, float max_weight,
+                                           const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,
+                                           void* workspace, size_t workspace_bytes, int phase, emf_stream_t stream) {
+    if (phase < 0 || phase > 2) return EMF_ERR_INVALID;
+    return emfb::launch_integrate(n_vol, vols, T_oc, K, depth, assoc, max_weight, gate_counts, gates, gate_thresh,
+                                  (unsigned long long*)stats, workspace, workspace_bytes, (cudaStream_t)stream, phase);
 }
 
 extern "C" EMF_API int emf_update_tsdf(const emf_image* depth, const emf_image* assoc_weights, float* tsdf, float* weights,

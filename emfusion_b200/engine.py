@@ -61,6 +61,7 @@ class EMFusionEngine:
         self.obj_raylengths, self.obj_vertices, self.obj_normals, self.obj_modelSegmentation = {}, {}, {}, {}
         self.vis_count = torch.zeros((EMFusionEngine.MAX_OBJ,), dtype=torch.int32, device=dev)
         self.vis_objs = set()
+        self._created = set()
         self._gather_bufs = None
 
     MAX_OBJ = 96
@@ -91,6 +92,7 @@ class EMFusionEngine:
         self.obj_modelSegmentation[obj.id] = torch.zeros((h, w), dtype=torch.uint8, device=dev)
         self.associationWeights[obj.id] = torch.ones((h, w), dtype=torch.float32, device=dev)
         self.vis_objs.add(obj.id)
+        self._created.add(obj.id)     # integrated at the next integrateDepth whatever a raycast in between says (EMFusion.cpp:550,918)
         return obj
 
     def local_volumes(self) -> List[TSDF]:
@@ -168,92 +170,15 @@ class EMFusionEngine:
         for i, c in zip(ids, counts):
             if int(c) > self.params.visibilityThresh:
                 self.vis_objs.add(i)
+        self.vis_objs |= self._created
 
     def _raycast_composite_distributed(self, rects):
-        """Each rank pre-composites its own objects (list order is preserved inside a shard), the
-        per-rank results are gathered on rank 0 and merged there in (raylength, list-order) order --
-        which is what the reference's sequential 'strictly nearer or first in list wins' loop computes."""
-        import torch.distributed as dist
-        h, w, dev = self.h, self.w, self.device
-        objs = self.objects
-        o_rects = rects[1:] if self.background is not None else rects
-        # local pre-composite against an empty background
-        if self._gather_bufs is None:
-            z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)
-            self._gather_bufs = dict(ray=z(h, w), vert=z(h, w, 3), norm=z(h, w, 3), seg=z(h, w, dt=torch.uint8),
-                                     zray=z(h, w), zvert=z(h, w, 3), zmask=z(h, w, dt=torch.uint8),
-                                     win=z(h, w, dt=torch.int32))
-        g = self._gather_bufs
-        # per-rank winner: encode the LIST INDEX (global) of the winner so rank 0 can break ties
-        ops.raycastComposite([o.id for o in objs], o_rects, [self.obj_raylengths[o.id] for o in objs],
-                             [self.obj_vertices[o.id] for o in objs], [self.obj_normals[o.id] for o in objs],
-                             [self.obj_modelSegmentation[o.id] for o in objs], g["zray"], g["zvert"], g["zvert"],
-                             g["zmask"], self.params.boundary, g["ray"], g["vert"], g["norm"], g["seg"],
-                             self.vis_count)
-        packed = torch.cat([g["ray"].reshape(-1), g["vert"].reshape(-1), g["norm"].reshape(-1),
-                            g["seg"].reshape(-1).to(torch.float32)])
-        if self.rank == 0:
-            bufs = [torch.empty_like(packed) for _ in range(self.world)]
-            dist.gather(packed, bufs, dst=0, group=self.group)
-            self._merge_on_root(bufs)
-        else:
-            dist.gather(packed, None, dst=0, group=self.group)
-        # visibility is a property of the final segmentation: rank 0 counts and broadcasts
-        n_all = len(self.all_ids)
-        counts = torch.zeros((max(n_all, 1),), dtype=torch.int32, device=dev)
-        if self.rank == 0 and n_all:
-            seg = self.modelSegmentation
-            b = self.params.boundary
-            inner = seg[b:h - b, b:w - b].reshape(-1).to(torch.int64)
-            hist = torch.bincount(inner, minlength=256)
-            ids = torch.tensor([min(i, 255) for i in self.all_ids], device=dev)
-            counts[:n_all] = hist[ids].to(torch.int32)
-        dist.broadcast(counts, src=0, group=self.group)
-        cs = counts.cpu().numpy()
-        self.vis_objs = {i for i, c in zip(self.all_ids, cs) if int(c) > self.params.visibilityThresh}
-
-    def _merge_on_root(self, bufs):
-        h, w = self.h, self.w
-        n = h * w
-        id_to_idx = {min(i, 255): k for k, i in enumerate(self.all_ids)}
-        lut = torch.full((256,), 1 << 30, dtype=torch.int64, device=self.device)
-        for i, k in id_to_idx.items():
-            lut[i] = k
-        best_ray = torch.zeros((n,), dtype=torch.float32, device=self.device)
-        best_idx = torch.full((n,), 1 << 30, dtype=torch.int64, device=self.device)
-        best_seg = torch.zeros((n,), dtype=torch.uint8, device=self.device)
-        best_vert = torch.zeros((n, 3), dtype=torch.float32, device=self.device)
-        best_norm = torch.zeros((n, 3), dtype=torch.float32, device=self.device)
-        for buf in bufs:
-            ray = buf[:n]
-            vert = buf[n:4 * n].reshape(n, 3)
-            norm = buf[4 * n:7 * n].reshape(n, 3)
-            seg = buf[7 * n:8 * n].to(torch.uint8)
-            has = seg != 0
-            idx = lut[seg.to(torch.int64)]
-            empty = best_seg == 0
-            # sequential rule in list order == lexicographic min over (ray, list index), with ray <= 0 always replaced
-            take = has & (empty | (best_ray <= 0) & (idx > best_idx) | (ray < best_ray) |
-                          ((ray == best_ray) & (idx < best_idx) & ~(best_ray <= 0)))
-            best_ray = torch.where(take, ray, best_ray)
-            best_idx = torch.where(take, idx, best_idx)
-            best_seg = torch.where(take, seg, best_seg)
-            best_vert = torch.where(take[:, None], vert, best_vert)
-            best_norm = torch.where(take[:, None], norm, best_norm)
-        bgm = self.bg_mask.reshape(-1) != 0
-        take_bg = bgm & ((best_ray - self.bg_raylengths.reshape(-1)) > 0.05)
-        seg = torch.where(take_bg, torch.zeros_like(best_seg), best_seg)
-        no_obj = seg == 0
-        bgv = torch.where(bgm[:, None], self.bg_vertices.reshape(n, 3), torch.zeros_like(best_vert))
-        bgn = torch.where(bgm[:, None], self.bg_normals.reshape(n, 3), torch.zeros_like(best_norm))
-        self.raylengths.copy_(best_ray.reshape(h, w))
-        self.modelSegmentation.copy_(seg.reshape(h, w))
-        self.vertices.copy_(torch.where(no_obj[:, None], bgv, best_vert).reshape(h, w, 3))
-        self.normals.copy_(torch.where(no_obj[:, None], bgn, best_norm).reshape(h, w, 3))
+        raise NotImplementedError("the staged engine is single-GPU; the multi-GPU frame is NativeEngine's (csrc/xchg.cu, emf_composite_merge)")
 
     # ---- EMFusion::integrateDepth (src/core/EMFusion.cpp:865-889) ----------------------------
     def integrateDepth(self, only_visible: bool = True):
-        vols = [v for v in self.local_volumes() if v.id == 0 or not only_visible or v.id in self.vis_objs]
+        vols = [v for v in self.local_volumes() if v.id == 0 or not only_visible or v.id in self.vis_objs or v.id in self._created]
+        self._created = set()
         if not vols:
             return
         cv = [v.c_volume() for v in vols]

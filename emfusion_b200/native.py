@@ -73,6 +73,7 @@ class NativeEngine(EMFusionEngine):
             rows = self.h // self.world
             check(L.emf_engine_set_background_rows(self._e, rank * rows, (rank + 1) * rows), "emf_engine_set_background_rows")
         self._T = None
+        self._T_key = None
         self._stage = (C.c_float * 3)()
         self._counts = (C.c_int32 * _lib.EMF_MAX_VOLUMES)()
         self._sync_volumes()
@@ -141,13 +142,22 @@ class NativeEngine(EMFusionEngine):
         if self._dirty:
             self._sync_volumes()
         vols = self._keep
-        if self._T is None:     # relative poses of the frame (cleared whenever a pose may have changed)
+        # relative poses: recomputed whenever any pose differs from the ones they were computed from (the caller may assign
+        # eng.pose / obj.pose between stage calls, as the reference does between tracking and the second association pass)
+        key = b"".join([self.pose.R.tobytes(), self.pose.t.tobytes()] + [v.pose.R.tobytes() + v.pose.t.tobytes() for v in vols])
+        if self._T is None or self._T_key != key:
             self._T = rel_pose_arrays(self.pose, [v.pose for v in vols]) if vols else (np.zeros((1, 12), np.float32),) * 2
+            self._T_key = key
         T_co, T_oc = self._T
         d = depth if depth is not None else self.depth
         check(self._L.emf_engine_frame(self._e, C.byref(ops.image(d)), T_co.ctypes.data_as(C.POINTER(Pose)),
                                        T_oc.ctypes.data_as(C.POINTER(Pose)), int(flags),
                                        torch.cuda.current_stream(self.device).cuda_stream), "emf_engine_frame")
+        # objects created since the last integrate are visible by definition until it has run (EMFusion.cpp:550,918)
+        if flags & (F_COMPOSITE | F_COMPOSITE_NOBG):
+            self._vis_extra = set(self._created)
+        if flags & F_INTEGRATE:
+            self._created = set()
         n = len(vols)
         launches = 0
         if flags & F_POINTS: launches += 1
@@ -293,6 +303,7 @@ class NativeEngine(EMFusionEngine):
         else:
             cs = self._global_counts.cpu().numpy()[:len(self.all_ids)]
             self._vis_objs = {i for i, c in zip(self.all_ids, cs) if int(c) > self.params.visibilityThresh}
+        self._vis_objs |= getattr(self, "_vis_extra", set())
 
     @property
     def vis_objs(self):

@@ -281,6 +281,15 @@ EMF_API int emf_integrate_volumes_ws(int n_vol, const emf_volume* vols, const em
                              void* workspace, size_t workspace_bytes, emf_stream_t stream);
 EMF_API size_t emf_integrate_workspace_bytes(int width, int height);
 
+/* emf_integrate_volumes_ws in two parts, so that the part that depends on the depth image and the poses alone can run on
+ * another stream next to the raycast: phase 1 = depth pyramid + classification of whole 32 x 4 x 4 voxel bricks against it
+ * (every volume: the visibility gate is not known yet), phase 2 = the integration itself (gated); phase 0 = both
+ * (= emf_integrate_volumes_ws).  Same arguments in both calls; the workspace carries the state between them. */
+EMF_API int emf_integrate_volumes_phase(int n_vol, const emf_volume* vols, const emf_pose* T_oc, const float K[9],
+                                const emf_image* depth, const emf_image* assoc, float max_weight,
+                                const int32_t* gate_counts, const int* gates, int gate_thresh, uint64_t* stats,
+                                void* workspace, size_t workspace_bytes, int phase, emf_stream_t stream);
+
 /* Derives brick_map from const_bits for every volume that carries both (others are skipped); two launches.
  * Call after integrating and before raycasting. */
 EMF_API int emf_update_brick_maps(int n_vol, const emf_volume* vols, emf_stream_t stream);

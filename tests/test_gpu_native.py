@@ -60,8 +60,44 @@ def test_native_engine_equals_staged_engine(cuda_dev, accelerate):
             assert_bits(va.tsdfWeights, vb.tsdfWeights.cpu().numpy(), f"frame {f} weights vol {va.id}")
         if f > 0:
             compare(nat, ref, f)
+        if f == 3:   # the new object's volume was integrated in its first frame, unseen by that frame's raycast (EMFusion.cpp:550,918)
+            for eng in (nat, ref):
+                new = [o for o in eng.objects if o.id == n_obj + 1][0]
+                assert float(new.tsdfWeights.max()) > 0, f"{type(eng).__name__}: an object created mid-stream was never integrated"
     assert len(nat.vis_objs) > 0
     assert int(nat.bg_mask.sum()) > 0.5 * w * h
+
+
+def test_pose_assigned_between_stage_calls(cuda_dev):
+    """the reference's order inside a frame: association, tracking (assigns the poses), association again, raycast,
+    integrate.  Poses assigned between stage calls must be the ones the following stages use (native == staged, and the
+    second association differs from the first)"""
+    w, h, bg, n_obj, obj = 160, 120, 64, 2, 32
+    scene = Scene(n_objects=n_obj, width=w, height=h, seed=6)
+    nat = make(NativeEngine, scene, w, h, bg, n_obj, obj)
+    ref = make(EMFusionEngine, scene, w, h, bg, n_obj, obj)
+    for eng in (nat, ref):
+        depth, inst = scene.render(0)
+        eng.processFrame(cu(depth), scene.cam_pose(0), {o.id: scene.object_pose(o.id - 1, 0) for o in eng.objects})
+        zeros = torch.zeros((h, w), dtype=torch.uint8, device=DEV)
+        for o in eng.objects:
+            o.integrateMask(cu((inst == o.id).astype(np.uint8)), zeros, eng.pose, eng.params.intr)
+    depth, _ = scene.render(5)
+    first = {}
+    for eng in (nat, ref):
+        eng.set_depth(cu(depth))
+        eng.computeAssociationWeights()                 # at the poses of frame 0
+        first[type(eng).__name__] = eng.bg_associationWeights.clone()
+        eng.pose = scene.cam_pose(5)                    # "tracking" moves everything
+        for o in eng.objects:
+            o.pose = scene.object_pose(o.id - 1, 5)
+        eng.computeAssociationWeights()
+        eng.raycast()
+        eng.integrateDepth()
+    compare(nat, ref, 5)
+    assert not torch.equal(first["NativeEngine"], nat.bg_associationWeights), "the second association used the stale poses"
+    for va, vb in zip(nat.local_volumes(), ref.local_volumes()):
+        assert_bits(va.tsdfVol, vb.tsdfVol.cpu().numpy(), f"tsdf vol {va.id}")
 
 
 def test_native_engine_stage_times(cuda_dev):
