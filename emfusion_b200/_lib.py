@@ -111,6 +111,10 @@ _SIGS = {
     "emf_assoc_normalise_parts": [C.c_int, _P(Image), C.c_int, _P(C.c_void_p), _P(Image), C.c_void_p, C.c_uint32, C.c_void_p,
                                   C.c_double, C.c_void_p],
     "emf_engine_set_partial_norm_target": [C.c_void_p, _P(Image)],
+    "emf_engine_set_composite_target": [C.c_void_p, _P(Image)],
+    "emf_engine_set_background_target": [C.c_void_p, _P(Image)],
+    "emf_engine_set_option": [C.c_void_p, C.c_int, C.c_int],
+    "emf_engine_set_gate_source": [C.c_void_p, C.c_void_p, _P(C.c_int), C.c_int],
     "emf_engine_normalise_from_parts": [C.c_void_p, C.c_int, _P(C.c_void_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_double,
                                         C.c_void_p],
     "emf_xchg_alloc": [C.c_size_t, _P(C.c_void_p), C.c_char_p],

@@ -31,6 +31,11 @@ struct emf_engine {
     size_t pool_bytes = 0;
     emf_image points{}, norm{}, ray{}, vert{}, nrm{}, seg{}, zero_f{}, zero_f3{}, zero_u8{};
     emf_image partial_target{};   // ptr == nullptr: partial normalisers go to `norm`
+    emf_image comp_target[4]{};   // ptr == nullptr: the composite goes to ray / vert / nrm / seg (else: e.g. a slot of an exchange buffer)
+    emf_image bg_target[4]{};     // ptr == nullptr: the background's raycast goes to v_ray[0] / v_vert[0] / v_norm[0] / v_mask[0]
+    int use_cert = -1;            // ray-space certificate for the background's raycast: -1 = EMF_RAY_CERT decides
+    const int32_t* gate_src = nullptr;   // nullptr: the integrate is gated by vis_count[list position]; else by gate_src[gate_idx[i]]
+    std::vector<int> gate_idx;
     std::vector<emf_image> a_img, v_ray, v_vert, v_norm, v_mask;
     int32_t* vis_count = nullptr;
     void* int_ws = nullptr;            // integrate workspace (depth pyramid)
@@ -240,15 +245,19 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         }
         if (e->has_bg && (e->rects[0] > 0 || e->rects[1] > 0 || e->rects[2] < w || e->rects[3] < h))
             // the composite reads the background's hit mask over the whole frame: pixels its box cannot cover are "no hit"
-            cudaMemsetAsync(e->v_mask[0].ptr, 0, e->v_mask[0].pitch * h, s);
+            cudaMemsetAsync(e->bg_target[3].ptr ? e->bg_target[3].ptr : e->v_mask[0].ptr, 0, e->v_mask[0].pitch * h, s);
         if (e->has_bg) {   // band of rows of the background (multi-GPU, replicated background)
             e->rects[1] = std::max(e->rects[1], e->bg_y0);
             e->rects[3] = std::max(e->rects[1], std::min(e->rects[3], e->bg_y1));
         }
-        // the ray-space certificate (emf_raycast_volumes_ws) is opt-in: EMF_RAY_CERT=1 (see DESIGN.md for the measurements)
-        static const bool use_cert = [] { const char* v = getenv("EMF_RAY_CERT"); return v && v[0] == '1'; }();
-        rc = emf_raycast_volumes_ws(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), e->v_ray.data(), e->v_vert.data(),
-                                    e->v_norm.data(), e->v_mask.data(), nullptr, use_cert ? e->ray_ws : nullptr,
+        // the ray-space certificate (emf_raycast_volumes_ws) is opt-in: EMF_RAY_CERT=1 or emf_engine_set_option (see
+        // DESIGN.md for the measurements: it pays when a GPU traces a band of the frame, not the whole of it)
+        static const bool env_cert = [] { const char* v = getenv("EMF_RAY_CERT"); return v && v[0] == '1'; }();
+        const bool use_cert = e->use_cert < 0 ? env_cert : e->use_cert != 0;
+        std::vector<emf_image> r_ray(e->v_ray), r_vert(e->v_vert), r_norm(e->v_norm), r_mask(e->v_mask);
+        if (e->has_bg && e->bg_target[0].ptr) { r_ray[0] = e->bg_target[0]; r_vert[0] = e->bg_target[1]; r_norm[0] = e->bg_target[2]; r_mask[0] = e->bg_target[3]; }
+        rc = emf_raycast_volumes_ws(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), r_ray.data(), r_vert.data(),
+                                    r_norm.data(), r_mask.data(), nullptr, use_cert ? e->ray_ws : nullptr,
                                     use_cert ? e->ray_ws_bytes : 0, stream);
         if (rc != EMF_OK) return rc;
     }
@@ -264,7 +273,9 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         const emf_image* bg_mask = with_bg ? &e->v_mask[0] : &e->zero_u8;
         rc = emf_raycast_composite(n_obj, e->ids.data(), e->rects.data() + 4 * o0, e->v_ray.data() + o0, e->v_vert.data() + o0,
                                    e->v_norm.data() + o0, e->v_mask.data() + o0, bg_ray, bg_vert, bg_norm, bg_mask,
-                                   e->cfg.boundary, &e->ray, &e->vert, &e->nrm, &e->seg, e->vis_count, stream);
+                                   e->cfg.boundary, e->comp_target[0].ptr ? &e->comp_target[0] : &e->ray,
+                                   e->comp_target[0].ptr ? &e->comp_target[1] : &e->vert, e->comp_target[0].ptr ? &e->comp_target[2] : &e->nrm,
+                                   e->comp_target[0].ptr ? &e->comp_target[3] : &e->seg, e->vis_count, stream);
         if (rc != EMF_OK) return rc;
         if (n_obj > 0) {
             cudaMemcpyAsync(e->vis_host, e->vis_count, sizeof(int32_t) * n_obj, cudaMemcpyDeviceToHost, s);
@@ -273,19 +284,34 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
     }
     if (overlap) cudaStreamWaitEvent(s, e->join, 0);   // (also when no integrate follows: the caller sees one stream)
     if (timed) cudaEventRecord(e->ev[2], s);
-    if ((flags & EMF_FRAME_INTEGRATE) && n > 0) {
+    if ((flags & (EMF_FRAME_INTEGRATE | EMF_FRAME_INTEGRATE_BG | EMF_FRAME_INTEGRATE_OBJ)) && n > 0) {
         if (!T_oc || !emfb::image_ok(depth, 4)) return EMF_ERR_INVALID;
-        const emf_image* assoc = e->a_img.data();
-        const bool gate = (flags & EMF_FRAME_INTEGRATE_ALL) == 0;
-        std::vector<int> g(e->gates);
-        for (int i = 0; i < n; ++i) if (e->force[i]) { g[i] = -1; e->force[i] = 0; }
-        if (prepared) cudaStreamWaitEvent(s, e->join2, 0);
-        rc = emf_integrate_volumes_phase(n, e->vols.data(), T_oc, e->cfg.K, depth, assoc, e->cfg.params.max_tsdf_weight,
-                                         gate ? e->vis_count : nullptr, gate ? g.data() : nullptr,
-                                         e->cfg.visibility_thresh, nullptr, e->int_ws, e->int_ws_bytes, prepared ? 2 : 0, stream);
-        if (rc != EMF_OK) return rc;
-        rc = emf_update_brick_maps(n, e->vols.data(), stream);
-        if (rc != EMF_OK) return rc;
+        // the whole list, or only the background (which no visibility counter gates: it need not wait for the composite), or
+        // only the objects
+        int i0 = 0, i1 = n;
+        if (!(flags & EMF_FRAME_INTEGRATE)) {
+            if ((flags & EMF_FRAME_INTEGRATE_BG) && !(flags & EMF_FRAME_INTEGRATE_OBJ)) i1 = e->has_bg ? 1 : 0;
+            else if ((flags & EMF_FRAME_INTEGRATE_OBJ) && !(flags & EMF_FRAME_INTEGRATE_BG)) i0 = e->has_bg ? 1 : 0;
+        }
+        if (i1 > i0) {
+            const emf_image* assoc = e->a_img.data() + i0;
+            const bool gate = (flags & EMF_FRAME_INTEGRATE_ALL) == 0;
+            std::vector<int> g(e->gates.begin() + i0, e->gates.begin() + i1);
+            const int32_t* counts = e->vis_count;
+            if (e->gate_src && (int)e->gate_idx.size() == n) {      // (multi-GPU: the merged frame's counters, by global list position)
+                counts = e->gate_src;
+                for (int i = i0; i < i1; ++i) if (g[i - i0] >= 0) g[i - i0] = e->gate_idx[i];
+            }
+            for (int i = i0; i < i1; ++i) if (e->force[i]) { g[i - i0] = -1; e->force[i] = 0; }
+            const bool prep = prepared && i0 == 0 && i1 == n;
+            if (prep) cudaStreamWaitEvent(s, e->join2, 0);
+            rc = emf_integrate_volumes_phase(i1 - i0, e->vols.data() + i0, T_oc + i0, e->cfg.K, depth, assoc, e->cfg.params.max_tsdf_weight,
+                                             gate ? counts : nullptr, gate ? g.data() : nullptr,
+                                             e->cfg.visibility_thresh, nullptr, e->int_ws, e->int_ws_bytes, prep ? 2 : 0, stream);
+            if (rc != EMF_OK) return rc;
+            rc = emf_update_brick_maps(i1 - i0, e->vols.data() + i0, stream);
+            if (rc != EMF_OK) return rc;
+        }
     }
     if (timed) { cudaEventRecord(e->ev[3], s); e->timed_valid = true; }
     return emfb::launch_status();
@@ -297,6 +323,43 @@ extern "C" EMF_API int emf_engine_set_partial_norm_target(emf_engine* e, const e
     if (!emfb::image_ok(target, 4) || target->width != e->cfg.width || target->height != e->cfg.height) return EMF_ERR_INVALID;
     e->partial_target = *target;
     return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_set_composite_target(emf_engine* e, const emf_image* target4) {
+    if (!e) return EMF_ERR_INVALID;
+    if (!target4) { for (int k = 0; k < 4; ++k) e->comp_target[k] = emf_image{}; return EMF_OK; }
+    const size_t el[4] = {4, 12, 12, 1};
+    for (int k = 0; k < 4; ++k)
+        if (!emfb::image_ok(&target4[k], el[k]) || target4[k].width != e->cfg.width || target4[k].height != e->cfg.height) return EMF_ERR_INVALID;
+    for (int k = 0; k < 4; ++k) e->comp_target[k] = target4[k];
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_set_background_target(emf_engine* e, const emf_image* target4) {
+    if (!e) return EMF_ERR_INVALID;
+    if (!target4) { for (int k = 0; k < 4; ++k) e->bg_target[k] = emf_image{}; return EMF_OK; }
+    const size_t el[4] = {4, 12, 12, 1};
+    for (int k = 0; k < 4; ++k)
+        if (!emfb::image_ok(&target4[k], el[k]) || target4[k].width != e->cfg.width || target4[k].height != e->cfg.height) return EMF_ERR_INVALID;
+    for (int k = 0; k < 4; ++k) e->bg_target[k] = target4[k];
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_set_gate_source(emf_engine* e, const int32_t* counts, const int* index, int n) {
+    if (!e) return EMF_ERR_INVALID;
+    if (!counts) { e->gate_src = nullptr; e->gate_idx.clear(); return EMF_OK; }
+    if (!index || n != e->n_vol) return EMF_ERR_INVALID;
+    e->gate_src = counts;
+    e->gate_idx.assign(index, index + n);
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_set_option(emf_engine* e, int option, int value) {
+    if (!e) return EMF_ERR_INVALID;
+    switch (option) {
+    case EMF_OPT_RAY_CERTIFICATE: e->use_cert = value; return EMF_OK;
+    default: return EMF_ERR_INVALID;
+    }
 }
 
 extern "C" EMF_API int emf_engine_normalise_from_parts(emf_engine* e, int n_parts, const float* const* parts, const uint32_t* flags,

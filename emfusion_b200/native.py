@@ -29,6 +29,8 @@ F_POINTS, F_ASSOC, F_ASSOC_PARTIAL, F_NORMALISE, F_RAYCAST, F_COMPOSITE, F_INTEG
 F_COMPOSITE_NOBG = 0x100
 F_ASSOC_PARTIAL_NOBG = 0x400
 F_TIMED = 0x200
+F_INTEGRATE_BG, F_INTEGRATE_OBJ = 0x800, 0x1000
+OPT_RAY_CERTIFICATE = 1
 F_ALL = F_POINTS | F_ASSOC | F_RAYCAST | F_COMPOSITE | F_INTEGRATE
 IMG_POINTS, IMG_NORM, IMG_RAY, IMG_VERT, IMG_NORMALS, IMG_SEG = range(6)
 IMG_VOL_ASSOC, IMG_VOL_RAY, IMG_VOL_VERT, IMG_VOL_NORMALS, IMG_VOL_MASK = range(16, 21)
@@ -74,9 +76,17 @@ class NativeEngine(EMFusionEngine):
             check(L.emf_engine_set_background_rows(self._e, rank * rows, (rank + 1) * rows), "emf_engine_set_background_rows")
         self._T = None
         self._T_key = None
+        self._marks = None
+        self._bg_integrated = False
+        self._defer_integrate = True      # stage-level calls (raycast(); integrateDepth()) keep the reference's order
         self._stage = (C.c_float * 3)()
         self._counts = (C.c_int32 * _lib.EMF_MAX_VOLUMES)()
         self._sync_volumes()
+
+    def set_ray_certificate(self, on: Optional[bool]):
+        """ray-space certificate + four-lanes-per-ray march for the background's raycast (csrc/raycast.cu: k_ray_certify,
+        k_raycast_cert): True / False, None = the environment variable EMF_RAY_CERT decides.  Same results either way."""
+        check(self._L.emf_engine_set_option(self._e, OPT_RAY_CERTIFICATE, -1 if on is None else int(bool(on))), "emf_engine_set_option")
 
     def __del__(self):
         e, self._e = getattr(self, "_e", None), None
@@ -166,7 +176,8 @@ class NativeEngine(EMFusionEngine):
         if flags & F_RAYCAST and n:   # (+ k_ray_certify and k_raycast_cert when the opt-in ray-space certificate is on)
             launches += 3 if (os.environ.get("EMF_RAY_CERT") == "1" and self.background is not None and n > 1) else (2 if os.environ.get("EMF_RAY_CERT") == "1" and self.background is not None else 1)
         if flags & (F_COMPOSITE | F_COMPOSITE_NOBG): launches += 1
-        if flags & F_INTEGRATE and n: launches += 2 + (2 if any(v.constBits is not None for v in vols) else 0)   # pyramid + integrate
+        if flags & (F_INTEGRATE | F_INTEGRATE_BG | F_INTEGRATE_OBJ) and n:   # depth pyramid + brick classification + integrate (+ brick maps)
+            launches += 3 + (2 if any(v.constBits is not None for v in vols) else 0)
         ops.LAUNCHES["engineFrame"] = ops.LAUNCHES.get("engineFrame", 0) + launches
 
     def set_depth(self, depth: torch.Tensor):
@@ -199,7 +210,24 @@ class NativeEngine(EMFusionEngine):
             self._frame(F_RAYCAST | F_COMPOSITE)
             self._pending_vis = True
             return
-        # every rank composites its own objects against an EMPTY background; rank 0 merges after the gather
+        # every rank composites its own objects against an EMPTY background; rank 0 merges
+        px = self._peer_exchange()
+        if px is not None:
+            if self._dirty:
+                self._sync_volumes()
+            px.begin_composite(self)            # raycast / pre-composite outputs go straight into this rank's exchange slot
+            self._frame(F_RAYCAST | F_COMPOSITE_NOBG)
+            px.signal_composite(self)
+            self._mark("ray_local")
+            # the background is gated by no visibility counter: integrate it now, under the other ranks' raycasts and the merge
+            if self.background is not None and not self._defer_integrate:
+                self._frame(F_INTEGRATE_BG)
+                self._bg_integrated = True
+            self._mark("int_bg")
+            px.finish_composite(self)
+            self._mark("merge")
+            self._pending_vis = True
+            return
         self._frame(F_RAYCAST | F_COMPOSITE_NOBG)
         self._composite_distributed()
 
@@ -239,14 +267,6 @@ class NativeEngine(EMFusionEngine):
                 g["pieces"] = [packed, u8(self.bg_raylengths[y0:y0 + rows]), u8(self.bg_vertices[y0:y0 + rows]),
                                u8(self.bg_normals[y0:y0 + rows]), u8(self.bg_mask[y0:y0 + rows])]
             self._gather_bufs = g
-        px = self._peer_exchange()
-        if px is not None:
-            px.composite(self, g, packed, offs, size, total, rows, band_off, n_all)
-            if g["local"].numel():
-                self.vis_count[:g["local"].numel()] = px.counts(self)[g["local"]]
-            self._global_counts = px.counts(self)
-            self._pending_vis = True
-            return
         if rows:
             torch.cat(g["pieces"], out=g["send"])
             send = g["send"]
@@ -315,8 +335,19 @@ class NativeEngine(EMFusionEngine):
         self._vis_objs = set(v)
         self._pending_vis = False
 
+    def _mark(self, name):
+        """stage events of a timed multi-GPU frame (torch events on the frame's stream)"""
+        if getattr(self, "_marks", None) is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.device))
+            self._marks[name] = ev
+
     def integrateDepth(self, only_visible: bool = True):
-        self._frame(F_INTEGRATE | (0 if only_visible else F_INTEGRATE_ALL))
+        if getattr(self, "_bg_integrated", False) and only_visible:      # (the staged multi-GPU raycast() already integrated the background)
+            self._bg_integrated = False
+            self._frame(F_INTEGRATE_OBJ)
+        else:
+            self._frame(F_INTEGRATE | (0 if only_visible else F_INTEGRATE_ALL))
         for v in self._keep:
             v._grads_dirty = True
             v.updateGradients()
@@ -338,10 +369,30 @@ class NativeEngine(EMFusionEngine):
             self._frame(F_ALL | t)
             self._pending_vis = True
         else:
+            px = self._peer_exchange()
+            if px is not None:
+                px.poll_errors()            # a peer wait that timed out in an earlier frame surfaces here (no stall: asynchronous copy)
+            if timed:       # (timed frames are issued back to back; stage_ms() reads all of them at once)
+                self._marks = {}
+                self._mark_log = getattr(self, "_mark_log", None) or []
+                self._mark_log.append(self._marks)
+            else:
+                self._marks = None
+            self._mark("start")
             self._frame(F_POINTS)
             self.computeAssociationWeights()
-            self.raycast()
-            self._frame(F_INTEGRATE)
+            self._mark("assoc")
+            self._bg_integrated = False
+            self._defer_integrate = False
+            try:
+                self.raycast()
+            finally:
+                self._defer_integrate = True
+            self._frame(F_INTEGRATE_OBJ if self._bg_integrated else F_INTEGRATE)
+            self._bg_integrated = False
+            self._mark("end")
+            if px is not None:
+                px.snapshot_errors(self)
         if self.materialize_grads:
             for v in self._keep:
                 v._grads_dirty = True
@@ -349,7 +400,23 @@ class NativeEngine(EMFusionEngine):
         self.frameCount += 1
 
     def stage_ms(self):
-        """device ms of (association, raycast + composite, integrate) of the last timed frame"""
+        """device ms of (association, raycast + composite, integrate) of the last timed frame.  Multi-GPU: this rank's times
+        between the stage marks -- association incl. the normaliser exchange; local raycast + pre-composite, plus the merge /
+        the wait for it; background integrate (under the merge) plus the objects' integrate"""
+        if self.world > 1:
+            log = [m for m in (getattr(self, "_mark_log", None) or []) if "end" in m]
+            self._mark_log = []
+            if not log:
+                raise _lib.EmfError("no timed frame")
+            log[-1]["end"].synchronize()
+            out = np.zeros(3)
+            for m in log:       # mean over the timed frames issued since the last call
+                dt = lambda a, b: m[a].elapsed_time(m[b]) if a in m and b in m else 0.0
+                if "ray_local" in m:
+                    out += [dt("start", "assoc"), dt("assoc", "ray_local") + dt("int_bg", "merge"), dt("ray_local", "int_bg") + dt("merge", "end")]
+                else:
+                    out += [dt("start", "assoc"), 0.0, dt("assoc", "end")]
+            return [float(x) for x in out / len(log)]
         check(self._L.emf_engine_stage_ms(self._e, self._stage), "emf_engine_stage_ms")
         return [float(x) for x in self._stage]
 
@@ -381,7 +448,7 @@ class PeerExchange:
         self.off_norm = 512 + 2 * 128 * 4
         self.norm_bytes = (w * h * 4 + 255) // 256 * 256
         self.off_pre = self.off_norm + 2 * self.norm_bytes
-        self.cap = (w * h * 29 + (h // n + 1) * w * 29 + 4096 + 255) // 256 * 256    # pre-composite + a background band
+        self.cap = 2 * sum((w * h * el + 255) // 256 * 256 for el in (4, 12, 12, 1))    # pre-composite + background raycast, full frames
         total = self.off_pre + 2 * self.cap
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
         ok = L.emf_xchg_alloc(total, C.byref(ptr), handle) == 0
@@ -461,41 +528,76 @@ class PeerExchange:
         o = self.off_counts + slot * 512
         return self.local[o:o + 512].view(torch.int32)
 
-    def composite(self, eng, g, packed, offs, size, total, rows, band_off, n_all):
-        """every rank leaves [pre-composite | background band] in its own buffer; rank 0 merges straight out of the peers'
-        buffers (emf_composite_merge with peer pointers) and stores the visibility counters into every rank's buffer"""
-        if total > self.cap:
-            raise _lib.EmfError("pre-composite larger than the exchange buffer")
+    # ---- the composite exchange.  A slot of this rank's buffer holds eight full-frame images:
+    #      [pre-composite ray | vert | normals | seg] [background raycast ray | vert | normals | mask]
+    def _slot_images(self, r, slot, w, h):
+        base = self.base[r] + self.off_pre + slot * self.cap
+        px = w * h
+        up = lambda b: (b + 255) // 256 * 256
+        o, out = 0, []
+        for el in (4, 12, 12, 1, 4, 12, 12, 1):
+            out.append(Image(base + o, w * el, w, h))
+            o += up(px * el)
+        return out
+
+    def begin_composite(self, eng):
+        """before EMF_FRAME_RAYCAST | EMF_FRAME_COMPOSITE_NOBG: the pre-composite and (replicated background) the background's
+        raycast are written by their kernels straight into this call's slot of the exchange buffer"""
         self.pre_seq += 1
+        slot = self.pre_seq & 1
+        key = ("tgt", slot)
+        t = self._merge.get(key)
+        if t is None:
+            im = self._slot_images(self.rank, slot, eng.w, eng.h)
+            t = ((Image * 4)(*im[:4]), (Image * 4)(*im[4:]))
+            self._merge[key] = t
+        check(self.L.emf_engine_set_composite_target(eng._e, t[0]), "set_composite_target")
+        if eng.replicate_background and eng.background is not None:
+            check(self.L.emf_engine_set_background_target(eng._e, t[1]), "set_background_target")
+        # the integrate is gated by the merged frame's counters, read where rank 0 stores them (this slot of this rank's buffer)
+        idx = self._merge.get("gate_idx")
+        if idx is None or idx[1] != tuple(v.id for v in eng._keep):
+            pos = {i: k for k, i in enumerate(eng.all_ids)}
+            arr = (C.c_int * max(len(eng._keep), 1))(*[pos.get(v.id, 0) for v in eng._keep])
+            idx = (arr, tuple(v.id for v in eng._keep))
+            self._merge["gate_idx"] = idx
+        check(self.L.emf_engine_set_gate_source(eng._e, self.base[self.rank] + self.off_counts + slot * 512, idx[0], len(eng._keep)),
+              "set_gate_source")
+
+    def signal_composite(self, eng):
+        self._signal(eng, self.KIND_PRE, [0], self.pre_seq)
+
+    def finish_composite(self, eng):
+        """rank 0 merges straight out of the peers' buffers (emf_composite_merge with peer pointers) into its engine's frame
+        images and stores the visibility counters into every rank's buffer; the others wait for the counters"""
         epoch, slot = self.pre_seq, self.pre_seq & 1
         s = torch.cuda.current_stream(eng.device).cuda_stream
         w, h = eng.w, eng.h
-        dst = self.local[self.off_pre + slot * self.cap: self.off_pre + slot * self.cap + total]
-        if rows:
-            torch.cat(g["pieces"], out=dst)
-        else:
-            dst.copy_(packed)
-        self._signal(eng, self.KIND_PRE, [0], epoch)
-        launches = 2
+        n_all = len(eng.all_ids)
+        rows = h // self.n if eng.replicate_background else 0
+        launches = 1
         if self.rank == 0:
             self._wait(eng, self.KIND_PRE, 0, self.n, epoch)
-            key = (slot, total, n_all, tuple(eng.all_ids))
+            key = ("merge", slot, n_all, tuple(eng.all_ids), rows)
             a = self._merge.get(key)
             if a is None:
-                base = [self.base[r] + self.off_pre + slot * self.cap for r in range(self.n)]
-                mk = lambda r, o, el: Image(base[r] + o, w * el, w, h)
-                arr = lambda o, el: (Image * self.n)(*[mk(r, o, el) for r in range(self.n)])
-                ptrs = lambda o: (C.c_void_p * self.n)(*[base[r] + size + o for r in range(self.n)])
+                ims = [self._slot_images(r, slot, w, h) for r in range(self.n)]
+                arr = lambda k: (Image * self.n)(*[ims[r][k] for r in range(self.n)])
+                # band p of the background = rows [p * rows, (p + 1) * rows) of rank p's background images
+                band = lambda k, el: (C.c_void_p * self.n)(*[ims[r][k].ptr + r * rows * w * el for r in range(self.n)])
                 cnt = self.base[0] + self.off_counts + slot * 512
-                a = (self.n, arr(offs[0], 4), arr(offs[1], 12), arr(offs[2], 12), arr(offs[3], 1), n_all,
-                     (C.c_int * max(n_all, 1))(*[int(i) for i in eng.all_ids]), ops.image(eng.bg_raylengths),
-                     ops.image(eng.bg_vertices), ops.image(eng.bg_normals), ops.image(eng.bg_mask), int(eng.params.boundary),
-                     ops.image(eng.raylengths), ops.image(eng.vertices), ops.image(eng.normals), ops.image(eng.modelSegmentation),
-                     cnt, rows, ptrs(band_off[0]) if rows else None, ptrs(band_off[1]) if rows else None,
-                     ptrs(band_off[2]) if rows else None, ptrs(band_off[3]) if rows else None)
+                if rows:
+                    bg = [ops.image(eng.bg_raylengths), ops.image(eng.bg_vertices), ops.image(eng.bg_normals), ops.image(eng.bg_mask)]
+                else:
+                    bg = [ops.image(eng.bg_raylengths), ops.image(eng.bg_vertices), ops.image(eng.bg_normals), ops.image(eng.bg_mask)]
+                args = (self.n, arr(0), arr(1), arr(2), arr(3), n_all, (C.c_int * max(n_all, 1))(*[int(i) for i in eng.all_ids]),
+                        bg[0], bg[1], bg[2], bg[3], int(eng.params.boundary),
+                        ops.image(eng.raylengths), ops.image(eng.vertices), ops.image(eng.normals), ops.image(eng.modelSegmentation),
+                        cnt, rows, band(4, 4) if rows else None, band(5, 12) if rows else None, band(6, 12) if rows else None,
+                        band(7, 1) if rows else None)
                 others = [self.base[r] + self.off_counts + slot * 512 for r in range(1, self.n)]
-                a = (a, cnt, (C.c_void_p * max(len(others), 1))(*others), len(others))
-                self._merge = {key: a}
+                a = (args, cnt, (C.c_void_p * max(len(others), 1))(*others), len(others))
+                self._merge[key] = a
             args, cnt, others, n_others = a
             check(self.L.emf_composite_merge(*args, s), "emf_composite_merge")
             if n_others and n_all:
@@ -505,4 +607,17 @@ class PeerExchange:
         else:
             self._wait(eng, self.KIND_COUNTS, 0, 1, epoch)
             launches += 1
+        eng._global_counts = self.counts(eng)
         ops.LAUNCHES["peerExchange"] = ops.LAUNCHES.get("peerExchange", 0) + launches
+
+    # ---- a timed-out wait sets the error word; it is copied out asynchronously after every frame and looked at before the next
+    def snapshot_errors(self, eng):
+        if getattr(self, "_err_host", None) is None:
+            self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._err_event = torch.cuda.Event()
+        self._err_host.copy_(self.local[self.off_err:self.off_err + 4].view(torch.int32), non_blocking=True)
+        self._err_event.record(torch.cuda.current_stream(eng.device))
+
+    def poll_errors(self):
+        if getattr(self, "_err_host", None) is not None and self._err_event.query() and int(self._err_host[0]) != 0:
+            raise _lib.EmfError(f"multi-GPU exchange: a wait for peer {int(self._err_host[0]) - 1} timed out; the frame used stale data")

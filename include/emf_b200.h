@@ -411,6 +411,8 @@ typedef struct emf_engine_config {
 #define EMF_FRAME_COMPOSITE_NOBG 0x100u /* ... composite against an empty background even if there is one (multi-GPU pre-composite) */
 #define EMF_FRAME_ASSOC_PARTIAL_NOBG 0x400u /* ... as ASSOC_PARTIAL, the background (a replica) left out of the partial sum */
 #define EMF_FRAME_TIMED 0x200u         /* record stage events for emf_engine_stage_ms */
+#define EMF_FRAME_INTEGRATE_BG 0x800u   /* integrate only the background (no visibility counter gates it: multi-GPU, before the merge) */
+#define EMF_FRAME_INTEGRATE_OBJ 0x1000u /* integrate only the (visible) objects */
 #define EMF_FRAME_ALL (EMF_FRAME_POINTS | EMF_FRAME_ASSOC | EMF_FRAME_RAYCAST | EMF_FRAME_COMPOSITE | EMF_FRAME_INTEGRATE)
 
 /* engine-owned images (emf_engine_image) */
@@ -483,6 +485,19 @@ EMF_API int emf_assoc_normalise_parts(int n_img, const emf_image* assoc_io, int 
  * buffer; NULL = the engine's own image again); emf_engine_normalise_from_parts = emf_assoc_normalise_parts over the
  * engine's association images and EMF_IMG_NORM. */
 EMF_API int emf_engine_set_partial_norm_target(emf_engine* e, const emf_image* target);
+/* Multi-GPU: where the composite (EMF_FRAME_COMPOSITE*) writes {ray f32, vert float3, normals float3, seg u8} and where the
+ * background's raycast writes {ray, vert, normals, mask} -- four W x H images each, e.g. inside this rank's exchange buffer,
+ * so that the merging rank reads them in place; NULL = the engine's own images again. */
+EMF_API int emf_engine_set_composite_target(emf_engine* e, const emf_image* target4);
+EMF_API int emf_engine_set_background_target(emf_engine* e, const emf_image* target4);
+/* Multi-GPU: gate the integrate of volume i by counts[index[i]] > visibility_thresh (device counters of the MERGED frame,
+ * e.g. in this rank's exchange buffer; index[i] = the volume's position in the global object list, ignored for the
+ * background) instead of the engine's own counters; counts == NULL restores them.  n = the engine's volume count. */
+EMF_API int emf_engine_set_gate_source(emf_engine* e, const int32_t* counts, const int* index, int n);
+/* Engine options.  EMF_OPT_RAY_CERTIFICATE: 1 = the background's raycast uses the ray-space certificate and the
+ * four-lanes-per-ray march (emf_raycast_volumes_ws), 0 = the plain march, -1 = the environment variable EMF_RAY_CERT decides. */
+#define EMF_OPT_RAY_CERTIFICATE 1
+EMF_API int emf_engine_set_option(emf_engine* e, int option, int value);
 EMF_API int emf_engine_normalise_from_parts(emf_engine* e, int n_parts, const float* const* parts, const uint32_t* flags,
                                     uint32_t value, uint32_t* err, double timeout_s, emf_stream_t stream);
 

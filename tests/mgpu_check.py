@@ -14,12 +14,14 @@ from emfusion_b200.synth import Scene                  # noqa: E402
 from emfusion_b200.volume import ObjTSDF, Params       # noqa: E402
 
 
-def run(out_path, world, rank, dev, n_frames=5, w=320, h=240, bg=96, n_obj=5, obj=32, group=None, replicate=None, peer=None):
+def run(out_path, world, rank, dev, n_frames=5, w=320, h=240, bg=96, n_obj=5, obj=32, group=None, replicate=None, peer=None, cert=None):
     scene = Scene(n_objects=n_obj, width=w, height=h, seed=11, dropout=0.01)
     prm = Params(frameSize=(w, h), intr=scene.K, globalVolumeDims=(bg,) * 3, globalVoxelSize=5.12 / bg,
                  objVolumeDims=(obj,) * 3, visibilityThresh=(40 * 40 * w * h) // (640 * 480), boundary=max(2, 20 * w // 640))
     ObjTSDF.nextID = 0
     eng = NativeEngine(prm, dev, rank=rank, world_size=world, group=group, replicate_background=replicate, peer_exchange=peer)
+    if cert is not None:
+        eng.set_ray_certificate(cert)
     for k in range(n_obj):
         eng.add_object(scene.object_pose(k, 0), scene.object_voxel_size(k, obj))
     res = {}
@@ -55,12 +57,19 @@ def run(out_path, world, rank, dev, n_frames=5, w=320, h=240, bg=96, n_obj=5, ob
     np.savez(out_path + f".rank{rank}.npz", **res)
 
 
+SIZES = {"small": dict(w=320, h=240, bg=96, n_obj=5, obj=32, n_frames=5),
+         # BASELINE sizes: 512^3 background, 128^3 objects, 640 x 480
+         "large": dict(w=640, h=480, bg=512, n_obj=8, obj=128, n_frames=4)}
+
+
 if __name__ == "__main__":
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    run(sys.argv[1], world, rank, dev, replicate={"auto": None, "0": False, "1": True}[sys.argv[2] if len(sys.argv) > 2 else "auto"],
-        peer={"auto": None, "nccl": False, "peer": True}[sys.argv[3] if len(sys.argv) > 3 else "auto"])
+    arg = lambda i, d: sys.argv[i] if len(sys.argv) > i else d
+    run(sys.argv[1], world, rank, dev, replicate={"auto": None, "0": False, "1": True}[arg(2, "auto")],
+        peer={"auto": None, "nccl": False, "peer": True}[arg(3, "auto")],
+        cert={"auto": None, "0": False, "1": True}[arg(5, "auto")], **SIZES[arg(4, "small")])
     dist.barrier()
     dist.destroy_process_group()

@@ -14,34 +14,67 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("exchange", ["nccl", "peer"], ids=["nccl_collectives", "nvlink_peer_memory"])
-@pytest.mark.parametrize("replicate", ["0", "1"], ids=["background_on_rank0", "background_replicated"])
-def test_two_rank_engine_equals_single_gpu(tmp_path, replicate, exchange):
+def _check(tmp_path, world, replicate, exchange, size="small", cert="auto", port=29530):
     from tests import mgpu_check
-    out2 = str(tmp_path / "w2")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "2953" + replicate, os.path.join(ROOT, "tests", "mgpu_check.py"), out2, replicate, exchange]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out2 = str(tmp_path / "wN")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_check.py"), out2, replicate, exchange, size, cert]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     out1 = str(tmp_path / "w1")
-    mgpu_check.run(out1, 1, 0, torch.device("cuda", 0))
+    kw = mgpu_check.SIZES[size]
+    mgpu_check.run(out1, 1, 0, torch.device("cuda", 0), **kw)
     a = np.load(out1 + ".rank0.npz")
-    b0, b1 = np.load(out2 + ".rank0.npz"), np.load(out2 + ".rank1.npz")
+    b = [np.load(out2 + f".rank{r}.npz") for r in range(world)]
+    b0 = b[0]
     assert int(b0["peer_exchange"][0]) == (1 if exchange == "peer" else 0)
-    for f in range(1, 5):
-        assert np.array_equal(a[f"seg{f}"], b0[f"seg{f}"]), f"frame {f}: segmentation"
-        assert np.array_equal(a[f"ray{f}"], b0[f"ray{f}"]), f"frame {f}: ray lengths"
-        assert np.array_equal(a[f"vert{f}"], b0[f"vert{f}"]), f"frame {f}: vertices"
+    for f in range(1, kw["n_frames"]):
+        if f == 1 or size == "small":
+            # the volumes of frame 1 were integrated with association == 1 on every rank: its raycast is bit-identical
+            assert np.array_equal(a[f"seg{f}"], b0[f"seg{f}"]), f"frame {f}: segmentation"
+            assert np.array_equal(a[f"ray{f}"], b0[f"ray{f}"]), f"frame {f}: ray lengths"
+            assert np.array_equal(a[f"vert{f}"], b0[f"vert{f}"]), f"frame {f}: vertices"
+        else:
+            # later frames see volumes integrated with association weights that differ in the last bits (the normaliser is
+            # summed rank by rank instead of object by object): within 1e-4, as BASELINE.json asks
+            same = a[f"seg{f}"] == b0[f"seg{f}"]
+            assert same.mean() > 0.9995, f"frame {f}: segmentation differs in {int((~same).sum())} pixels"
+            both = same & (a[f"ray{f}"] > 0) & (b0[f"ray{f}"] > 0)
+            assert float(np.abs(a[f"ray{f}"] - b0[f"ray{f}"])[both].max()) <= 1e-4, f"frame {f}: ray lengths"
+            assert ((a[f"ray{f}"] > 0) == (b0[f"ray{f}"] > 0)).mean() > 0.9995
         assert np.array_equal(a[f"vis{f}"], b0[f"vis{f}"]), f"frame {f}: visibility"
         assert float(np.abs(a[f"bgassoc{f}"] - b0[f"bgassoc{f}"]).max()) <= 1e-5
     assert float(np.abs(a["bg_tsdf"] - b0["bg_tsdf"]).max()) <= 1e-4
     seen = 0
-    for k in range(1, 6):
+    for k in range(1, kw["n_obj"] + 1):
         key = f"obj{k}_tsdf"
-        src = b0 if key in b0.files else b1
-        assert key in src.files, f"object {k} is owned by no rank"
-        assert float(np.abs(a[key] - src[key]).max()) <= 1e-4
-        assert float(np.abs(a[f"obj{k}_assoc"] - src[f"obj{k}_assoc"]).max()) <= 1e-5
+        src = [x for x in b if key in x.files]
+        assert len(src) == 1, f"object {k} is owned by {len(src)} ranks"
+        assert float(np.abs(a[key] - src[0][key]).max()) <= 1e-4
+        assert float(np.abs(a[f"obj{k}_assoc"] - src[0][f"obj{k}_assoc"]).max()) <= 1e-5
         seen += 1
-    assert seen == 5
+    assert seen == kw["n_obj"]
+    assert int((a[f"seg{kw['n_frames'] - 1}"] > 0).sum()) > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["nccl", "peer"], ids=["nccl_collectives", "nvlink_peer_memory"])
+@pytest.mark.parametrize("replicate", ["0", "1"], ids=["background_on_rank0", "background_replicated"])
+def test_two_rank_engine_equals_single_gpu(tmp_path, replicate, exchange):
+    _check(tmp_path, 2, replicate, exchange, port=29530 + int(replicate))
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_n_rank_engine_equals_single_gpu(tmp_path, world):
+    """4 / 8 ranks (as many as the box has): NVLink peer-memory exchange, replicated background, ray-space certificate on
+    (the configuration bench.py --gpus N runs)"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _check(tmp_path, world, "1", "peer", cert="1", port=29540 + world)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("cert", ["0", "1"], ids=["plain_march", "ray_certificate"])
+def test_two_rank_engine_baseline_sizes(tmp_path, cert):
+    """512^3 background + 8 objects @128^3, 640 x 480, over 2 ranks == one GPU"""
+    _check(tmp_path, 2, "1", "peer", size="large", cert=cert, port=29550 + int(cert))
