@@ -57,7 +57,7 @@ def parse():
                     help="multi-GPU: NCCL collectives (all-reduce, gather, broadcast) instead of the NVLink peer-memory exchange")
     ap.add_argument("--ray-certificate", type=int, default=-1,
                     help="1 / 0: ray-space certificate + four-lanes-per-ray march for the background's raycast on / off "
-                         "(default: on for N > 1, where a rank traces a band of the frame; off for N = 1 -- DESIGN.md section 4.3)")
+                         "(default: off -- measured slower at every N on the bench scene, DESIGN.md section 4.3)")
     ap.add_argument("--materialize-grads", action="store_true",
                     help="also materialise the float3 gradient volumes every frame (reference behaviour)")
     return ap.parse_args()
@@ -265,7 +265,7 @@ def run_ours(args):
     eng = NativeEngine(prm, dev, rank=rank, world_size=world, materialize_grads=args.materialize_grads,
                        accelerate=args.brick_maps, replicate_background=False if args.background_on_rank0 else None,
                        peer_exchange=False if args.nccl_exchange else None)
-    use_cert = args.ray_certificate if args.ray_certificate >= 0 else (1 if world > 1 else 0)
+    use_cert = args.ray_certificate if args.ray_certificate >= 0 else 0
     eng.set_ray_certificate(bool(use_cert))
     for i in range(k):
         eng.add_object(scene.object_pose(i, 0), scene.object_voxel_size(i, ob))

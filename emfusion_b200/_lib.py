@@ -111,6 +111,9 @@ _SIGS = {
     "emf_assoc_normalise_parts": [C.c_int, _P(Image), C.c_int, _P(C.c_void_p), _P(Image), C.c_void_p, C.c_uint32, C.c_void_p,
                                   C.c_double, C.c_void_p],
     "emf_engine_set_partial_norm_target": [C.c_void_p, _P(Image)],
+    "emf_engine_submit_host": [C.c_void_p, C.c_void_p, _P(Pose), _P(Pose), C.c_uint, C.c_int, C.c_void_p, _P(C.c_longlong)],
+    "emf_engine_result_host": [C.c_void_p, C.c_longlong, _P(C.c_void_p), _P(C.c_void_p)],
+    "emf_engine_depth_slot": [C.c_void_p, C.c_longlong, _P(Image)],
     "emf_engine_set_composite_target": [C.c_void_p, _P(Image)],
     "emf_engine_set_background_target": [C.c_void_p, _P(Image)],
     "emf_engine_set_option": [C.c_void_p, C.c_int, C.c_int],

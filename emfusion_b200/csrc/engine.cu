@@ -33,6 +33,14 @@ struct emf_engine {
     emf_image partial_target{};   // ptr == nullptr: partial normalisers go to `norm`
     emf_image comp_target[4]{};   // ptr == nullptr: the composite goes to ray / vert / nrm / seg (else: e.g. a slot of an exchange buffer)
     emf_image bg_target[4]{};     // ptr == nullptr: the background's raycast goes to v_ray[0] / v_vert[0] / v_norm[0] / v_mask[0]
+    // host-facing frames (emf_engine_submit_host): two slots, three streams
+    struct HostSlot {
+        float* depth_dev = nullptr; uint8_t* seg_dev = nullptr; float* ray_dev = nullptr;
+        uint8_t* seg_host = nullptr; float* ray_host = nullptr;       // pinned
+        cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
+    } hs[2];
+    cudaStream_t up = nullptr, down = nullptr;
+    long long host_count = 0;
     int use_cert = -1;            // ray-space certificate for the background's raycast: -1 = EMF_RAY_CERT decides
     const int32_t* gate_src = nullptr;   // nullptr: the integrate is gated by vis_count[list position]; else by gate_src[gate_idx[i]]
     std::vector<int> gate_idx;
@@ -87,6 +95,8 @@ void carve(emf_engine* e, char* base, size_t* total) {
 
 }  // namespace
 
+static bool host_slots_ready(emf_engine* e);
+
 extern "C" EMF_API emf_engine* emf_engine_create(const emf_engine_config* cfg) {
     if (!cfg || cfg->width <= 0 || cfg->height <= 0) return nullptr;
     emf_engine* e = new (std::nothrow) emf_engine();
@@ -101,6 +111,7 @@ extern "C" EMF_API emf_engine* emf_engine_create(const emf_engine_config* cfg) {
     ok = ok && cudaStreamCreateWithFlags(&e->aux2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->fork2, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->join2, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && host_slots_ready(e);      // (page-locked allocations are slow: not on the first frame's path)
     if (!ok) { emf_engine_destroy(e); return nullptr; }
     for (int k = 0; k < EMF_MAX_VOLUMES; ++k) e->vis_host[k] = 0;
     return e;
@@ -114,6 +125,18 @@ extern "C" EMF_API void emf_engine_destroy(emf_engine* e) {
     if (e->vis_ready) cudaEventDestroy(e->vis_ready);
     if (e->fork) cudaEventDestroy(e->fork);
     if (e->join) cudaEventDestroy(e->join);
+    for (auto& h : e->hs) {
+        if (h.depth_dev) cudaFree(h.depth_dev);
+        if (h.seg_dev) cudaFree(h.seg_dev);
+        if (h.ray_dev) cudaFree(h.ray_dev);
+        if (h.seg_host) cudaFreeHost(h.seg_host);
+        if (h.ray_host) cudaFreeHost(h.ray_host);
+        if (h.uploaded) cudaEventDestroy(h.uploaded);
+        if (h.computed) cudaEventDestroy(h.computed);
+        if (h.downloaded) cudaEventDestroy(h.downloaded);
+    }
+    if (e->up) cudaStreamDestroy(e->up);
+    if (e->down) cudaStreamDestroy(e->down);
     if (e->aux) cudaStreamDestroy(e->aux);
     if (e->fork2) cudaEventDestroy(e->fork2);
     if (e->join2) cudaEventDestroy(e->join2);
@@ -322,6 +345,77 @@ extern "C" EMF_API int emf_engine_set_partial_norm_target(emf_engine* e, const e
     if (!target) { e->partial_target = emf_image{}; return EMF_OK; }
     if (!emfb::image_ok(target, 4) || target->width != e->cfg.width || target->height != e->cfg.height) return EMF_ERR_INVALID;
     e->partial_target = *target;
+    return EMF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-facing frame: what emf::EMFusion::processFrame does between `depth_raw.upload` (reference src/core/EMFusion.cpp:72)
+// and the host-side consumers of the raycast (getLastMasks / the renderers, :131-200), with host buffers at both ends.
+// The reference uploads, processes and downloads strictly one after the other, blocking the host on each.  Here the upload
+// of frame n + 1 and the download of frame n run on their own streams under the kernels of the neighbouring frames; the
+// host only waits when it asks for a result.  Every frame's depth crosses PCIe once, every result is read back once.
+// ---------------------------------------------------------------------------------------------
+static bool host_slots_ready(emf_engine* e) {
+    if (e->up) return true;
+    const size_t px = (size_t)e->cfg.width * e->cfg.height;
+    bool ok = cudaStreamCreateWithFlags(&e->up, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->down, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& h : e->hs) {
+        ok = ok && cudaMalloc((void**)&h.depth_dev, px * 4) == cudaSuccess && cudaMalloc((void**)&h.seg_dev, px) == cudaSuccess &&
+             cudaMalloc((void**)&h.ray_dev, px * 4) == cudaSuccess && cudaMallocHost((void**)&h.seg_host, px) == cudaSuccess &&
+             cudaMallocHost((void**)&h.ray_host, px * 4) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h.uploaded, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h.computed, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h.downloaded, cudaEventDisableTiming) == cudaSuccess;
+    }
+    return ok;
+}
+
+extern "C" EMF_API int emf_engine_submit_host(emf_engine* e, const float* depth_host, const emf_pose* T_co, const emf_pose* T_oc,
+                                      unsigned flags, int download, emf_stream_t stream, long long* ticket_out) {
+    if (!e || !e->pool || !depth_host) return EMF_ERR_INVALID;
+    if (!host_slots_ready(e)) return EMF_ERR_CUDA;
+    const int w = e->cfg.width, h = e->cfg.height;
+    const size_t px = (size_t)w * h;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long k = e->host_count;
+    emf_engine::HostSlot& H = e->hs[k & 1];
+    if (k >= 2) cudaStreamWaitEvent(e->up, H.computed, 0);          // the frame that last used this depth slot is done with it
+    cudaMemcpyAsync(H.depth_dev, depth_host, px * 4, cudaMemcpyHostToDevice, e->up);
+    cudaEventRecord(H.uploaded, e->up);
+    cudaStreamWaitEvent(s, H.uploaded, 0);
+    if (k >= 2) cudaStreamWaitEvent(s, H.downloaded, 0);            // ... and its staged result has left the device
+    emf_image depth{H.depth_dev, (size_t)w * 4, w, h};
+    const int rc = emf_engine_frame(e, &depth, T_co, T_oc, flags, stream);
+    if (rc != EMF_OK) return rc;
+    if (download) {   // stage the composite on the compute stream so that the next frame may overwrite the engine's images
+        cudaMemcpyAsync(H.seg_dev, e->seg.ptr, px, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(H.ray_dev, e->ray.ptr, px * 4, cudaMemcpyDeviceToDevice, s);
+    }
+    cudaEventRecord(H.computed, s);
+    cudaStreamWaitEvent(e->down, H.computed, 0);
+    if (download) {
+        cudaMemcpyAsync(H.seg_host, H.seg_dev, px, cudaMemcpyDeviceToHost, e->down);
+        cudaMemcpyAsync(H.ray_host, H.ray_dev, px * 4, cudaMemcpyDeviceToHost, e->down);
+    }
+    cudaEventRecord(H.downloaded, e->down);
+    if (ticket_out) *ticket_out = k;
+    e->host_count = k + 1;
+    return emfb::launch_status();
+}
+
+extern "C" EMF_API int emf_engine_result_host(emf_engine* e, long long ticket, const uint8_t** seg_host, const float** ray_host) {
+    if (!e || !e->up || ticket < e->host_count - 2 || ticket >= e->host_count) return EMF_ERR_INVALID;
+    emf_engine::HostSlot& H = e->hs[ticket & 1];
+    if (cudaEventSynchronize(H.downloaded) != cudaSuccess) return EMF_ERR_CUDA;
+    if (seg_host) *seg_host = H.seg_host;
+    if (ray_host) *ray_host = H.ray_host;
+    return EMF_OK;
+}
+
+extern "C" EMF_API int emf_engine_depth_slot(emf_engine* e, long long ticket, emf_image* depth_out) {
+    if (!e || !e->up || !depth_out || ticket < e->host_count - 2 || ticket >= e->host_count) return EMF_ERR_INVALID;
+    *depth_out = emf_image{e->hs[ticket & 1].depth_dev, (size_t)e->cfg.width * 4, e->cfg.width, e->cfg.height};
     return EMF_OK;
 }
 

@@ -148,7 +148,7 @@ class NativeEngine(EMFusionEngine):
         self._pk = None
 
     # ---- one call = some phases of a frame ----------------------------------------------------------------
-    def _frame(self, flags: int, depth: Optional[torch.Tensor] = None):
+    def _frame(self, flags: int, depth: Optional[torch.Tensor] = None, host_depth: Optional[torch.Tensor] = None, download: bool = True):
         if self._dirty:
             self._sync_volumes()
         vols = self._keep
@@ -159,10 +159,24 @@ class NativeEngine(EMFusionEngine):
             self._T = rel_pose_arrays(self.pose, [v.pose for v in vols]) if vols else (np.zeros((1, 12), np.float32),) * 2
             self._T_key = key
         T_co, T_oc = self._T
-        d = depth if depth is not None else self.depth
-        check(self._L.emf_engine_frame(self._e, C.byref(ops.image(d)), T_co.ctypes.data_as(C.POINTER(Pose)),
-                                       T_oc.ctypes.data_as(C.POINTER(Pose)), int(flags),
-                                       torch.cuda.current_stream(self.device).cuda_stream), "emf_engine_frame")
+        if host_depth is not None:
+            # host buffers at both ends (emf_engine_submit_host): upload, frame, download of the composite, all queued
+            tk = C.c_longlong()
+            check(self._L.emf_engine_submit_host(self._e, host_depth.data_ptr(), T_co.ctypes.data_as(C.POINTER(Pose)),
+                                                 T_oc.ctypes.data_as(C.POINTER(Pose)), int(flags), 1 if download else 0,
+                                                 torch.cuda.current_stream(self.device).cuda_stream, C.byref(tk)), "emf_engine_submit_host")
+            self._ticket = int(tk.value)
+            dv = self.__dict__.setdefault("_depth_views", {})
+            self.depth = dv.get(self._ticket & 1)
+            if self.depth is None:      # (two fixed device slots)
+                im = Image()
+                check(self._L.emf_engine_depth_slot(self._e, self._ticket, C.byref(im)), "emf_engine_depth_slot")
+                self.depth = dv[self._ticket & 1] = torch.as_tensor(_DevMem(im.ptr, (self.h, self.w), "<f4"), device=self.device)
+        else:
+            d = depth if depth is not None else self.depth
+            check(self._L.emf_engine_frame(self._e, C.byref(ops.image(d)), T_co.ctypes.data_as(C.POINTER(Pose)),
+                                           T_oc.ctypes.data_as(C.POINTER(Pose)), int(flags),
+                                           torch.cuda.current_stream(self.device).cuda_stream), "emf_engine_frame")
         # objects created since the last integrate are visible by definition until it has run (EMFusion.cpp:550,918)
         if flags & (F_COMPOSITE | F_COMPOSITE_NOBG):
             self._vis_extra = set(self._created)
@@ -334,6 +348,52 @@ class NativeEngine(EMFusionEngine):
     def vis_objs(self, v):
         self._vis_objs = set(v)
         self._pending_vis = False
+
+    # ---- host buffers at both ends: the C ABI's emf_engine_submit_host / emf_engine_result_host -----------------------
+    def submit_host(self, depth_host: torch.Tensor, cam_pose: Optional[Affine] = None, obj_poses: Optional[dict] = None,
+                    download: bool = True) -> int:
+        """processFrame with the depth image in page-locked HOST memory (H x W float32): upload, frame and download of the
+        composite (segmentation + ray lengths) are queued on three streams inside the library; returns a ticket at once.
+        Single GPU (the multi-GPU frame is several engine calls around the exchanges: pipeline.HostFramePipeline)."""
+        if self.world != 1:
+            raise _lib.EmfError("submit_host drives a single-GPU frame; use pipeline.HostFramePipeline for world_size > 1")
+        if not (depth_host.is_pinned() and depth_host.dtype == torch.float32 and depth_host.is_contiguous()
+                and tuple(depth_host.shape) == (self.h, self.w)):
+            raise _lib.EmfError("depth_host must be a pinned, contiguous H x W float32 tensor")
+        if cam_pose is not None:
+            self.pose = cam_pose
+        if obj_poses:
+            for o in self.objects:
+                if o.id in obj_poses:
+                    o.pose = obj_poses[o.id]
+        if self.frameCount == 0:
+            self._frame(F_POINTS | F_INTEGRATE | F_INTEGRATE_ALL, host_depth=depth_host, download=download)
+        else:
+            self._frame(F_ALL, host_depth=depth_host, download=download)
+            self._pending_vis = True
+        if self.materialize_grads:
+            for v in self._keep:
+                v._grads_dirty = True
+                v.updateGradients()
+        self.frameCount += 1
+        return self._ticket
+
+    def result_host(self, ticket: int):
+        """(segmentation uint8, ray lengths float32) of a submitted frame as tensors over the library's page-locked buffers;
+        blocks until they have arrived.  Valid until two further frames have been submitted."""
+        ps, pr = C.c_void_p(), C.c_void_p()
+        rc = self._L.emf_engine_result_host(self._e, int(ticket), C.byref(ps), C.byref(pr))
+        if rc == _lib.EMF_ERR_INVALID:
+            raise ValueError("result of this frame is no longer (or not yet) available")
+        check(rc, "emf_engine_result_host")
+        views = self.__dict__.setdefault("_host_views", {})
+        v = views.get(ps.value)
+        if v is None:       # (the library double-buffers: two fixed pairs of page-locked buffers)
+            n = self.h * self.w
+            seg = np.ctypeslib.as_array((C.c_uint8 * n).from_address(ps.value)).reshape(self.h, self.w)
+            ray = np.ctypeslib.as_array((C.c_float * n).from_address(pr.value)).reshape(self.h, self.w)
+            v = views[ps.value] = (torch.from_numpy(seg), torch.from_numpy(ray))
+        return v
 
     def _mark(self, name):
         """stage events of a timed multi-GPU frame (torch events on the frame's stream)"""

@@ -24,6 +24,15 @@ class HostFramePipeline:
         """download=False: a rank that does not hold the composite (multi-GPU, rank != 0) only uploads and computes"""
         self.eng = engine
         self.download = download
+        # one GPU: upload / frame / download are queued by the library itself (include/emf_b200.h: emf_engine_submit_host);
+        # several GPUs: the frame is several engine calls around the exchanges, the three streams are driven from here
+        self._native = getattr(engine, "world", 1) == 1 and hasattr(engine, "submit_host")
+        self._count = 0
+        if self._native:
+            w, h = engine.params.frameSize
+            self.h2d_bytes_per_frame = h * w * 4
+            self.d2h_bytes_per_frame = h * w * 5
+            return
         dev = engine.device
         w, h = engine.params.frameSize
         self._main = torch.cuda.current_stream(dev)
@@ -45,6 +54,9 @@ class HostFramePipeline:
     def submit(self, depth_host: torch.Tensor, cam_pose: Optional[Affine] = None, obj_poses: Optional[dict] = None) -> int:
         """Queue one frame (depth_host: pinned H x W float32).  Returns its ticket; never blocks the host unless the slot's
         previous result has not been read back yet."""
+        if self._native:       # single GPU: the whole pipeline is one C-ABI call (emf_engine_submit_host)
+            self._count += 1
+            return self.eng.submit_host(depth_host, cam_pose, obj_poses, download=self.download)
         k = self._count
         s = k % self.DEPTH_SLOTS
         with torch.cuda.stream(self._up):
@@ -73,6 +85,8 @@ class HostFramePipeline:
     def result(self, ticket: int):
         """(segmentation, ray lengths) of a submitted frame in pinned host memory; blocks until they have arrived.  Valid
         until DEPTH_SLOTS further frames have been submitted."""
+        if self._native:
+            return self.eng.result_host(ticket)
         if ticket < self._count - self.DEPTH_SLOTS or ticket >= self._count:
             raise ValueError("result of this frame is no longer (or not yet) available")
         s = ticket % self.DEPTH_SLOTS

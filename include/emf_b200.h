@@ -435,6 +435,20 @@ EMF_API int emf_engine_set_volumes(emf_engine* e, int n_vol, const emf_volume* v
 EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, const emf_pose* T_co, const emf_pose* T_oc, unsigned flags,
                      emf_stream_t stream);
 
+/* One frame with HOST buffers at both ends: emf::EMFusion::processFrame between `depth_raw.upload(frame.getDepth())`
+ * (src/core/EMFusion.cpp:72) and the host-side consumers of the model view (getLastMasks / the renderers, :131-200).
+ * depth_host: W x H f32, continuous, page-locked.  The call queues: upload (own stream) -> emf_engine_frame(flags) on
+ * `stream` -> download of the composite's segmentation (u8) and ray lengths (f32) into engine-owned page-locked memory
+ * (own stream; download = 0: skipped, e.g. on a rank that does not hold the composite) and returns at once with a ticket.
+ * emf_engine_result_host blocks until that frame's result has arrived and returns pointers to it (valid until two further
+ * frames have been submitted: the engine double-buffers).  The upload of frame n + 1 and the download of frame n thus run
+ * under the kernels of their neighbours, where the reference uploads, processes and downloads strictly in sequence.
+ * emf_engine_depth_slot: the device copy of a submitted frame's depth (for callers that drive the phases themselves). */
+EMF_API int emf_engine_submit_host(emf_engine* e, const float* depth_host, const emf_pose* T_co, const emf_pose* T_oc,
+                           unsigned flags, int download, emf_stream_t stream, long long* ticket_out);
+EMF_API int emf_engine_result_host(emf_engine* e, long long ticket, const uint8_t** seg_host, const float** ray_host);
+EMF_API int emf_engine_depth_slot(emf_engine* e, long long ticket, emf_image* depth_out);
+
 /* Device times of {association, raycast + composite, integrate} of the last EMF_FRAME_TIMED frame (waits for it). */
 EMF_API int emf_engine_stage_ms(emf_engine* e, float ms[3]);
 
