@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "unchanged-caller"],
+                    help="unchanged-caller: the reference's launch structure (what an unmodified src/core/EMFusion.cpp does) over this "
+                         "repo's level-1 operators -- the operator-level drop-in of INTEGRATION.md section 1")
     ap.add_argument("--config", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--brick-maps", action="store_true",
@@ -439,6 +441,12 @@ def run_reference(args):
     if rank != 0:
         return
     from tests import ref_gpu
+    unchanged = args.impl == "unchanged-caller"
+    if unchanged:
+        if not os.path.exists(ref_gpu.B200OPS_PATH):
+            emit({"impl": "unchanged-caller", "unavailable": "oracle/_ref/libemf_ref_b200ops.so not built (make -C oracle b200ops)"})
+            return
+        ref_gpu.use_library(ref_gpu.B200OPS_PATH)
     if not ref_gpu.available():
         emit({"impl": "reference", "unavailable": "oracle/_ref/libemf_ref.so not built (needs /root/reference at build time)"})
         return
@@ -543,12 +551,14 @@ def run_reference(args):
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
     nvox = total_voxels(args.config)
     n_vis = sum(1 for i in range(1, len(vols)) if ref.visible(i))
-    out = {"impl": "reference", "metric": "Mvoxels/s (integrate+raycast+assoc)", "value": nvox / (ms_hot * 1e-3) / 1e6,
+    out = {"impl": args.impl, "metric": "Mvoxels/s (integrate+raycast+assoc)", "value": nvox / (ms_hot * 1e-3) / 1e6,
            "unit": "Mvoxels/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_hot,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": name, "voxels_per_frame": nvox, "visible_objects": n_vis,
                       "step": "one frame = computePoints + association + raycast/composite + integrate (+ gradients), K frames back to back",
-                      "what": "reference CUDA kernels (src/core/cuda/*.cu compiled unchanged, sm_100a) + restated OpenCV-CUDA "
+                      "what": ("this repo's level-1 operators (bindings/emf_b200_opencv_binding.cpp on libemf_b200.so) driven with the "
+                               "reference's launch structure: what an UNCHANGED src/core/EMFusion.cpp gets" if unchanged else
+                               "reference CUDA kernels (src/core/cuda/*.cu compiled unchanged, sm_100a)") + " + restated OpenCV-CUDA "
                               "element-wise launches, per-volume streams and host barriers as in src/core/EMFusion.cpp"},
            "stages_ms": {"association": float(ms_stage[0]), "raycast+composite": float(ms_stage[1]), "integrate+gradients": float(ms_stage[2])},
            "e2e": {"value": nvox / (ms_e2e * 1e-3) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_e2e,
@@ -584,7 +594,7 @@ def emit(obj):
 if __name__ == "__main__":
     a = parse()
     quiet_stdout()
-    if a.impl == "reference":
+    if a.impl in ("reference", "unchanged-caller"):
         run_reference(a)
     else:
         run_ours(a)

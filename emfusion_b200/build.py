@@ -51,6 +51,8 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
 
 def build_checkers() -> None:
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], check=True)
+    # the reference's launch structure over this repo's operators (a measurement: bench.py --impl unchanged-caller)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "b200ops"], check=True)
 
 
 if __name__ == "__main__":

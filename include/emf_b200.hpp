@@ -231,6 +231,7 @@ public:
     void setPose(const Affine& p) { pose = p; }
     const Affine& relPoseCO() const { return rel_pose_CO; }
     void setRelPoseCO(const Affine& T) { rel_pose_CO = T; }
+    Image<float>& trackingWeightsImage() { return intWeights; }    // (scratch of the fused tracker iteration: emf_track_iterate)
 
     TSDFParams params;
     bool trackingConverged = false;

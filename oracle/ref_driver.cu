@@ -418,6 +418,7 @@ REF_API int emfref_compute_points(const float* depth, float* points, int w, int 
     return status();
 }
 
+#ifndef EMFREF_NO_TRACKER   // (the 'reference launch structure + this repo's operators' build has no tracker operators)
 // ------------------------------------------------------------------------------------------------
 // 4. tracker: the device part of one iteration of emf::TSDF's Levenberg-Marquardt loop, as
 //    emf::EMFusion::performTracking drives it (src/core/EMFusion.cpp:672-722): the reference kernels
@@ -582,6 +583,7 @@ REF_API int emfref_tracker_error(void* h, const float* tsdf, const float* points
     return status();
 }
 
+#endif   // EMFREF_NO_TRACKER
 // emf::cuda::TSDF::copyValues (src/core/cuda/TSDF.cu:768-819); channels 1 / 2 / 3
 REF_API int emfref_copy_values(const float* src, float* dst, int channels, const int* offset, const int* src_res,
                                const int* dst_res) {

@@ -11,6 +11,15 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libemf_ref.so")
+# the same launch structure over THIS REPO's level-1 operators (oracle/Makefile: b200ops) -- bench.py --impl unchanged-caller
+B200OPS_PATH = os.path.join(ROOT, "oracle", "_ref", "libemf_ref_b200ops.so")
+
+
+def use_library(path: str) -> None:
+    """load another build of ref_driver.cu instead of the reference kernels (before the first call)"""
+    global REF_PATH, _lib
+    REF_PATH, _lib = path, None
+
 
 
 def available() -> bool:
@@ -58,6 +67,9 @@ def lib():
         L.emfref_memcpy_d2d.argtypes = [vp, vp, C.c_size_t]
         L.emfref_compute_points.argtypes = [vp, vp, ci, ci, vp]
         L.emfref_copy_values.argtypes = [vp, vp, ci, vp, vp, vp]
+        if not hasattr(L, "emfref_tracker_create"):      # (a build without the tracker operators)
+            _lib = L
+            return _lib
         L.emfref_tracker_create.argtypes = [ci, ci]
         L.emfref_tracker_create.restype = vp
         L.emfref_tracker_destroy.argtypes = [vp]
