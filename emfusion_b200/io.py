@@ -6,8 +6,10 @@
  * the raw volume dump of emf::EMFusion::writeVolume (src/core/EMFusion.cpp:1302-1313): int32 resolution[3], size_t element
    size, float voxel size, then the array -- and its inverse, which gives parity tests a fixture format the reference can
    produce.
-The Co-Fusion reader (src/utils/ImageReader.cpp:41-116) takes OpenEXR depth; no EXR codec exists in this image, so only
-its file naming (`Color%04d.png`, `Depth%04d.exr`) and its `depth > 100 -> 0` rule are restated (cofusion_names, cofusion_clean).
+The Co-Fusion reader (src/utils/ImageReader.cpp:41-116: `Color%04d.png`, `Depth%04d.exr` float metres, `depth > 100 -> 0`)
+takes OpenEXR depth through cv::imread.  No EXR codec exists in this image, so a minimal one is written out here
+(read_exr / write_exr: single-part scan-line files, FLOAT or HALF channels, compression NONE / ZIPS / ZIP -- what depth
+dumps use); ImageReader mirrors the reference class on top of it.
 """
 from __future__ import annotations
 
@@ -122,7 +124,181 @@ def readVolume(filename: str):
     return data.reshape(shape).copy(), res, voxel
 
 
-# -- src/utils/ImageReader.cpp:41-116 (naming and the depth rule only; EXR decoding is not available here)
+# ------------------------------------------------------------------------------------------------
+# OpenEXR, the subset depth images use: single-part scan-line files; channels FLOAT (32 bit) or HALF (16 bit);
+# compression NONE (0), ZIPS (2: one scan line per chunk) or ZIP (3: 16 scan lines per chunk).
+# Layout (OpenEXR file layout specification): magic 20000630, version word, attributes `name\0 type\0 size value`
+# terminated by \0, one uint64 offset per chunk, chunks `y, size, data`; inside a chunk the scan lines follow each other,
+# each holding its channels in alphabetical order; ZIP data is zlib-deflated after a byte reordering (even / odd bytes
+# split) and a delta predictor.
+# ------------------------------------------------------------------------------------------------
+_EXR_MAGIC = 20000630
+
+
+def _exr_unzip(blob: bytes, raw_size: int) -> bytes:
+    import zlib
+    if len(blob) >= raw_size:           # stored uncompressed when deflate does not help
+        return blob
+    t = np.frombuffer(zlib.decompress(blob), dtype=np.uint8).astype(np.int64)
+    if t.size != raw_size:
+        raise ValueError("EXR: chunk inflates to the wrong size")
+    t = (np.cumsum(t) - 128 * np.arange(t.size)) & 0xFF        # predictor: t[i] = t[i-1] + t[i] - 128
+    t = t.astype(np.uint8)
+    half = (raw_size + 1) // 2
+    out = np.empty(raw_size, dtype=np.uint8)
+    out[0::2] = t[:half]
+    out[1::2] = t[half:]
+    return out.tobytes()
+
+
+def _exr_zip(raw: bytes) -> bytes:
+    import zlib
+    a = np.frombuffer(raw, dtype=np.uint8)
+    t = np.concatenate([a[0::2], a[1::2]]).astype(np.int64)
+    d = t.copy()
+    d[1:] = (t[1:] - t[:-1] + 128 + 256) & 0xFF
+    blob = zlib.compress(d.astype(np.uint8).tobytes(), 6)
+    return blob if len(blob) < len(raw) else raw
+
+
+def read_exr(filename: str, channel: str = None) -> np.ndarray:
+    """-> (H, W) float32: the named channel, or the file's only channel, or the first of Z / Y / R / G / B that exists."""
+    with open(filename, "rb") as fh:
+        buf = fh.read()
+    magic, version = struct.unpack_from("<iI", buf, 0)
+    if magic != _EXR_MAGIC:
+        raise ValueError("not an OpenEXR file")
+    if version & 0x1A00:
+        raise ValueError("EXR: tiled / deep / multi-part files are not supported")
+    pos = 8
+    attrs = {}
+    while buf[pos] != 0:
+        e = buf.index(b"\0", pos); name = buf[pos:e].decode(); pos = e + 1
+        e = buf.index(b"\0", pos); typ = buf[pos:e].decode(); pos = e + 1
+        (size,) = struct.unpack_from("<i", buf, pos); pos += 4
+        attrs[name] = (typ, buf[pos:pos + size]); pos += size
+    pos += 1
+    chans = []                                  # (name, pixel type, x sampling, y sampling), in file (alphabetical) order
+    cb = attrs["channels"][1]
+    q = 0
+    while cb[q] != 0:
+        e = cb.index(b"\0", q); cname = cb[q:e].decode(); q = e + 1
+        ptype, _, xs, ys = struct.unpack_from("<iIii", cb, q); q += 16
+        chans.append((cname, ptype, xs, ys))
+    comp = attrs["compression"][1][0]
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    lines_per_chunk = {0: 1, 2: 1, 3: 16}.get(comp)
+    if lines_per_chunk is None:
+        raise ValueError(f"EXR: compression {comp} is not supported (NONE, ZIPS, ZIP are)")
+    if any(xs != 1 or ys != 1 for _, _, xs, ys in chans):
+        raise ValueError("EXR: sub-sampled channels are not supported")
+    names = [c[0] for c in chans]
+    if channel is None:
+        channel = names[0] if len(names) == 1 else next((c for c in ("Z", "Y", "R", "G", "B") if c in names), names[0])
+    if channel not in names:
+        raise ValueError(f"EXR: no channel {channel!r} (has {names})")
+    bpp = {0: 4, 1: 2, 2: 4}
+    line_bytes = sum(bpp[c[1]] * w for c in chans)
+    n_chunks = (h + lines_per_chunk - 1) // lines_per_chunk
+    offsets = struct.unpack_from(f"<{n_chunks}Q", buf, pos)
+    out = np.zeros((h, w), dtype=np.float32)
+    for off in offsets:
+        y, size = struct.unpack_from("<ii", buf, off)
+        n_lines = min(lines_per_chunk, y1 - y + 1)
+        raw = buf[off + 8:off + 8 + size]
+        if comp != 0:
+            raw = _exr_unzip(raw, n_lines * line_bytes)
+        for ln in range(n_lines):
+            o = ln * line_bytes
+            for cname, ptype, _, _ in chans:
+                nb = bpp[ptype] * w
+                if cname == channel:
+                    dt = {0: "<u4", 1: "<f2", 2: "<f4"}[ptype]
+                    out[y - y0 + ln] = np.frombuffer(raw, dtype=dt, count=w, offset=o).astype(np.float32)
+                o += nb
+    return out
+
+
+def write_exr(filename: str, img: np.ndarray, channel: str = "Y", compression: int = 3):
+    """(H, W) float32 -> single-channel FLOAT scan-line EXR (compression 0 NONE, 2 ZIPS, 3 ZIP).  Channel "Y": what cv::imread
+    (the reference's reader, src/utils/ImageReader.cpp:108) turns into a CV_32FC1 image."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w = img.shape
+    lpc = {0: 1, 2: 1, 3: 16}[compression]
+
+    def attr(name, typ, val):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(val)) + val
+
+    head = struct.pack("<iI", _EXR_MAGIC, 2)
+    head += attr("channels", "chlist", channel.encode() + b"\0" + struct.pack("<iIii", 2, 0, 1, 1) + b"\0")
+    head += attr("compression", "compression", bytes([compression]))
+    head += attr("dataWindow", "box2i", struct.pack("<4i", 0, 0, w - 1, h - 1))
+    head += attr("displayWindow", "box2i", struct.pack("<4i", 0, 0, w - 1, h - 1))
+    head += attr("lineOrder", "lineOrder", bytes([0]))
+    head += attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+    head += attr("screenWindowCenter", "v2f", struct.pack("<2f", 0.0, 0.0))
+    head += attr("screenWindowWidth", "float", struct.pack("<f", 1.0))
+    head += b"\0"
+    chunks = []
+    for y in range(0, h, lpc):
+        raw = img[y:y + lpc].astype("<f4").tobytes()
+        data = raw if compression == 0 else _exr_zip(raw)
+        chunks.append(struct.pack("<ii", y, len(data)) + data)
+    off = len(head) + 8 * len(chunks)
+    table = b""
+    for c in chunks:
+        table += struct.pack("<Q", off)
+        off += len(c)
+    with open(filename, "wb") as fh:
+        fh.write(head + table + b"".join(chunks))
+
+
+class ImageReader:
+    """emf::ImageReader (reference src/utils/ImageReader.cpp:41-116): a Co-Fusion style directory pair, `colour/Color%04d.png`
+    and `depth/Depth%04d.exr` (float32 metres); depth > 100 m counts as missing."""
+
+    def __init__(self, colorpath: str, depthpath: str):
+        self.colorpath, self.depthpath = colorpath, depthpath
+        rgbs = len([f for f in os.listdir(colorpath) if f.endswith(".png")])
+        depths = len([f for f in os.listdir(depthpath) if f.endswith(".exr")])
+        if rgbs != depths:
+            raise RuntimeError("Different number of rgb and depth files!")
+        self._n = rgbs
+        self.currFrame = 0
+        while not all(os.path.exists(f) for f in cofusion_names(colorpath, depthpath, self.currFrame)):   # :72-89
+            self.currFrame += 1
+            if self.currFrame >= rgbs:
+                raise RuntimeError("Could not find starting index!")
+
+    def numFrames(self) -> int:
+        return self._n
+
+    def readFrame(self, index: int) -> Tuple[np.ndarray, np.ndarray]:
+        from PIL import Image
+        cname, dname = cofusion_names(self.colorpath, self.depthpath, index)
+        depth = read_exr(dname)
+        if depth.dtype != np.float32:
+            raise ValueError("Unsupported depth-files")
+        rgb = np.asarray(Image.open(cname).convert("RGB"))[..., ::-1].copy()
+        return rgb, cofusion_clean(depth)
+
+
+def write_cofusion_stream(path: str, depths: Sequence[np.ndarray], rgbs: Sequence[np.ndarray] = None, start: int = 0,
+                          compression: int = 3) -> Tuple[str, str]:
+    """frames -> `<path>/colour/Color%04d.png`, `<path>/depth/Depth%04d.exr`; returns (colorpath, depthpath)"""
+    from PIL import Image
+    cp, dp = os.path.join(path, "colour"), os.path.join(path, "depth")
+    os.makedirs(cp, exist_ok=True); os.makedirs(dp, exist_ok=True)
+    for i, d in enumerate(depths):
+        cname, dname = cofusion_names(cp, dp, start + i)
+        write_exr(dname, d, compression=compression)
+        rgb = rgbs[i] if rgbs is not None else np.zeros(d.shape + (3,), dtype=np.uint8)
+        Image.fromarray(np.ascontiguousarray(rgb[..., ::-1])).save(cname)
+    return cp, dp
+
+
+# -- src/utils/ImageReader.cpp:41-116: file naming and the depth rule
 def cofusion_names(colorpath: str, depthpath: str, index: int) -> Tuple[str, str]:
     return os.path.join(colorpath, f"Color{index:04d}.png"), os.path.join(depthpath, f"Depth{index:04d}.exr")
 

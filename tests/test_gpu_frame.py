@@ -21,7 +21,10 @@ pytestmark = pytest.mark.gpu
 CASES = [("k3_64", 320, 240, 64, 3, 32), ("k8_96", 640, 480, 96, 8, 32),
          # BASELINE.json sizes: config 4's volumes (512^3 background, 128^3 objects; 4 of the 32 objects) and config 5's
          # 1024^3 background at 1280x960 (64-bit offsets: tsdf 4 GiB, reference gradients 12 GiB)
-         ("cfg4_512_128", 640, 480, 512, 4, 128), ("cfg5_1024", 1280, 960, 1024, 1, 128)]
+         ("cfg4_512_128", 640, 480, 512, 4, 128), ("cfg5_1024", 1280, 960, 1024, 1, 128),
+         # the shapes of BASELINE.json's configs 3 and 4 in full: 512^3 + 8 objects @64^3, 512^3 + 32 objects @128^3 (the
+         # bench's 33-volume table)
+         ("cfg3_512_8x64", 640, 480, 512, 8, 64), ("cfg4_full_32x128", 640, 480, 512, 32, 128)]
 
 
 def build_engine(w, h, bg_res, n_obj, obj_res, seed=1, world=1, rank=0, cls=EMFusionEngine):
@@ -71,7 +74,7 @@ def test_engine_vs_reference_frames(case, engine, cuda_dev):
     for i in range(len(vols)):
         ref.fill_assoc(i, 1.0)
     K = prm.intr
-    n_frames = 4 if bg_res <= 512 else 3
+    n_frames = 4 if (bg_res <= 512 and n_obj <= 4) or bg_res < 512 else 3
     for f in range(n_frames):
         depth, inst = scene.render(f)
         d = cu(depth)

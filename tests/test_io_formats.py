@@ -54,6 +54,57 @@ def test_volume_dump_round_trip(tmp_path):
         assert r2 == res and vs == np.float32(0.0125) and np.array_equal(back, vol)
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_exr_reader_against_opencv_fixtures():
+    """files written by OpenCV's EXR codec (tests/golden/generate_exr_golden.py; the codec behind the reference's cv::imread)
+    decode to the exact pixel values: FLOAT and HALF channels, compression NONE / ZIPS / ZIP"""
+    want = np.load(os.path.join(GOLDEN, "cv2_depth.npy"))
+    for name in ("zip", "zips", "none"):
+        got = emfio.read_exr(os.path.join(GOLDEN, f"cv2_depth_{name}.exr"))
+        assert got.dtype == np.float32 and np.array_equal(got, want), name
+    half = emfio.read_exr(os.path.join(GOLDEN, "cv2_depth_half_zip.exr"))
+    assert np.array_equal(half, want.astype(np.float16).astype(np.float32))
+
+
+def test_exr_round_trip_and_opencv_reads_ours(tmp_path):
+    rng = np.random.default_rng(3)
+    img = (rng.random((33, 47)) * 6).astype(np.float32)
+    for comp in (0, 2, 3):
+        fn = str(tmp_path / f"d{comp}.exr")
+        emfio.write_exr(fn, img, compression=comp)
+        assert np.array_equal(emfio.read_exr(fn), img)
+    with pytest.raises(ValueError):
+        emfio.read_exr(os.path.join(GOLDEN, "cv2_depth.npy"))
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    try:
+        import cv2
+        back = cv2.imread(str(tmp_path / "d3.exr"), cv2.IMREAD_UNCHANGED)
+    except Exception:
+        back = None
+    if back is not None:       # the reference's own reader sees a CV_32FC1 image with the same values
+        assert back.dtype == np.float32 and back.shape == img.shape and np.array_equal(back, img)
+
+
+def test_cofusion_stream_round_trip(tmp_path):
+    """config 3's container: colour/Color%04d.png + depth/Depth%04d.exr, starting index found like the reference does"""
+    scene = Scene(n_objects=2, width=160, height=120, seed=1)
+    frames = [scene.render(f) for f in range(3)]
+    depths = [d.copy() for d, _ in frames]
+    depths[1][0, 0] = 500.0                                   # > 100 m: treated as missing (ImageReader.cpp:113)
+    cp, dp = emfio.write_cofusion_stream(str(tmp_path), depths, start=2)
+    rd = emfio.ImageReader(cp, dp)
+    assert rd.numFrames() == 3 and rd.currFrame == 2
+    for f in range(3):
+        rgb, depth = rd.readFrame(2 + f)
+        want = depths[f].copy(); want[want > 100] = 0
+        assert depth.dtype == np.float32 and np.array_equal(depth, want)
+    os.remove(os.path.join(dp, "Depth0004.exr"))
+    with pytest.raises(RuntimeError):
+        emfio.ImageReader(cp, dp)
+
+
 def test_cofusion_rules():
     c, d = emfio.cofusion_names("/a/colour", "/a/depth", 7)
     assert c.endswith("Color0007.png") and d.endswith("Depth0007.exr")
