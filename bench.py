@@ -135,7 +135,7 @@ def cpu_baseline(cfg, seed=0, budget_s=20.0):
     from emfusion_b200.poses import rel_pose_CO, rel_pose_OC
     o = oracle_c.load()
     name, bg, k, ob, w, h = CONFIGS[cfg]
-    k_s = min(k, 8)                                    # 8 of the objects (their volumes are identical in size)
+    k_s = k                                            # the full configuration: every object volume
     sc = S.make("cpu", o, w, h, (bg,) * 3, k_s, (ob,) * 3, n_frames=8, integrate_frames=1, seed=seed)
     nvox = bg ** 3 + k_s * ob ** 3
     t_assoc = t_ray = t_int = 0.0
@@ -175,7 +175,7 @@ def cpu_baseline(cfg, seed=0, budget_s=20.0):
             break
     tot = t_assoc + t_ray + t_int
     return {"value": nvox * frames / tot / 1e6, "unit": "Mvoxels/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{frames} frame(s) {w}x{h}: bg {bg}^3 + {k_s} obj @{ob}^3 ({nvox} voxels/frame); assoc {t_assoc:.2f}s "
+            "sample": f"{frames} frame(s) {w}x{h} of the full configuration: bg {bg}^3 + {k_s} obj @{ob}^3 ({nvox} voxels/frame); assoc {t_assoc:.2f}s "
                       f"raycast+gradients {t_ray:.2f}s integrate {t_int:.2f}s (scalar C oracle, OpenMP, all host cores)"}
 
 
@@ -361,14 +361,25 @@ def run_ours(args):
     nvox = total_voxels(args.config)
     if rank == 0:
         peak, peak_src = peaks()
-        roof = {"bound": "hbm", "kernel": "k_integrate_seg", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+        roof = {"bound": "hbm", "kernel": "k_integrate_bricks", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "peak_source": peak_src}
-        try:   # DRAM bytes per launch of the same kernel on the same workload, from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as fh:
-                tr = json.load(fh)["k_integrate_seg"]
+        ray_roof = None
+        try:   # per-launch DRAM bytes / warp instructions of the same kernels on the same workload, from the committed ncu
+               # capture -- only if it was taken from the kernel sources as they are now (stamped with their git blob hashes)
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
+                tr_all = json.load(fh)
+            cur = {f: subprocess.run(["git", "hash-object", os.path.join(ROOT, "emfusion_b200", "csrc", f)], capture_output=True,
+                                     text=True).stdout.strip() for f in ("integrate.cu", "raycast.cu")}
             if args.config == 4 and world == 1:
-                roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                roof["traffic_source"] = "profiles/r1e_ncu_full_summary.md"
+                tr = tr_all.get("k_integrate_bricks")
+                if tr and tr_all.get("source_hashes", {}).get("integrate.cu") == cur["integrate.cu"]:
+                    roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                    roof["traffic_source"] = tr_all.get("source")
+                else:
+                    roof["traffic_source"] = "stale: profiles/r2_traffic.json was captured from another integrate.cu"
+                rr = tr_all.get("k_raycast")
+                if rr and tr_all.get("source_hashes", {}).get("raycast.cu") == cur["raycast.cu"]:
+                    ray_roof = rr
         except Exception:
             pass
         if world == 1:
@@ -398,6 +409,16 @@ def run_ours(args):
                                       "voxels_on_exact_path": int(c[5]), "segments_decided_free": int(c[6]),
                                       "segments_decided_occluded": int(c[7])}})
             del scratch
+            if ray_roof and clocks and clocks.get("sm_mhz"):
+                # the raycast is bound by issue slots, not bytes: warp instructions of one launch (ncu) against what the SMs can
+                # issue in the kernel's share of the frame (148 SMs x 4 schedulers x clock)
+                peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+                t_ray = max(float(ms_stage[1]) - 0.016, 1e-6) * 1e-3        # (the composite launch is ~16 us of the stage)
+                roof["raycast"] = {"bound": "issue", "kernel": "k_raycast", "warp_instructions": ray_roof["warp_instructions"],
+                                   "achieved": ray_roof["warp_instructions"] / t_ray / 1e9, "peak": peak_issue / 1e9,
+                                   "unit": "G warp-instructions/s", "frac": ray_roof["warp_instructions"] / t_ray / peak_issue,
+                                   "kernel_ms": t_ray * 1e3, "samples": ray_roof.get("samples"),
+                                   "note": "frac = issue slots used; the rest is the dependent chain of the longest rays (DESIGN.md section 4.2)"}
         out = {
             "metric": "Mvoxels/s (integrate+raycast+assoc)", "value": nvox / (ms_step * 1e-3) / 1e6, "unit": "Mvoxels/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,

@@ -96,6 +96,8 @@ _SIGS = {
                                  C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_integrate_volumes_phase": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(Image), _P(Image), C.c_float,
                                     C.c_void_p, _P(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p],
+    "emf_mesh_count": [_P(Volume), C.c_void_p, C.c_size_t, C.c_void_p],
+    "emf_mesh_extract": [_P(Volume), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "emf_update_brick_maps": [C.c_int, _P(Volume), C.c_void_p],
     "emf_reset_bitmaps": [_P(Volume), C.c_void_p],
     "emf_preprocess_depth": [_P(Image), _P(Image), _P(Image), _P(C.c_float), C.c_int, C.c_float, C.c_float, C.c_void_p],
@@ -130,7 +132,7 @@ _SIGS = {
     "emf_xchg_scatter_u32": [C.c_void_p, C.c_int, C.c_int, _P(C.c_void_p), C.c_void_p],
     "emf_volume_screen_rect": [_P(C.c_int), C.c_float, _P(Pose), _P(C.c_float), C.c_int, C.c_int, _P(C.c_int)],
 }
-EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes", "emf_track_workspace_bytes", "emf_integrate_workspace_bytes", "emf_raycast_workspace_bytes", "emf_engine_create", "emf_engine_destroy",
+EXPORTED = sorted(list(_SIGS) + ["emf_version", "emf_brick_map_bytes", "emf_track_workspace_bytes", "emf_integrate_workspace_bytes", "emf_raycast_workspace_bytes", "emf_mesh_workspace_bytes", "emf_engine_create", "emf_engine_destroy",
                                 "emf_engine_vis_counts_device"])
 
 _lib = None
@@ -154,6 +156,8 @@ def lib() -> C.CDLL:
         L.emf_integrate_workspace_bytes.restype = C.c_size_t
         L.emf_raycast_workspace_bytes.argtypes = [C.c_int, C.c_int]
         L.emf_raycast_workspace_bytes.restype = C.c_size_t
+        L.emf_mesh_workspace_bytes.argtypes = [_P(C.c_int)]
+        L.emf_mesh_workspace_bytes.restype = C.c_size_t
         L.emf_track_workspace_bytes.argtypes = [C.c_int]
         L.emf_track_workspace_bytes.restype = C.c_size_t
         L.emf_brick_map_bytes.argtypes = [_P(C.c_int)]

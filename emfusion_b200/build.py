@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "emfusion_b200", "csrc")
 LIBDIR = os.path.join(ROOT, "emfusion_b200", "lib")
 LIB = os.path.join(LIBDIR, "libemf_b200.so")
-SOURCES = ["integrate.cu", "raycast.cu", "bricks.cu", "assoc.cu", "fgprob.cu", "track.cu", "resize.cu", "preprocess.cu", "xchg.cu", "host.cu", "engine.cu"]
+SOURCES = ["integrate.cu", "raycast.cu", "bricks.cu", "assoc.cu", "fgprob.cu", "track.cu", "resize.cu", "mcubes.cu", "preprocess.cu", "xchg.cu", "host.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--default-stream", "legacy",

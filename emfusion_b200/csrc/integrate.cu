@@ -890,9 +890,29 @@ __global__ void __launch_bounds__(kClassifyThreads) k_brick_classify(const __gri
     else if (kind == 1) P.list_whole[base_w + __popc(mw & below)] = item;
 }
 
+// ---- A/B (EMF_INT_TMA=1, off by default): the depth pixels a mixed brick slice can touch are staged in shared memory with
+// the TMA engine's bulk copies (cp.async.bulk, one per image row of the slice's pixel box, completion on an mbarrier), and the
+// per-voxel path gathers from there.  Measured on the bench frame: see DESIGN.md section 9 (no gain: the gathers hit L1 / L2 and
+// the kernel is bound by issue slots; the tile costs occupancy).
+#ifndef EMF_INT_TMA
+#define EMF_INT_TMA 0
+#endif
+constexpr int kTmaRows = 12, kTmaCols = 96;      // (8 warps x 12 x 96 floats = 36 KB of static shared memory)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 template <bool STATS>
-__global__ void __launch_bounds__(kBrickThreads, 4) k_integrate_bricks(const __grid_constant__ IntParams P) {
+__global__ void __launch_bounds__(kBrickThreads, EMF_INT_TMA ? 3 : 4) k_integrate_bricks(const __grid_constant__ IntParams P) {
     __shared__ uint8_t s_src[kBrickThreads / 32][32];
+#if EMF_INT_TMA
+    __shared__ __align__(128) float s_tile[kBrickThreads / 32][kTmaRows][kTmaCols];
+    __shared__ __align__(8) unsigned long long s_bar[kBrickThreads / 32];
+    uint32_t tma_phase = 0;
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[threadIdx.x >> 5])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int seg = lane & 7, yy = lane >> 3;          // this lane's 4-voxel segment inside a 32 x 4 slice of a brick
@@ -1001,6 +1021,10 @@ __global__ void __launch_bounds__(kBrickThreads, 4) k_integrate_bricks(const __g
             // ---- phase A: classify the segment as a whole.  0 skip, 1 free, 2 occluded, 3 per voxel, 4 behind the camera
             //      (the lanes of a sub-brick that k_brick_classify decided already know)
             int cls_s = cls == kBrMixed ? 3 : cls;          // (kBrOut / kBrFree / kBrOcc / kBrBehind = 0 / 1 / 2 / 4)
+#if EMF_INT_TMA
+            int bu0 = 1 << 20, bu1 = -(1 << 20), bv0 = 1 << 20, bv1 = -(1 << 20);      // pixel box of this lane's segment, if undecided
+            bool nobox = false;
+#endif
             if (cls == kBrMixed) {
                 const float xf0 = (float)x0, xf3 = (float)(x0 + 3);
                 const float zz0 = fmaf(xf0, qzb, qza), zz3 = fmaf(xf3, qzb, qza);
@@ -1015,6 +1039,9 @@ __global__ void __launch_bounds__(kBrickThreads, 4) k_integrate_bricks(const __g
                         cls_s = 0;   // every voxel projects outside the image: the reference touches nothing
                     } else if (ulo >= 0.0f && vlo >= 0.0f && uhi <= fw - 1.0f && vhi <= fh - 1.0f) {
                         const int iu0 = (int)ulo, iv0 = (int)vlo, iu1 = (int)uhi + 1, iv1 = (int)vhi + 1;
+#if EMF_INT_TMA
+                        bu0 = iu0; bu1 = min(iu1, P.w - 1); bv0 = iv0; bv1 = min(iv1, P.h - 1);
+#endif
                         const int e = max(iu1 - iu0, iv1 - iv0);
                         const int L = max(1, 32 - __clz(max(e - 1, 0)));   // tile 2^L >= e  =>  the box spans at most 2 tiles per axis
                         if (L <= kPyrLevels) {
@@ -1085,6 +1112,31 @@ __global__ void __launch_bounds__(kBrickThreads, 4) k_integrate_bricks(const __g
             }
             // ---- phase C: the other segments, one voxel per lane (the canonical arithmetic of the reference, bit for bit)
             const unsigned mixed = __ballot_sync(kFull, cls_s == 3);
+#if EMF_INT_TMA
+            // the depth pixels the undecided segments of this slice can touch: one bulk copy per image row into shared memory
+            int U0 = __reduce_min_sync(kFull, cls_s == 3 ? bu0 : (1 << 20)), U1 = __reduce_max_sync(kFull, cls_s == 3 ? bu1 : -(1 << 20));
+            int V0 = __reduce_min_sync(kFull, cls_s == 3 ? bv0 : (1 << 20)), V1 = __reduce_max_sync(kFull, cls_s == 3 ? bv1 : -(1 << 20));
+            U0 &= ~3;
+            const int tw = ((U1 - U0 + 1) + 3) & ~3, th = V1 - V0 + 1;
+            const bool staged = mixed && U1 >= U0 && tw <= kTmaCols && th >= 1 && th <= kTmaRows && U0 + tw <= P.w &&
+                                (P.depth_pitch & 15) == 0 && (((uintptr_t)P.depth) & 15) == 0;
+            if (staged) {
+                const uint32_t bar = smem_u32(&s_bar[wid]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(tw * 4 * th)) : "memory");
+                __syncwarp();
+                if (lane < th) {
+                    const char* src = (const char*)P.depth + (size_t)(V0 + lane) * P.depth_pitch + (size_t)U0 * 4;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(&s_tile[wid][lane][0])), "l"(src), "r"((uint32_t)(tw * 4)), "r"(bar) : "memory");
+                }
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok) : "r"(bar), "r"(tma_phase) : "memory");
+                tma_phase ^= 1u;
+            }
+#endif
             if (mixed) {
                 if (cls_s == 3) s_src[wid][__popc(mixed & ((1u << lane) - 1u))] = (uint8_t)lane;
                 __syncwarp();
@@ -1121,7 +1173,13 @@ __global__ void __launch_bounds__(kBrickThreads, 4) k_integrate_bricks(const __g
                             if ((unsigned)px >= (unsigned)P.w || (unsigned)py >= (unsigned)P.h) {
                                 if (STATS) ++st[4];
                             } else {
+#if EMF_INT_TMA
+                                const float d = (staged && px >= U0 && px < U0 + tw && py >= V0 && py <= V1)
+                                                    ? s_tile[wid][py - V0][px - U0]
+                                                    : __ldg((const float*)((const char*)P.depth + (size_t)py * P.depth_pitch) + px);
+#else
                                 const float d = __ldg((const float*)((const char*)P.depth + (size_t)py * P.depth_pitch) + px);
+#endif
                                 if (!(d > 0.0f)) {
                                     if (w == 0.0f) *tp = 0.0f;
                                     if (STATS) ++st[3];

@@ -21,7 +21,7 @@ from .poses import Affine
 LAUNCHES = {}
 _KERNELS_PER_CALL = {"computePoints": 1, "updateTSDF": 1, "computeTSDFGrads": 1, "raycastTSDF": 1, "getVolumeVals": 1,
                      "updateFgBgProbs": 1, "computeFgProbs": 1, "computeAssociation": 1, "assocWeights": 1,
-                     "assocNormalise": 1, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
+                     "assocNormalise": 1, "marchingCubes": 3, "raycastVolumes": 1, "raycastComposite": 1, "integrateVolumes": 1,
                      "updateBrickMaps": 2, "trackLinearise": 1, "trackNormalisedWeights": 1, "copyValues": 1,
                      "resizeVolume": 1, "preprocessDepth": 1, "trackIterate": 2}
 
@@ -453,3 +453,24 @@ class TrackLoopPlan:
                        self._iw, self._rec, self._ws.data_ptr(), self._ws.numel(), int(n_iterations), _stream(stream)),
               "trackIterate")
         LAUNCHES["trackIterate"] = LAUNCHES.get("trackIterate", 0) + 2 * int(n_iterations)
+
+
+def marchingCubes(vol, stream=None):
+    """emf::TSDF::getMesh / emf::ObjTSDF::getMesh on the device (csrc/mcubes.cu): -> (vertices (n, 3) float32, normals (n, 3)
+    float32, triangles (m, 4) int32 = VTK polygons [3, i0, i1, i2]) as CUDA tensors; one device->host read (the two counts)."""
+    L = _lib.lib()
+    res = (C.c_int * 3)(*[int(r) for r in vol.res])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ws = torch.empty(int(L.emf_mesh_workspace_bytes(res)), dtype=torch.uint8, device=dev)
+    check(L.emf_mesh_count(C.byref(vol), ws.data_ptr(), ws.numel(), _stream(stream)), "meshCount")
+    nv, nt = [int(x) for x in ws[:8].view(torch.int32).cpu().tolist()]
+    if nv < 0 or nt < 0:
+        raise _lib.EmfError("mesh larger than 2^31 - 1 elements")
+    verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+    norms = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+    tris = torch.empty((nt // 4, 4), dtype=torch.int32, device=dev)
+    if nv:
+        check(L.emf_mesh_extract(C.byref(vol), ws.data_ptr(), ws.numel(), verts.data_ptr(), norms.data_ptr(), tris.data_ptr(),
+                                 _stream(stream)), "meshExtract")
+    _count("marchingCubes", 3 if nv else 2)
+    return verts, norms, tris

@@ -180,6 +180,13 @@ class TSDF:
     def getWeightsVol(self) -> np.ndarray:
         return self.tsdfWeights.cpu().numpy()
 
+    # -- src/core/TSDF.cpp:356-373, src/core/ObjTSDF.cpp:247-268: marching cubes over the voxels with weight > 0 (objects: and
+    #    fgProb > 0.5); cv::viz::Mesh's cloud / normals / polygons as arrays
+    def getMesh(self):
+        v, n, t = ops.marchingCubes(ops.volume(self.tsdfVol, self.tsdfWeights, self.volumeRes, self.voxelSize, self.truncdist,
+                                               fg_probs=self._fg(), vid=self.id))
+        return {"cloud": v, "normals": n, "polygons": t}
+
 
 class ObjTSDF(TSDF):
     nextID = 0   # static counter, incremented only by the constructor (src/core/ObjTSDF.cpp:28,34)

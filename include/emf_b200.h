@@ -182,6 +182,21 @@ EMF_API int emf_resize_volume(const float* src_tsdf, const float* src_weights, c
                       float* dst_tsdf, float* dst_weights, float* dst_fgbg, const int dst_res[3], const int offset[3],
                       emf_stream_t stream);
 
+/* emf::TSDF::getMesh / emf::ObjTSDF::getMesh = emf::cuda::TSDF::marchingCubes (include/EMFusion/core/cuda/TSDF.cuh:255-265,
+ * src/core/cuda/TSDF.cu:855-1152) with the mask passes of src/core/TSDF.cpp:356-373 / src/core/ObjTSDF.cpp:247-268 folded in:
+ * a cube is meshed iff all eight corners have weight > 0 (and fgProb > 0.5 when vol->fg_probs is given).
+ * Two calls, because the sizes are data dependent: emf_mesh_count leaves {number of vertices, number of triangle ints}
+ * in the first two int32 of the workspace (device memory, emf_mesh_workspace_bytes(res) bytes, 16-byte aligned; -1 = more
+ * than 2^31 - 1); the caller reads them, allocates, and calls emf_mesh_extract with the SAME workspace: vertices and normals
+ * 3 floats each (metres, volume frame; the "normals" are the interpolated forward-difference gradients, not normalised --
+ * as in the reference, whose `float3 /= float` does nothing, common.cuh:170-173), triangles as VTK polygons (3, i0, i1, i2)
+ * like cv::viz::Mesh::polygons.  One vertex per crossed edge and cube, cubes in (z, y, x) order, edges ascending: the
+ * reference's order.  The reference's three scratch volumes (9 B / voxel) are not needed: 8 B per row of cubes. */
+EMF_API size_t emf_mesh_workspace_bytes(const int res[3]);
+EMF_API int emf_mesh_count(const emf_volume* vol, void* workspace, size_t workspace_bytes, emf_stream_t stream);
+EMF_API int emf_mesh_extract(const emf_volume* vol, void* workspace, size_t workspace_bytes, float* vertices, float* normals,
+                     int32_t* triangles, emf_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Level 3: frame-level batched operations (one call = one EMFusion method).
  * vols[0] is the background when has_background != 0; objects follow in the

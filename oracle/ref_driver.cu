@@ -594,3 +594,35 @@ REF_API int emfref_copy_values(const float* src, float* dst, int channels, const
     cudaDeviceSynchronize();
     return status();
 }
+
+
+#ifndef EMFREF_NO_TRACKER   // (reference-only operators: not in the build over this repo's operators)
+// emf::cuda::TSDF::marchingCubes (src/core/cuda/TSDF.cu:1107-1152) with the mask of emf::TSDF::getMesh (src/core/TSDF.cpp:357:
+// weights > 0; objects: & fgVolMask, src/core/ObjTSDF.cpp:251-252) built by the caller.  Two calls like the product's: the first
+// runs the reference launcher and keeps its outputs, the second copies them out.
+struct RefMesh { GpuMat vertices, normals, triangles; };
+REF_API void* emfref_marching_cubes(const float* tsdf, const float* grads, const uint8_t* mask, const int* res, float voxel, int* counts) {
+    const int rows = res[1] * res[2];
+    GpuMat tv = mat((void*)tsdf, rows, res[0], CV_32FC1), gv = mat((void*)grads, rows, res[0], CV_32FC3), mv = mat((void*)mask, rows, res[0], CV_8UC1);
+    GpuMat cls = cv::cuda::createContinuous((res[1] - 1) * (res[2] - 1), res[0] - 1, CV_8UC1);
+    GpuMat vib = cv::cuda::createContinuous((res[1] - 1) * (res[2] - 1), res[0] - 1, CV_32SC1);
+    GpuMat tib = cv::cuda::createContinuous((res[1] - 1) * (res[2] - 1), res[0] - 1, CV_32SC1);
+    cls.setTo(cv::Scalar(0)); vib.setTo(cv::Scalar(0)); tib.setTo(cv::Scalar(0));
+    cudaDeviceSynchronize();
+    RefMesh* m = new RefMesh();
+    emf::cuda::TSDF::marchingCubes(tv, gv, mv, v3i(res), voxel, cls, vib, tib, m->vertices, m->normals, m->triangles);
+    cudaDeviceSynchronize();
+    counts[0] = m->vertices.cols; counts[1] = m->triangles.cols;
+    return m;
+}
+REF_API int emfref_mesh_fetch(void* h, float* vertices, float* normals, int* triangles) {
+    RefMesh* m = (RefMesh*)h;
+    if (m->vertices.cols > 0) {
+        cudaMemcpy(vertices, m->vertices.data, (size_t)m->vertices.cols * 12, cudaMemcpyDeviceToDevice);
+        cudaMemcpy(normals, m->normals.data, (size_t)m->normals.cols * 12, cudaMemcpyDeviceToDevice);
+        cudaMemcpy(triangles, m->triangles.data, (size_t)m->triangles.cols * 4, cudaMemcpyDeviceToDevice);
+    }
+    delete m;
+    return status();
+}
+#endif

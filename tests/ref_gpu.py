@@ -67,6 +67,10 @@ def lib():
         L.emfref_memcpy_d2d.argtypes = [vp, vp, C.c_size_t]
         L.emfref_compute_points.argtypes = [vp, vp, ci, ci, vp]
         L.emfref_copy_values.argtypes = [vp, vp, ci, vp, vp, vp]
+        if hasattr(L, "emfref_marching_cubes"):
+            L.emfref_marching_cubes.argtypes = [vp, vp, vp, vp, cf, vp]
+            L.emfref_marching_cubes.restype = vp
+            L.emfref_mesh_fetch.argtypes = [vp, vp, vp, vp]
         if not hasattr(L, "emfref_tracker_create"):      # (a build without the tracker operators)
             _lib = L
             return _lib
@@ -264,3 +268,16 @@ class RefTracker:
         _chk(lib().emfref_memcpy_d2d(out.data_ptr(), lib().emfref_tracker_ptr(self.handle, what), out.numel() * out.element_size()),
              "memcpy")
         return out
+
+
+def marching_cubes(tsdf, grads, mask, res, voxel):
+    """the reference's emf::cuda::TSDF::marchingCubes -> (vertices (n, 3), normals (n, 3), triangles (m, 4) int32) CUDA tensors"""
+    counts = np.zeros(2, dtype=np.int32)
+    r = np.asarray(res, dtype=np.int32)
+    h = lib().emfref_marching_cubes(tsdf.data_ptr(), grads.data_ptr(), mask.data_ptr(), r.ctypes.data, float(voxel), counts.ctypes.data)
+    nv, nt = int(counts[0]), int(counts[1])
+    v = torch.empty((nv, 3), dtype=torch.float32, device=tsdf.device)
+    n = torch.empty((nv, 3), dtype=torch.float32, device=tsdf.device)
+    t = torch.empty((nt // 4, 4), dtype=torch.int32, device=tsdf.device)
+    _chk(lib().emfref_mesh_fetch(h, v.data_ptr(), n.data_ptr(), t.data_ptr()), "mesh_fetch")
+    return v, n, t
