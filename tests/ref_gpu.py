@@ -270,14 +270,30 @@ class RefTracker:
         return out
 
 
+MESH_PATH = os.path.join(ROOT, "oracle", "_ref", "libemf_ref_mesh.so")
+_mesh = None
+
+
+def mesh_lib():
+    """the reference's TSDF.cu compiled with a 64-register cap (oracle/Makefile says why): its marching-cubes launcher only"""
+    global _mesh
+    if _mesh is None:
+        _mesh = C.CDLL(MESH_PATH)
+        _mesh.emfref_marching_cubes.restype = C.c_void_p
+        _mesh.emfref_marching_cubes.argtypes = [C.c_void_p] * 4 + [C.c_float, C.c_void_p]
+        _mesh.emfref_mesh_fetch.restype = C.c_int
+        _mesh.emfref_mesh_fetch.argtypes = [C.c_void_p] * 4
+    return _mesh
+
+
 def marching_cubes(tsdf, grads, mask, res, voxel):
     """the reference's emf::cuda::TSDF::marchingCubes -> (vertices (n, 3), normals (n, 3), triangles (m, 4) int32) CUDA tensors"""
     counts = np.zeros(2, dtype=np.int32)
     r = np.asarray(res, dtype=np.int32)
-    h = lib().emfref_marching_cubes(tsdf.data_ptr(), grads.data_ptr(), mask.data_ptr(), r.ctypes.data, float(voxel), counts.ctypes.data)
+    h = mesh_lib().emfref_marching_cubes(tsdf.data_ptr(), grads.data_ptr(), mask.data_ptr(), r.ctypes.data, float(voxel), counts.ctypes.data)
     nv, nt = int(counts[0]), int(counts[1])
     v = torch.empty((nv, 3), dtype=torch.float32, device=tsdf.device)
     n = torch.empty((nv, 3), dtype=torch.float32, device=tsdf.device)
     t = torch.empty((nt // 4, 4), dtype=torch.int32, device=tsdf.device)
-    _chk(lib().emfref_mesh_fetch(h, v.data_ptr(), n.data_ptr(), t.data_ptr()), "mesh_fetch")
+    _chk(mesh_lib().emfref_mesh_fetch(h, v.data_ptr(), n.data_ptr(), t.data_ptr()), "mesh_fetch")
     return v, n, t
