@@ -217,7 +217,8 @@ __device__ void lm_step(const TrackParams& P, const TrackVol& V, emf_track_state
         }
         float x[6];
         for (int k = 0; k < 6; ++k) x[k] = S.x[k];
-        if (lm_solve6(S.A, (float)S.mu, S.b, x)) for (int k = 0; k < 6; ++k) S.x[k] = x[k];
+        const bool solved = lm_solve6(S.A, (float)S.mu, S.b, x);                   // cv::solve zeroes dst when the LU fails: the step test below then ends the run
+        for (int k = 0; k < 6; ++k) S.x[k] = solved ? x[k] : 0.0f;
         float xn = 0.0f;
         for (int k = 0; k < 6; ++k) xn += S.x[k] * S.x[k];
         xn = sqrtf(xn);

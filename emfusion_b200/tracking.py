@@ -186,8 +186,8 @@ class Tracker:
                     s.firstIteration = False
                 try:
                     s.x = np.linalg.solve(s.A + np.float32(s.mu) * np.eye(6, dtype=np.float32), s.b).astype(np.float32)
-                except np.linalg.LinAlgError:   # cv::solve returns false and leaves x: the step is then the old one
-                    pass
+                except np.linalg.LinAlgError:   # cv::solve returns false and zeroes x: the step test below then ends the run
+                    s.x = np.zeros(6, dtype=np.float32)
                 if float(np.linalg.norm(s.x)) < s.vol.params.eps2 * (float(np.linalg.norm(se3_log(s.rel_pose_CO))) + s.vol.params.eps2):
                     s.trackingConverged = True
                     continue

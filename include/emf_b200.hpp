@@ -219,6 +219,7 @@ public:
         for (int k = 0; k < 9; ++k) rel_pose_CO.R[k] = (float)st.R[k];
         for (int k = 0; k < 3; ++k) rel_pose_CO.t[k] = (float)st.t[k];
         trackingConverged = st.converged != 0;
+        trackIterations = st.iterations;
         return st.iterations;
     }
     // :333-338
@@ -235,6 +236,7 @@ public:
 
     TSDFParams params;
     bool trackingConverged = false;
+    int trackIterations = 0;          // iterations of the last track() (diagnostic)
 
 protected:
     emf_volume cVolume(const float* fg) const {
@@ -421,6 +423,12 @@ public:
     EMFusion(const EMFusion&) = delete;
     EMFusion& operator=(const EMFusion&) = delete;
     ~EMFusion() { if (engine_) emf_engine_destroy(engine_); }
+
+    // Anything that re-allocates a volume's arrays behind the engine's back (ObjTSDF::resize as called by updateObj,
+    // src/core/EMFusion.cpp:1010-1018) must be followed by invalidate(): the next frame re-submits the volume table.
+    void invalidate() { dirty_ = true; }
+    // updateObj's resize (:1010-1018) on an object owned by this instance
+    template <class... A> void resizeObj(size_t i, A&&... a) { objects.at(i)->resize(std::forward<A>(a)...); dirty_ = true; }
 
     // createObj (:908-920, the volume part): a new object volume; its association image starts at 1
     ObjTSDF& createObj(const Affine& obj_pose, float voxelSize) {
