@@ -279,9 +279,10 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         const bool use_cert = e->use_cert < 0 ? env_cert : e->use_cert != 0;
         std::vector<emf_image> r_ray(e->v_ray), r_vert(e->v_vert), r_norm(e->v_norm), r_mask(e->v_mask);
         if (e->has_bg && e->bg_target[0].ptr) { r_ray[0] = e->bg_target[0]; r_vert[0] = e->bg_target[1]; r_norm[0] = e->bg_target[2]; r_mask[0] = e->bg_target[3]; }
-        rc = emf_raycast_volumes_ws(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), r_ray.data(), r_vert.data(),
-                                    r_norm.data(), r_mask.data(), nullptr, use_cert ? e->ray_ws : nullptr,
-                                    use_cert ? e->ray_ws_bytes : 0, stream);
+        static const bool env_sched = [] { const char* v = getenv("EMF_RAY_SCHED"); return !(v && v[0] == '0'); }();
+        rc = emf_raycast_volumes_opt(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), r_ray.data(), r_vert.data(),
+                                     r_norm.data(), r_mask.data(), nullptr, e->ray_ws, e->ray_ws_bytes,
+                                     (use_cert ? EMF_RAY_CERTIFICATE : 0u) | (env_sched ? EMF_RAY_SCHEDULE : 0u), stream);
         if (rc != EMF_OK) return rc;
     }
     if (flags & (EMF_FRAME_COMPOSITE | EMF_FRAME_COMPOSITE_NOBG)) {

@@ -231,7 +231,7 @@ EMF_API int emf_raycast_volumes(int n_vol, const emf_volume* vols, const emf_pos
                         emf_stream_t stream);
 
 /* emf_raycast_volumes with a workspace of emf_raycast_workspace_bytes(W, H) bytes (device memory, 16-byte aligned,
- * contents irrelevant).  With it, a pre-pass (k_ray_certify) certifies, per 8 x 4 pixel tile and per slab of voxels along
+ * zeroed once before its first use).  With it, a pre-pass (k_ray_certify) certifies, per 8 x 4 pixel tile and per slab of voxels along
  * the volume axis the camera looks along, that every voxel a march sample of the tile can touch there holds exactly +1;
  * rays of the first volume without fg_probs (the background) then skip those samples -- no-ops of the reference's march
  * loop, src/core/cuda/TSDF.cu:523-572 -- in closed form.  Same results, bit for bit (stats[1], [2] count what was skipped);
@@ -241,6 +241,19 @@ EMF_API int emf_raycast_volumes_ws(int n_vol, const emf_volume* vols, const emf_
                            const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
                            void* workspace, size_t workspace_bytes, emf_stream_t stream);
 EMF_API size_t emf_raycast_workspace_bytes(int width, int height);
+/* The same with the workspace's two uses selected separately (emf_raycast_volumes_ws = both).  The workspace must be ZEROED once
+ * before its first use and then kept between frames.
+ * EMF_RAY_CERTIFICATE: the pre-pass above.
+ * EMF_RAY_SCHEDULE: the tiles (16 x 8 pixels) of the FIRST volume are marched longest first, in the order of the cost (march
+ *   iterations of the tile's longest ray) the previous call recorded in the workspace; the blocks of the other volumes follow
+ *   (EMF_RAY_FRONT=<percent> places them after that share of the first volume's tiles instead).  The launch otherwise ends with a few SMs marching the longest rays (rim of the frustum, shadow seams:
+ *   3-4 x the median) that happen to start last.  Scheduling only: no result depends on the order. */
+#define EMF_RAY_CERTIFICATE 1u
+#define EMF_RAY_SCHEDULE 2u
+EMF_API int emf_raycast_volumes_opt(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
+                            const int* rects, const emf_image* ray_out, const emf_image* vert_out,
+                            const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
+                            void* workspace, size_t workspace_bytes, unsigned options, emf_stream_t stream);
 
 /* Compositing of emf::EMFusion::raycast, src/core/EMFusion.cpp:760-794, in one launch.
  * Objects i = 0..n_obj-1 in list order with ids[i]; background images bg_*.

@@ -1,7 +1,8 @@
 """GPU diagnostic: per-warp timeline of the whole frame's raycast launch (bench scene): who runs when, for how long."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["EMF_RAY_HIST"] = "2"
+if os.environ.get("EMF_RAY_TIMELINE") != "1":
+    os.environ["EMF_RAY_HIST"] = "2"
 from emfusion_b200 import ops
 from emfusion_b200.engine import EMFusionEngine
 from emfusion_b200.poses import rel_pose_CO
@@ -40,11 +41,12 @@ mask = [eng.bg_mask] + [eng.obj_modelSegmentation[o.id] for o in eng.objects]
 cv = [v.c_volume(with_grads=True) for v in vols]
 ws = ops.raycastWorkspace(w, h, dev)
 nblk = sum(((r[2] - r[0] + 15) // 16) * ((r[3] - r[1] + 7) // 8) for r in rects)
-for name, wk in (("plain", None), ("cert", ws)):
-    for rep in range(2):
+TL = os.environ.get("EMF_RAY_TIMELINE") == "1"
+for name, wk in (("plain", None), ("sched", ws)) + (() if TL else (("cert", ws),)):
+    for rep in range(3):
         st = torch.zeros(32 + 4 * 4 * nblk, dtype=torch.int64, device=dev)
         torch.cuda.synchronize()
-        ops.raycastVolumes(cv, T, prm.intr, rects, ray, vert, norm, mask, stats=st, workspace=wk)
+        ops.raycastVolumes(cv, T, prm.intr, rects, ray, vert, norm, mask, stats=st, workspace=wk, certificate=name == "cert")
         torch.cuda.synchronize()
     a = st.cpu().numpy()
     rec = a[32:].reshape(-1, 4)

@@ -103,3 +103,29 @@ def test_certificate_skips_most_free_space(oracle, cuda_dev):
     assert_bits(norm, o["norm"], "norm")
     assert int(o["steps"][0]) == int(s[0] + s[1])
     assert int(o["mask"].sum()) > 0.5 * w * h
+
+
+def test_schedule_changes_nothing(cuda_dev):
+    """longest-first tile order (k_ray_schedule): the second and third call run in the order the previous one recorded; every
+    output of every volume stays bit-identical to the row-major launch"""
+    w, h = 320, 240
+    scene = Scene(n_objects=3, width=w, height=h, seed=5)
+    pose = Affine.translation([0, 0, 2.56])
+    v, t_g, w_g, voxel, trunc = integrated_volume((128, 128, 128), scene, 4, w, h, pose)
+    v2, *_ = integrated_volume((96, 64, 80), scene, 3, w, h, pose)
+    ws = ops.raycastWorkspace(w, h, DEV)
+    z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=DEV)
+    for f in (4, 5, 6):
+        T = rel_pose_CO(scene.cam_pose(f), pose)
+        rects = [[0, 0, w, h], [40, 30, 290, 200]]
+        outs = []
+        for wk in (None, ws):
+            ray, vert, norm, mask = [z(h, w), z(h, w)], [z(h, w, 3), z(h, w, 3)], [z(h, w, 3), z(h, w, 3)], [z(h, w, dt=torch.uint8), z(h, w, dt=torch.uint8)]
+            ops.raycastVolumes([v, v2], [T, T], scene.K, rects, ray, vert, norm, mask, workspace=wk, certificate=False)
+            outs.append(ray + vert + norm + mask)
+        for a, b in zip(*outs):
+            assert_bits(b, a.cpu().numpy(), f"frame {f}")
+        hdr = ws[-(4 + 2 * 20 * 30) * 4:].view(torch.int32)[:4].cpu().numpy()
+        assert hdr[0] == 20 * 30       # the order for the next call is in place
+        order = ws[-(4 + 2 * 20 * 30) * 4:].view(torch.int32)[4:4 + 600].cpu().numpy()
+        assert np.array_equal(np.sort(order), np.arange(600))
