@@ -225,6 +225,27 @@ public:
     // :333-338
     void syncTrack(Affine& cam_pose) { cam_pose = pose * rel_pose_CO; }
 
+    // getMesh (:356-373; ObjTSDF :247-268 through descriptor()'s fgProbs): marching cubes over the voxels with weight > 0
+    // (objects: and fgProb > 0.5); cv::viz::Mesh's three arrays on the host
+    struct Mesh { std::vector<float> cloud, normals; std::vector<int32_t> polygons; };
+    Mesh getMesh(cudaStream_t stream = nullptr) const {
+        const emf_volume v = descriptor();
+        const size_t wsb = emf_mesh_workspace_bytes(v.res);
+        DeviceArray<unsigned char> ws(wsb);
+        ok(emf_mesh_count(&v, ws.data(), wsb, (emf_stream_t)stream), "emf_mesh_count");
+        int32_t counts[2] = {0, 0};
+        cu(cudaMemcpyAsync(counts, ws.data(), sizeof counts, cudaMemcpyDeviceToHost, stream), "mesh counts");
+        cu(cudaStreamSynchronize(stream), "sync");
+        if (counts[0] < 0 || counts[1] < 0) throw std::runtime_error("mesh larger than 2^31 - 1 elements");
+        Mesh m;
+        if (counts[0] == 0) return m;
+        DeviceArray<float> dv((size_t)3 * counts[0]), dn((size_t)3 * counts[0]);
+        DeviceArray<int32_t> dt((size_t)counts[1]);
+        ok(emf_mesh_extract(&v, ws.data(), wsb, dv.data(), dn.data(), dt.data(), (emf_stream_t)stream), "emf_mesh_extract");
+        cu(cudaStreamSynchronize(stream), "sync");
+        m.cloud = dv.download(); m.normals = dn.download(); m.polygons = dt.download();
+        return m;
+    }
     virtual std::vector<float> getTSDF() const { return tsdfVol.download(); }
     virtual std::vector<float> getWeightsVol() const { return tsdfWeights.download(); }
     // the volume as the C ABI sees it (for the batched / engine entry points)

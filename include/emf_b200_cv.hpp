@@ -156,12 +156,24 @@ public:
     void getHuberWeights(cv::Mat& weights) const { weights = cv::Mat(); }        // (diagnostic images of saveOutput: not kept by the fused tracker)
     void getTrackingWeights(cv::Mat& weights) const { weights = cv::Mat(); }
 
-    virtual cv::viz::Mesh getMesh() { return cv::viz::Mesh(); }
+    virtual cv::viz::Mesh getMesh() { return meshOf(*impl_); }
     virtual cv::Mat getTSDF() const { return volumeMat(impl_->getTSDF()); }
     virtual cv::Mat getWeightsVol() const { return volumeMat(impl_->getWeightsVol()); }
 
 protected:
     explicit TSDF(std::shared_ptr<emfb::TSDF> impl, const ::emf::TSDFParams& p) : params(p), impl_(std::move(impl)) {}
+    static cv::viz::Mesh meshOf(const emfb::TSDF& t) {          // 1 x n CV_32FC3 / CV_32FC3 / 1 x m CV_32SC1, as the reference downloads them
+        const emfb::TSDF::Mesh h = t.getMesh();
+        cv::viz::Mesh m;
+        if (h.cloud.empty()) return m;
+        m.cloud = cv::Mat(1, (int)(h.cloud.size() / 3), CV_32FC3);
+        m.normals = cv::Mat(1, (int)(h.normals.size() / 3), CV_32FC3);
+        m.polygons = cv::Mat(1, (int)h.polygons.size(), CV_32SC1);
+        std::memcpy(m.cloud.ptr<float>(), h.cloud.data(), h.cloud.size() * sizeof(float));
+        std::memcpy(m.normals.ptr<float>(), h.normals.data(), h.normals.size() * sizeof(float));
+        std::memcpy(m.polygons.ptr<int>(), h.polygons.data(), h.polygons.size() * sizeof(int32_t));
+        return m;
+    }
     cv::Mat volumeMat(const std::vector<float>& v) const {
         const emfb::Vec3i r = impl_->getVolumeRes();
         cv::Mat m(r[1] * r[2], r[0], CV_32FC1);          // rows = Ry * Rz, cols = Rx (src/core/TSDF.cpp:35-42)
@@ -257,7 +269,7 @@ public:
         for (size_t i = 1; i < classProbs.size(); ++i) if (classProbs[i] > classProbs[best]) best = (int)i;
         return best;
     }
-    virtual cv::viz::Mesh getMesh() override { return cv::viz::Mesh(); }
+    virtual cv::viz::Mesh getMesh() override { return meshOf(*impl_); }     // (descriptor() carries fgProbs: the fgVolMask test)
     cv::Mat getFgProbVol() { return volumeMat(obj()->getFgProbVol()); }
     cv::cuda::GpuMat getFgVolMask() { return cv::cuda::GpuMat(); }      // (not materialised: the fgProb > 0.5 test runs inside the raycast)
 

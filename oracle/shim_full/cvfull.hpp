@@ -17,6 +17,7 @@
 #define CV_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << CV_CN_SHIFT))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
 #define CV_32FC2 CV_MAKETYPE(CV_32F, 2)
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
 #define CV_Assert(expr) do { if (!(expr)) throw std::string("CV_Assert: " #expr); } while (0)

@@ -230,6 +230,16 @@ int main() {
         CHECK(std::fabs(emf.pose.t[2]) < 0.003f && emf.frameCount == 4, "EMFusion tracking: z %.4f (perturbed by 0.01)", emf.pose.t[2]);
         CHECK(emf.background.trackIterations > 0, "EMFusion tracking: %d iterations", emf.background.trackIterations);
     }
+    {
+        // getMesh: a closed-form check -- every polygon is (3, a, b, c) with indices inside the vertex list, vertices inside the volume
+        const emfb::TSDF::Mesh m = bg.getMesh();
+        bool okm = !m.cloud.empty() && m.cloud.size() == m.normals.size() && m.polygons.size() % 4 == 0 && !m.polygons.empty();
+        const int nv = (int)(m.cloud.size() / 3);
+        for (size_t k = 0; okm && k < m.polygons.size(); k += 4)
+            okm = m.polygons[k] == 3 && m.polygons[k + 1] >= 0 && m.polygons[k + 1] < nv && m.polygons[k + 2] >= 0 && m.polygons[k + 2] < nv &&
+                  m.polygons[k + 3] >= 0 && m.polygons[k + 3] < nv;
+        CHECK(okm, "getMesh: %zu vertices, %zu polygon ints", m.cloud.size() / 3, m.polygons.size());
+    }
     if (fails == 0) std::printf("host mirror ok\n");
     return fails ? 1 : 0;
 }
