@@ -364,10 +364,18 @@ def run_ours(args):
         for s in range(n_stage):
             step(f, timed=True); f += 1
         ms_stage = np.array(eng.stage_ms())
+    stage_detail = None
     if world > 1:       # per phase, the slowest rank (the phases of different ranks overlap: they need not add up to the frame)
         ts = torch.tensor(ms_stage, dtype=torch.float64, device=dev)
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         ms_stage = ts.cpu().numpy()
+        det = getattr(eng, "stage_detail", None)
+        if det:         # every rank's own phases (rank 0 merges, the others wait for it)
+            keys = list(det)
+            mine = torch.tensor([det[k] for k in keys], dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            stage_detail = {"phases": keys, "per_rank_ms": [[round(float(x), 4) for x in t.cpu().numpy()] for t in allr]}
 
     # ---- e2e: host depth in (pinned), composited result out (pinned), every step, through the public host-facing API
     #      (HostFramePipeline: upload of frame n+1 and download of frame n overlap the kernels; every frame's depth
@@ -477,6 +485,7 @@ def run_ours(args):
             "exchange_errors": (eng._px.check_errors() if getattr(eng, "_px", None) is not None else 0),
             "parity_vs_n1": parity,
             "clocks": clocks,
+            "stages_per_rank": stage_detail,
             "roofline": roof,
         }
         if not args.no_cpu_baseline and world == 1:

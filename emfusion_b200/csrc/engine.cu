@@ -42,6 +42,7 @@ struct emf_engine {
     cudaStream_t up = nullptr, down = nullptr;
     long long host_count = 0;
     int use_cert = -1;            // ray-space certificate for the background's raycast: -1 = EMF_RAY_CERT decides
+    int use_wide = -1;            // four lanes per background ray (EMF_RAY_WIDE): -1 = the environment variable decides
     const int32_t* gate_src = nullptr;   // nullptr: the integrate is gated by vis_count[list position]; else by gate_src[gate_idx[i]]
     std::vector<int> gate_idx;
     std::vector<emf_image> a_img, v_ray, v_vert, v_norm, v_mask;
@@ -279,10 +280,13 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         const bool use_cert = e->use_cert < 0 ? env_cert : e->use_cert != 0;
         std::vector<emf_image> r_ray(e->v_ray), r_vert(e->v_vert), r_norm(e->v_norm), r_mask(e->v_mask);
         if (e->has_bg && e->bg_target[0].ptr) { r_ray[0] = e->bg_target[0]; r_vert[0] = e->bg_target[1]; r_norm[0] = e->bg_target[2]; r_mask[0] = e->bg_target[3]; }
+        static const bool env_wide = [] { const char* v = getenv("EMF_RAY_WIDE"); return v && v[0] == '1'; }();
+        const bool use_wide = e->use_wide < 0 ? env_wide : e->use_wide != 0;
         static const bool env_sched = [] { const char* v = getenv("EMF_RAY_SCHED"); return !(v && v[0] == '0'); }();
         rc = emf_raycast_volumes_opt(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), r_ray.data(), r_vert.data(),
                                      r_norm.data(), r_mask.data(), nullptr, e->ray_ws, e->ray_ws_bytes,
-                                     (use_cert ? EMF_RAY_CERTIFICATE : 0u) | (env_sched ? EMF_RAY_SCHEDULE : 0u), stream);
+                                     (use_cert ? EMF_RAY_CERTIFICATE : 0u) | (env_sched ? EMF_RAY_SCHEDULE : 0u) |
+                                         (use_wide && !use_cert ? EMF_RAY_WIDE : 0u), stream);
         if (rc != EMF_OK) return rc;
     }
     if (flags & (EMF_FRAME_COMPOSITE | EMF_FRAME_COMPOSITE_NOBG)) {
@@ -453,6 +457,7 @@ extern "C" EMF_API int emf_engine_set_option(emf_engine* e, int option, int valu
     if (!e) return EMF_ERR_INVALID;
     switch (option) {
     case EMF_OPT_RAY_CERTIFICATE: e->use_cert = value; return EMF_OK;
+    case EMF_OPT_RAY_WIDE: e->use_wide = value; return EMF_OK;
     default: return EMF_ERR_INVALID;
     }
 }

@@ -878,7 +878,9 @@ __global__ void __launch_bounds__(kRayThreads, EMF_CERT_MINB) k_raycast_cert(con
     const int yr = V.y0 + ty * kWarpH + warp;
     const bool valid = xr < V.x1 && yr < V.y1;
     __shared__ uint32_t s_cert[2 * kCertWords];   // [0, kCertWords): all +1 ; [kCertWords, 2 kCertWords): all 0
-    if (warp == 0) {
+    if (warp == 0 && !V.cert) {          // (EMF_RAY_WIDE: the four-lane march without a certificate -- nothing is ever skipped)
+        if (lane < 2 * kCertWords) s_cert[lane] = 0u;
+    } else if (warp == 0) {
         // the tile's slab bits, one word per 32 slabs (lane = slab of the word, bit = the tile inside its group of 32)
         const int ti = ty * V.cert_txc + tx;
         const int g = ti >> 5, tb = ti & 31;
@@ -1553,12 +1555,19 @@ extern "C" EMF_API int emf_raycast_volumes_opt(int n_vol, const emf_volume* vols
     for (int i = 0; i < n_vol; ++i) jump = jump || P.v[i].bmap != nullptr;
     const cudaStream_t cs = (cudaStream_t)stream;
     int n_rest = n_vol;
-    if (!jump && workspace && ((uintptr_t)workspace & 15) == 0 && (options & EMF_RAY_CERTIFICATE)) {
+    if (!jump && (((options & EMF_RAY_CERTIFICATE) && workspace && ((uintptr_t)workspace & 15) == 0) || (options & EMF_RAY_WIDE))) {
         // ray-space certificate for the first volume without a foreground mask (the background: long rays through free
         // space); that volume gets its own launch of the certified march, the others follow in the plain one
         for (int i = 0; i < n_vol; ++i) {
             if (P.v[i].fg_probs) continue;
-            if (launch_certify(P.v[i], K, workspace, workspace_bytes, cs)) {
+            bool wide = false;
+            if ((options & EMF_RAY_WIDE) && !(options & EMF_RAY_CERTIFICATE) && !P.v[i].bmap && !P.v[i].tube && P.v[i].x1 > P.v[i].x0 && P.v[i].y1 > P.v[i].y0) {
+                RayVol& d = P.v[i];
+                d.tiles_y = (d.y1 - d.y0 + kTileH - 1) / kTileH;
+                d.cert = nullptr; d.cert_G = 0; d.cert_txc = 2 * d.tiles_x; d.cert_axis = 0; d.cert_sign = 1; d.cert_L = 0; d.cert_nw = 0;
+                wide = true;
+            }
+            if (wide || ((options & EMF_RAY_CERTIFICATE) && launch_certify(P.v[i], K, workspace, workspace_bytes, cs))) {
                 static CertRayParams Pc;
                 Pc.v = P.v[i];
                 Pc.v.first_block = 0;

@@ -470,12 +470,18 @@ class NativeEngine(EMFusionEngine):
                 raise _lib.EmfError("no timed frame")
             log[-1]["end"].synchronize()
             out = np.zeros(3)
+            detail = np.zeros(5)
             for m in log:       # mean over the timed frames issued since the last call
                 dt = lambda a, b: m[a].elapsed_time(m[b]) if a in m and b in m else 0.0
+                detail += [dt("start", "assoc"), dt("assoc", "ray_local"), dt("ray_local", "int_bg"), dt("int_bg", "merge"), dt("merge", "end")]
                 if "ray_local" in m:
                     out += [dt("start", "assoc"), dt("assoc", "ray_local") + dt("int_bg", "merge"), dt("ray_local", "int_bg") + dt("merge", "end")]
                 else:
                     out += [dt("start", "assoc"), 0.0, dt("assoc", "end")]
+            # this rank's phases one by one: association + normaliser exchange, local raycast + pre-composite, background
+            # integrate, merge (rank 0) / wait for it, objects' integrate
+            self.stage_detail = dict(zip(("association", "raycast_local", "integrate_background", "merge_or_wait", "integrate_objects"),
+                                         (float(x) for x in detail / len(log))))
             return [float(x) for x in out / len(log)]
         check(self._L.emf_engine_stage_ms(self._e, self._stage), "emf_engine_stage_ms")
         return [float(x) for x in self._stage]

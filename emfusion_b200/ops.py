@@ -216,16 +216,18 @@ def raycastWorkspace(width, height, device):
 
 
 def raycastVolumes(vols, rel_poses_CO, intr, rects, ray_out, vert_out, norm_out, mask_out, stream=None, stats=None,
-                   workspace=None, certificate=True, schedule=True):
+                   workspace=None, certificate=True, schedule=True, wide=False):
     """workspace (raycastWorkspace): certificate = the background's rays skip certified free-space samples, schedule = the first
-    volume's tiles are marched longest first by the previous call's cost (same results either way)."""
+    volume's tiles are marched longest first by the previous call's cost; wide = four lanes per background ray (no workspace
+    needed).  Same results whatever the options."""
     if stats is not None and (stats.numel() < 8 or stats.element_size() != 8):
         raise _lib.EmfError("raycast stats must be a tensor of at least 8 64-bit counters")
     flat = (C.c_int * (4 * len(vols)))(*[int(v) for r in rects for v in r]) if rects is not None else None
     check(_lib.lib().emf_raycast_volumes_opt(len(vols), _vol_array(vols), poses(rel_poses_CO), _f9(intr), flat,
                                              images(ray_out), images(vert_out), images(norm_out), images(mask_out),
                                              _ptr(stats), _ptr(workspace), workspace.numel() if workspace is not None else 0,
-                                             (1 if certificate else 0) | (2 if schedule else 0), _stream(stream)), "raycastVolumes")
+                                             (1 if certificate else 0) | (2 if schedule else 0) | (4 if wide else 0), _stream(stream)),
+          "raycastVolumes")
     _count("raycastVolumes", 1 if workspace is None else 2)
 
 

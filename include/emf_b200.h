@@ -250,6 +250,9 @@ EMF_API size_t emf_raycast_workspace_bytes(int width, int height);
  *   3-4 x the median) that happen to start last.  Scheduling only: no result depends on the order. */
 #define EMF_RAY_CERTIFICATE 1u
 #define EMF_RAY_SCHEDULE 2u
+#define EMF_RAY_WIDE 4u          /* the first volume without fg_probs is marched with four lanes per ray (eight samples of a ray in
+                                  * flight; needs no workspace): shortens the longest dependent chain where a GPU traces a band of
+                                  * the frame and is otherwise idle (multi-GPU), costs instructions where it is not */
 EMF_API int emf_raycast_volumes_opt(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
                             const int* rects, const emf_image* ray_out, const emf_image* vert_out,
                             const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
@@ -539,6 +542,7 @@ EMF_API int emf_engine_set_gate_source(emf_engine* e, const int32_t* counts, con
 /* Engine options.  EMF_OPT_RAY_CERTIFICATE: 1 = the background's raycast uses the ray-space certificate and the
  * four-lanes-per-ray march (emf_raycast_volumes_ws), 0 = the plain march, -1 = the environment variable EMF_RAY_CERT decides. */
 #define EMF_OPT_RAY_CERTIFICATE 1
+#define EMF_OPT_RAY_WIDE 2          /* 1 = four lanes per background ray (EMF_RAY_WIDE above), 0 = off, -1 = environment variable EMF_RAY_WIDE */
 EMF_API int emf_engine_set_option(emf_engine* e, int option, int value);
 EMF_API int emf_engine_normalise_from_parts(emf_engine* e, int n_parts, const float* const* parts, const uint32_t* flags,
                                     uint32_t value, uint32_t* err, double timeout_s, emf_stream_t stream);

@@ -129,3 +129,20 @@ def test_schedule_changes_nothing(cuda_dev):
         assert hdr[0] == 20 * 30       # the order for the next call is in place
         order = ws[-(4 + 2 * 20 * 30) * 4:].view(torch.int32)[4:4 + 600].cpu().numpy()
         assert np.array_equal(np.sort(order), np.arange(600))
+
+
+def test_wide_march_changes_nothing(cuda_dev):
+    """EMF_RAY_WIDE: four lanes per background ray, no certificate -- same bits as one ray per lane"""
+    w, h = 320, 240
+    scene = Scene(n_objects=3, width=w, height=h, seed=7)
+    pose = Affine.translation([0, 0, 2.56])
+    v, *_ = integrated_volume((128, 128, 128), scene, 5, w, h, pose)
+    z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=DEV)
+    for f in (5, 9):
+        T = rel_pose_CO(scene.cam_pose(f), pose)
+        for rect in ([0, 0, w, h], [33, 17, 300, 201]):
+            a = cast(v, T, scene.K, w, h, rect, None)
+            ray, vert, norm, mask = [z(h, w)], [z(h, w, 3)], [z(h, w, 3)], [z(h, w, dt=torch.uint8)]
+            ops.raycastVolumes([v], [T], scene.K, [rect], ray, vert, norm, mask, certificate=False, schedule=False, wide=True)
+            for x, y, what in zip(a, (ray[0], vert[0], norm[0], mask[0]), ("ray", "vert", "norm", "mask")):
+                assert_bits(y, x.cpu().numpy(), f"frame {f} rect {rect} {what}")
