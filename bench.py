@@ -382,6 +382,14 @@ def run_ours(args):
     #      crosses PCIe once and every frame's result is read back once, all inside the timed region)
     from emfusion_b200.pipeline import HostFramePipeline
     pipe = HostFramePipeline(eng, download=(rank == 0))
+    prev = None
+    for s in range(max(args.warmup, 3)):     # W untimed frames through the same entry (first use of its slots, streams and caches)
+        i = f % N_STREAM_FRAMES
+        tk = pipe.submit(d_pin[i], cams[i], oposes[i]); f += 1
+        if prev is not None:
+            pipe.result(prev)
+        prev = tk
+    pipe.result(prev)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -395,6 +403,26 @@ def run_ours(args):
     pipe.result(prev)
     e1.record()
     barrier()
+    if os.environ.get("EMF_BENCH_E2E_DIAG") == "1" and world == 1:      # diagnostics (stderr): where the e2e loop's time goes
+        def loop(p, wait):
+            nonlocal f
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pv = None
+            for _ in range(args.steps):
+                i = f % N_STREAM_FRAMES
+                k = p.submit(d_pin[i], cams[i], oposes[i]); f += 1
+                if wait and pv is not None:
+                    p.result(pv)
+                pv = k
+            p.result(pv)
+            b.record()
+            barrier()
+            return a.elapsed_time(b) / args.steps
+        print("e2e diag: e2e again %.4f, host never waits inside the loop %.4f, no download %.4f, no download + no wait %.4f ms" % (
+            loop(pipe, True), loop(pipe, False), loop(HostFramePipeline(eng, download=False), True),
+            loop(HostFramePipeline(eng, download=False), False)), file=sys.stderr)
     t = torch.tensor([ms_step, e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -84,6 +84,7 @@ _SIGS = {
                                _P(Image), _P(Image), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_raycast_volumes_opt": [C.c_int, _P(Volume), _P(Pose), _P(C.c_float), _P(C.c_int), _P(Image), _P(Image),
                                 _P(Image), _P(Image), C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p],
+    "emf_raycast_schedule_update": [C.c_int, C.c_int, _P(C.c_int), C.c_void_p, C.c_size_t, C.c_void_p],
     "emf_raycast_composite": [C.c_int, _P(C.c_int), _P(C.c_int), _P(Image), _P(Image), _P(Image), _P(Image),
                               _P(Image), _P(Image), _P(Image), _P(Image), C.c_int, _P(Image), _P(Image), _P(Image),
                               _P(Image), C.c_void_p, C.c_void_p],

@@ -56,6 +56,8 @@ struct emf_engine {
     cudaEvent_t vis_ready = nullptr;
     cudaStream_t aux = nullptr;        // the association runs here, next to the raycast (both only read the volumes)
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t ray_done = nullptr, sched_done = nullptr;   // the raycast's tile sort for the next frame runs on aux, behind the raycast
+    bool sched_pending = false;
     cudaStream_t aux2 = nullptr;       // the integrate's preparation (depth pyramid, brick classification)
     cudaEvent_t fork2 = nullptr, join2 = nullptr;
     bool timed_valid = false;
@@ -109,6 +111,8 @@ extern "C" EMF_API emf_engine* emf_engine_create(const emf_engine_config* cfg) {
     ok = ok && cudaStreamCreateWithFlags(&e->aux, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->ray_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->sched_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&e->aux2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->fork2, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&e->join2, cudaEventDisableTiming) == cudaSuccess;
@@ -126,6 +130,8 @@ extern "C" EMF_API void emf_engine_destroy(emf_engine* e) {
     if (e->vis_ready) cudaEventDestroy(e->vis_ready);
     if (e->fork) cudaEventDestroy(e->fork);
     if (e->join) cudaEventDestroy(e->join);
+    if (e->ray_done) cudaEventDestroy(e->ray_done);
+    if (e->sched_done) cudaEventDestroy(e->sched_done);
     for (auto& h : e->hs) {
         if (h.depth_dev) cudaFree(h.depth_dev);
         if (h.seg_dev) cudaFree(h.seg_dev);
@@ -283,11 +289,21 @@ extern "C" EMF_API int emf_engine_frame(emf_engine* e, const emf_image* depth, c
         static const bool env_wide = [] { const char* v = getenv("EMF_RAY_WIDE"); return v && v[0] == '1'; }();
         const bool use_wide = e->use_wide < 0 ? env_wide : e->use_wide != 0;
         static const bool env_sched = [] { const char* v = getenv("EMF_RAY_SCHED"); return !(v && v[0] == '0'); }();
+        const bool sched = env_sched && !use_cert && !use_wide;
+        if (e->sched_pending) { cudaStreamWaitEvent(s, e->sched_done, 0); e->sched_pending = false; }
         rc = emf_raycast_volumes_opt(n, e->vols.data(), T_co, e->cfg.K, e->rects.data(), r_ray.data(), r_vert.data(),
                                      r_norm.data(), r_mask.data(), nullptr, e->ray_ws, e->ray_ws_bytes,
-                                     (use_cert ? EMF_RAY_CERTIFICATE : 0u) | (env_sched ? EMF_RAY_SCHEDULE : 0u) |
+                                     (use_cert ? EMF_RAY_CERTIFICATE : 0u) | (sched ? (EMF_RAY_SCHEDULE | EMF_RAY_SCHEDULE_DEFER) : 0u) |
                                          (use_wide && !use_cert ? EMF_RAY_WIDE : 0u), stream);
         if (rc != EMF_OK) return rc;
+        if (sched) {      // the sort of the next frame's tile order: on the side stream, under the composite / integrate
+            cudaEventRecord(e->ray_done, s);
+            cudaStreamWaitEvent(e->aux, e->ray_done, 0);
+            rc = emf_raycast_schedule_update(w, h, e->rects.data(), e->ray_ws, e->ray_ws_bytes, (emf_stream_t)e->aux);
+            if (rc != EMF_OK) return rc;
+            cudaEventRecord(e->sched_done, e->aux);
+            e->sched_pending = true;
+        }
     }
     if (flags & (EMF_FRAME_COMPOSITE | EMF_FRAME_COMPOSITE_NOBG)) {
         // (force flags -- objects created since the last integrate, reference src/core/EMFusion.cpp:550,918: createObj puts

@@ -745,25 +745,60 @@ __global__ void __launch_bounds__(kRayThreads, EMF_RAY_MINB) k_raycast(const __g
     }
 }
 
-// counting sort of the first volume's tiles by the cost the launch just recorded, longest first, for the NEXT launch
+// STABLE counting sort of the first volume's tiles by the cost the launch just recorded, longest class first, for the NEXT
+// launch.  Eight coarse classes (64 pair iterations each) and row-major order inside a class: tiles that run at the same
+// time stay neighbours in the image and share their voxels in L1 / L2.  One CTA; a thread owns a contiguous chunk of tiles.
+constexpr int kSchedClasses = 8;
+__device__ __forceinline__ int sched_class(uint32_t cost) { return kSchedClasses - 1 - (int)min((uint32_t)(kSchedClasses - 1), cost >> 6); }
 __global__ void __launch_bounds__(1024) k_ray_schedule(uint32_t* __restrict__ sched, int n, int n_max, int front_pct) {
-    __shared__ int hist[64], base[64];
+    __shared__ int warp_tot[kSchedClasses][32];
+    __shared__ int class_base[kSchedClasses];
     uint32_t* order = sched + 4;
     uint32_t* cost = sched + 4 + n_max;
-    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int i0 = min(n, tid * chunk), i1 = min(n, i0 + chunk);
+    int cnt[kSchedClasses];
+#pragma unroll
+    for (int k = 0; k < kSchedClasses; ++k) cnt[k] = 0;
+    for (int i = i0; i < i1; ++i) {
+        const int c = sched_class(cost[i]);
+#pragma unroll
+        for (int k = 0; k < kSchedClasses; ++k) cnt[k] += (c == k);
+    }
+    int pre[kSchedClasses];          // exclusive prefix of this thread inside its warp, per class
+#pragma unroll
+    for (int k = 0; k < kSchedClasses; ++k) {
+        int v = cnt[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+        pre[k] = v - cnt[k];
+        if (lane == 31) warp_tot[k][wid] = v;
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[63 - min(63u, cost[i] >> 4)], 1);
+    if (wid < kSchedClasses) {       // warp k scans the 32 warp totals of class k
+        const int t = warp_tot[wid][lane];
+        int v = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+        warp_tot[wid][lane] = v - t;
+        if (lane == 31) class_base[wid] = v;          // (the class total, turned into a base below)
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         int acc = 0;
-        for (int k = 0; k < 64; ++k) { base[k] = acc; acc += hist[k]; }
+        for (int k = 0; k < kSchedClasses; ++k) { const int t = class_base[k]; class_base[k] = acc; acc += t; }
         sched[0] = (uint32_t)n;
         sched[1] = (uint32_t)(((long long)n * front_pct) / 100);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int k = 63 - min(63u, cost[i] >> 4);
-        order[atomicAdd(&base[k], 1)] = (uint32_t)i;
+    int pos[kSchedClasses];
+#pragma unroll
+    for (int k = 0; k < kSchedClasses; ++k) pos[k] = class_base[k] + warp_tot[k][wid] + pre[k];
+    for (int i = i0; i < i1; ++i) {
+        const int c = sched_class(cost[i]);
+#pragma unroll
+        for (int k = 0; k < kSchedClasses; ++k) if (c == k) order[pos[k]++] = (uint32_t)i;
         cost[i] = 0;
     }
 }
@@ -1606,9 +1641,24 @@ extern "C" EMF_API int emf_raycast_volumes_opt(int n_vol, const emf_volume* vols
         } else {
             if (stats) k_raycast<true, 0><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
             else k_raycast<false, 0><<<(unsigned)blocks, kRayThreads, 0, cs>>>(P);
-            if (P.sched) k_ray_schedule<<<1, 1024, 0, cs>>>(P.sched, P.sched_n0, P.sched_max, sched_front_pct());
+            if (P.sched && !(options & EMF_RAY_SCHEDULE_DEFER)) k_ray_schedule<<<1, 1024, 0, cs>>>(P.sched, P.sched_n0, P.sched_max, sched_front_pct());
         }
     }
+    return launch_status();
+}
+
+extern "C" EMF_API int emf_raycast_schedule_update(int width, int height, const int rect0[4], void* workspace, size_t workspace_bytes,
+                                                   emf_stream_t stream) {
+    if (width <= 0 || height <= 0 || !workspace || ((uintptr_t)workspace & 15) != 0 || workspace_bytes < emf_raycast_workspace_bytes(width, height))
+        return EMF_ERR_INVALID;
+    const int x0 = rect0 ? max(rect0[0], 0) : 0, y0 = rect0 ? max(rect0[1], 0) : 0;
+    const int x1 = rect0 ? min(rect0[2], width) : width, y1 = rect0 ? min(rect0[3], height) : height;
+    if (x1 <= x0 || y1 <= y0) return EMF_OK;
+    const int64_t n0 = (int64_t)((x1 - x0 + kTileW - 1) / kTileW) * ((y1 - y0 + kTileH - 1) / kTileH);
+    const int64_t n_max = (int64_t)((width + kTileW - 1) / kTileW) * ((height + kTileH - 1) / kTileH);
+    if (n0 > n_max) return EMF_ERR_INVALID;
+    k_ray_schedule<<<1, 1024, 0, (cudaStream_t)stream>>>((uint32_t*)((char*)workspace + sched_offset(width, height)), (int)n0, (int)n_max,
+                                                        sched_front_pct());
     return launch_status();
 }
 

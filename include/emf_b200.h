@@ -253,10 +253,17 @@ EMF_API size_t emf_raycast_workspace_bytes(int width, int height);
 #define EMF_RAY_WIDE 4u          /* the first volume without fg_probs is marched with four lanes per ray (eight samples of a ray in
                                   * flight; needs no workspace): shortens the longest dependent chain where a GPU traces a band of
                                   * the frame and is otherwise idle (multi-GPU), costs instructions where it is not */
+#define EMF_RAY_SCHEDULE_DEFER 8u /* with EMF_RAY_SCHEDULE: record the costs and use the order, but leave the sort of the next order to
+                                  * emf_raycast_schedule_update (e.g. on a side stream, off the frame's critical path) */
 EMF_API int emf_raycast_volumes_opt(int n_vol, const emf_volume* vols, const emf_pose* T_co, const float K[9],
                             const int* rects, const emf_image* ray_out, const emf_image* vert_out,
                             const emf_image* norm_out, const emf_image* mask_out, uint64_t* stats,
                             void* workspace, size_t workspace_bytes, unsigned options, emf_stream_t stream);
+/* The sort that EMF_RAY_SCHEDULE_DEFER left out: turns the costs the last emf_raycast_volumes_opt call recorded into the order
+ * of the next one.  rect0 = the first volume's rectangle of that call (NULL = the whole frame).  Must run after that call and
+ * before the next one (the caller orders the streams). */
+EMF_API int emf_raycast_schedule_update(int width, int height, const int rect0[4], void* workspace, size_t workspace_bytes,
+                                emf_stream_t stream);
 
 /* Compositing of emf::EMFusion::raycast, src/core/EMFusion.cpp:760-794, in one launch.
  * Objects i = 0..n_obj-1 in list order with ids[i]; background images bg_*.
