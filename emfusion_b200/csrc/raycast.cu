@@ -302,27 +302,133 @@ __device__ __forceinline__ bool samp_resolve(Ray& r, const RayConst& c, const Co
     r.f = fn;
     return false;
 }
-// at most max_iters pair iterations (<= 2 max_iters samples); true = the ray is finished
+// The rare outcomes of a sample -- a sign change against the ray's previous value -- out of line: the back-face test
+// (TSDF.cu:532) and the front-face refinement (TSDF.cu:540-566) with their weight gathers.  The sample's position is
+// recomputed from its ray parameter (a pure function of it).  Returns true when the ray is finished; r.f is updated as the
+// reference's loop would (left alone on `continue`).
+#ifndef EMF_RAY_EVENT_INLINE
+#define EMF_RAY_EVENT_INLINE 1
+#endif
+template <bool STATS>
+#if EMF_RAY_EVENT_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+bool pair_event(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, float fn, unsigned long long* st) {
+    Samp q;
+    samp_pos(q, r.tcur, c, div_s, V);
+    if (r.f < 0.0f) {                       // (fn > 0) back face
+        if (STATS) ++st[3];
+        if (trilinear_weight(V, q.vx, q.vy, q.vz) > 0.0f) return true;
+    } else {                                // f > 0, fn < 0: front face (the step already follows fn)
+        const float ts = fsub(r.tcur, fdiv(fmul(r.f, r.step), fsub(fn, r.f)));
+        const float mx = fmul(c.dx, ts), my = fmul(c.dy, ts), mz = fmul(c.dz, ts);
+        const float sx = fadd(c.hxh, div_s(fadd(c.ox, mx)));
+        const float sy = fadd(c.hyh, div_s(fadd(c.oy, my)));
+        const float sz = fadd(c.hzh, div_s(fadd(c.oz, mz)));
+        if (out_of_thr(sx, sy, sz, V.thr2)) return false;
+        if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
+            r.hit = true; r.out_t = ts;
+            r.hvx = sx; r.hvy = sy; r.hvz = sz; r.hmx = mx; r.hmy = my; r.hmz = mz;
+            return true;
+        }
+    }
+    r.f = fn;
+    return false;
+}
+
+// one general march step out of line (ray ends, samples outside the march bounds, guarded divisions: a few per ray)
+template <bool STATS>
+__device__ __noinline__ bool march_step_slow(Ray& r, const RayConst& c, const RayVol& V, unsigned long long* st) {
+    const ConstDiv div_s(c.s);
+    return march_step<STATS>(r, c, div_s, V, V.rx, V.rx * V.ry, st);
+}
+
+// The march, two samples per iteration.  Fast path: both samples exist, both positions take the unguarded division, both lie
+// inside the march bounds (one combined test each) -- then 16 gathers are issued together, the second sample speculatively
+// (it is discarded if the first one ends the ray, keeps f, or changes the step).  Everything else goes through ONE general
+// step and the loop goes on.  Same samples, same arithmetic, same order as march_step.  true = the ray is finished.
 template <bool STATS>
 __device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
                                             unsigned long long* st, int max_iters = 0x7fffffff, int* iters = nullptr) {
+    const float* __restrict__ vol = V.tsdf;
     for (int it = 0; it < max_iters; ++it) {
         if (iters) *iters = it;
         if (STATS) { const unsigned am = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am) - 1) { ++st[4]; st[5] += __popc(am); } }
         const float t1 = fadd(r.tcur, r.step);
-        if (!(t1 <= c.tmax)) return true;
         const float t2 = fadd(t1, r.step);
+        const float n1x = ffma(c.dx, t1, c.ox), n1y = ffma(c.dy, t1, c.oy), n1z = ffma(c.dz, t1, c.oz);
+        const float n2x = ffma(c.dx, t2, c.ox), n2y = ffma(c.dy, t2, c.oy), n2z = ffma(c.dz, t2, c.oz);
+        bool fast = c.sane && t2 <= c.tmax &&
+                    fminf(fminf(fminf(fabsf(n1x), fabsf(n1y)), fabsf(n1z)), fminf(fminf(fabsf(n2x), fabsf(n2y)), fabsf(n2z))) > 5.5e-20f;
+        const float v1x = fadd(c.hxh, div_s.fast(n1x)), v1y = fadd(c.hyh, div_s.fast(n1y)), v1z = fadd(c.hzh, div_s.fast(n1z));
+        const float v2x = fadd(c.hxh, div_s.fast(n2x)), v2y = fadd(c.hyh, div_s.fast(n2y)), v2z = fadd(c.hzh, div_s.fast(n2z));
+        fast = fast && !out_of_thr(v1x, v1y, v1z, V.thr2) && !out_of_thr(v2x, v2y, v2z, V.thr2);
+        if (!fast) {
+            if (march_step_slow<STATS>(r, c, V, st)) return true;
+            continue;
+        }
+        // ---- base voxels, fractions, 16 gathers
+        const int l1x = __float2int_rz(v1x), l1y = __float2int_rz(v1y), l1z = __float2int_rz(v1z);
+        const int l2x = __float2int_rz(v2x), l2y = __float2int_rz(v2y), l2z = __float2int_rz(v2z);
+        const float* p1 = vol + (uint32_t)(l1z * plane + l1y * rx + l1x);
+        const float* p2 = vol + (uint32_t)(l2z * plane + l2y * rx + l2x);
+        const float a000 = __ldg(p1), a001 = __ldg(p1 + 1), a010 = __ldg(p1 + rx), a011 = __ldg(p1 + rx + 1);
+        const float a100 = __ldg(p1 + plane), a101 = __ldg(p1 + plane + 1), a110 = __ldg(p1 + plane + rx), a111 = __ldg(p1 + plane + rx + 1);
+        const float b000 = __ldg(p2), b001 = __ldg(p2 + 1), b010 = __ldg(p2 + rx), b011 = __ldg(p2 + rx + 1);
+        const float b100 = __ldg(p2 + plane), b101 = __ldg(p2 + plane + 1), b110 = __ldg(p2 + plane + rx), b111 = __ldg(p2 + plane + rx + 1);
+        float fn;
+        {
+            const float ax = fsub(v1x, (float)l1x), ay = fsub(v1y, (float)l1y), az = fsub(v1z, (float)l1z);
+            const float bx = fsub(1.0f, ax), by = fsub(1.0f, ay), bz = fsub(1.0f, az);
+            fn = lerp1(bz, lerp1(by, lerp1(bx, a000, ax, a001), ay, lerp1(bx, a010, ax, a011)), az,
+                       lerp1(by, lerp1(bx, a100, ax, a101), ay, lerp1(bx, a110, ax, a111)));
+        }
+        // ---- first sample (the order of march_step: back-face test, step update, front-face test, f = fn)
         const float step0 = r.step;
-        Samp a, b;
-        samp_fetch(a, t1, c, div_s, V, rx, plane);
-        const bool have2 = t2 <= c.tmax;
-        b.in = false;
-        if (have2) samp_fetch(b, t2, c, div_s, V, rx, plane);
         r.tcur = t1;
-        if (a.in && samp_resolve<STATS>(r, c, div_s, V, a, samp_value(a), st)) return true;
-        if (!have2 || r.step != step0) continue;     // the speculation failed (or there is no second sample)
+        if (STATS) { ++st[0]; if (r.f == 1.0f && fn == 1.0f) ++st[6]; }
+        if ((r.f < 0.0f && fn > 0.0f) || (r.f > 0.0f && fn < 0.0f)) {
+            if (r.f < 0.0f) {
+                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
+                if (fabsf(fn) < 1.0f) r.step = c.s;
+                if (fabsf(fn) < 0.8f) r.step = c.half_s;
+            } else {
+                if (fabsf(fn) < 1.0f) r.step = c.s;
+                if (fabsf(fn) < 0.8f) r.step = c.half_s;
+                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
+            }
+        } else {
+            if (fabsf(fn) < 1.0f) r.step = c.s;
+            if (fabsf(fn) < 0.8f) r.step = c.half_s;
+            r.f = fn;
+        }
+        if (r.step != step0) continue;               // the speculation failed: the second sample is somewhere else
+        // ---- second sample
+        {
+            const float ax = fsub(v2x, (float)l2x), ay = fsub(v2y, (float)l2y), az = fsub(v2z, (float)l2z);
+            const float bx = fsub(1.0f, ax), by = fsub(1.0f, ay), bz = fsub(1.0f, az);
+            fn = lerp1(bz, lerp1(by, lerp1(bx, b000, ax, b001), ay, lerp1(bx, b010, ax, b011)), az,
+                       lerp1(by, lerp1(bx, b100, ax, b101), ay, lerp1(bx, b110, ax, b111)));
+        }
         r.tcur = t2;
-        if (b.in && samp_resolve<STATS>(r, c, div_s, V, b, samp_value(b), st)) return true;
+        if (STATS) { ++st[0]; if (r.f == 1.0f && fn == 1.0f) ++st[6]; }
+        if ((r.f < 0.0f && fn > 0.0f) || (r.f > 0.0f && fn < 0.0f)) {
+            if (r.f < 0.0f) {
+                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
+                if (fabsf(fn) < 1.0f) r.step = c.s;
+                if (fabsf(fn) < 0.8f) r.step = c.half_s;
+            } else {
+                if (fabsf(fn) < 1.0f) r.step = c.s;
+                if (fabsf(fn) < 0.8f) r.step = c.half_s;
+                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
+            }
+        } else {
+            if (fabsf(fn) < 1.0f) r.step = c.s;
+            if (fabsf(fn) < 0.8f) r.step = c.half_s;
+            r.f = fn;
+        }
     }
     return false;
 }
@@ -556,7 +662,7 @@ __device__ __forceinline__ bool ray_begin(const RayVol& V, const float* K, int x
 #define EMF_CERT_L 2      // log2 of the smallest slab thickness (voxels)
 #endif
 #ifndef EMF_RAY_MINB
-#define EMF_RAY_MINB 8
+#define EMF_RAY_MINB 7      // 72 registers, no spills, 28 warps per SM: 1.114 ms per frame; 8 (64 registers, 36 B of spills) 1.128; 6 1.126
 #endif
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
