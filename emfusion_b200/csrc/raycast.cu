@@ -353,11 +353,15 @@ template <bool STATS>
 __device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane,
                                             unsigned long long* st, int max_iters = 0x7fffffff, int* iters = nullptr) {
     const float* __restrict__ vol = V.tsdf;
+    // (the march state in scalars: the out-of-line general step takes a COPY of the ray, so that nothing of the hot loop's
+    //  state has its address taken and ends up in local memory)
+    float tcur = r.tcur, step = r.step, f = r.f;
+    bool done = false;
     for (int it = 0; it < max_iters; ++it) {
         if (iters) *iters = it;
         if (STATS) { const unsigned am = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am) - 1) { ++st[4]; st[5] += __popc(am); } }
-        const float t1 = fadd(r.tcur, r.step);
-        const float t2 = fadd(t1, r.step);
+        const float t1 = fadd(tcur, step);
+        const float t2 = fadd(t1, step);
         const float n1x = ffma(c.dx, t1, c.ox), n1y = ffma(c.dy, t1, c.oy), n1z = ffma(c.dz, t1, c.oz);
         const float n2x = ffma(c.dx, t2, c.ox), n2y = ffma(c.dy, t2, c.oy), n2z = ffma(c.dz, t2, c.oz);
         bool fast = c.sane && t2 <= c.tmax &&
@@ -366,7 +370,11 @@ __device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const Con
         const float v2x = fadd(c.hxh, div_s.fast(n2x)), v2y = fadd(c.hyh, div_s.fast(n2y)), v2z = fadd(c.hzh, div_s.fast(n2z));
         fast = fast && !out_of_thr(v1x, v1y, v1z, V.thr2) && !out_of_thr(v2x, v2y, v2z, V.thr2);
         if (!fast) {
-            if (march_step_slow<STATS>(r, c, V, st)) return true;
+            Ray tmp = r;
+            tmp.tcur = tcur; tmp.step = step; tmp.f = f;
+            done = march_step_slow<STATS>(tmp, c, V, st);
+            tcur = tmp.tcur; step = tmp.step; f = tmp.f;
+            if (done) { r = tmp; break; }
             continue;
         }
         // ---- base voxels, fractions, 16 gathers
@@ -386,25 +394,23 @@ __device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const Con
                        lerp1(by, lerp1(bx, a100, ax, a101), ay, lerp1(bx, a110, ax, a111)));
         }
         // ---- first sample (the order of march_step: back-face test, step update, front-face test, f = fn)
-        const float step0 = r.step;
-        r.tcur = t1;
-        if (STATS) { ++st[0]; if (r.f == 1.0f && fn == 1.0f) ++st[6]; }
-        if ((r.f < 0.0f && fn > 0.0f) || (r.f > 0.0f && fn < 0.0f)) {
-            if (r.f < 0.0f) {
-                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
-                if (fabsf(fn) < 1.0f) r.step = c.s;
-                if (fabsf(fn) < 0.8f) r.step = c.half_s;
-            } else {
-                if (fabsf(fn) < 1.0f) r.step = c.s;
-                if (fabsf(fn) < 0.8f) r.step = c.half_s;
-                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
-            }
+        const float step0 = step;
+        tcur = t1;
+        if (STATS) { ++st[0]; if (f == 1.0f && fn == 1.0f) ++st[6]; }
+        if ((f < 0.0f && fn > 0.0f) || (f > 0.0f && fn < 0.0f)) {
+            const bool back = f < 0.0f;
+            if (!back) { if (fabsf(fn) < 1.0f) step = c.s; if (fabsf(fn) < 0.8f) step = c.half_s; }
+            r.tcur = tcur; r.step = step; r.f = f;
+            done = pair_event<STATS>(r, c, div_s, V, fn, st);
+            f = r.f;
+            if (done) break;
+            if (back) { if (fabsf(fn) < 1.0f) step = c.s; if (fabsf(fn) < 0.8f) step = c.half_s; }
         } else {
-            if (fabsf(fn) < 1.0f) r.step = c.s;
-            if (fabsf(fn) < 0.8f) r.step = c.half_s;
-            r.f = fn;
+            if (fabsf(fn) < 1.0f) step = c.s;
+            if (fabsf(fn) < 0.8f) step = c.half_s;
+            f = fn;
         }
-        if (r.step != step0) continue;               // the speculation failed: the second sample is somewhere else
+        if (step != step0) continue;                 // the speculation failed: the second sample is somewhere else
         // ---- second sample
         {
             const float ax = fsub(v2x, (float)l2x), ay = fsub(v2y, (float)l2y), az = fsub(v2z, (float)l2z);
@@ -412,25 +418,24 @@ __device__ __forceinline__ bool march_pairs(Ray& r, const RayConst& c, const Con
             fn = lerp1(bz, lerp1(by, lerp1(bx, b000, ax, b001), ay, lerp1(bx, b010, ax, b011)), az,
                        lerp1(by, lerp1(bx, b100, ax, b101), ay, lerp1(bx, b110, ax, b111)));
         }
-        r.tcur = t2;
-        if (STATS) { ++st[0]; if (r.f == 1.0f && fn == 1.0f) ++st[6]; }
-        if ((r.f < 0.0f && fn > 0.0f) || (r.f > 0.0f && fn < 0.0f)) {
-            if (r.f < 0.0f) {
-                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
-                if (fabsf(fn) < 1.0f) r.step = c.s;
-                if (fabsf(fn) < 0.8f) r.step = c.half_s;
-            } else {
-                if (fabsf(fn) < 1.0f) r.step = c.s;
-                if (fabsf(fn) < 0.8f) r.step = c.half_s;
-                if (pair_event<STATS>(r, c, div_s, V, fn, st)) return true;
-            }
+        tcur = t2;
+        if (STATS) { ++st[0]; if (f == 1.0f && fn == 1.0f) ++st[6]; }
+        if ((f < 0.0f && fn > 0.0f) || (f > 0.0f && fn < 0.0f)) {
+            const bool back = f < 0.0f;
+            if (!back) { if (fabsf(fn) < 1.0f) step = c.s; if (fabsf(fn) < 0.8f) step = c.half_s; }
+            r.tcur = tcur; r.step = step; r.f = f;
+            done = pair_event<STATS>(r, c, div_s, V, fn, st);
+            f = r.f;
+            if (done) break;
+            if (back) { if (fabsf(fn) < 1.0f) step = c.s; if (fabsf(fn) < 0.8f) step = c.half_s; }
         } else {
-            if (fabsf(fn) < 1.0f) r.step = c.s;
-            if (fabsf(fn) < 0.8f) r.step = c.half_s;
-            r.f = fn;
+            if (fabsf(fn) < 1.0f) step = c.s;
+            if (fabsf(fn) < 0.8f) step = c.half_s;
+            f = fn;
         }
     }
-    return false;
+    r.tcur = tcur; r.step = step; r.f = f;
+    return done;
 }
 
 // ---- certified skipping (k_ray_certify below).  While a ray carries exactly +1, a march sample whose eight corners all
