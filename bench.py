@@ -84,9 +84,21 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.h = None
+            try:        # the device this process computes on, by UUID (CUDA_VISIBLE_DEVICES may renumber or name devices by UUID)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except TypeError:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = None
+            if self.h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
             self.t = threading.Thread(target=self._poll, daemon=True)

@@ -1,4 +1,4 @@
-"""Turns what scripts/gpu_round.sh prof brought back in gpurun_out/ into the committed summaries under profiles/:
+"""Turns what scripts/gpu_round2.sh prof brought back in gpurun_out/ into the committed summaries under profiles/:
   python scripts/summarise_profiles.py r1d"""
 import collections
 import csv
