@@ -263,6 +263,10 @@ __device__ __forceinline__ void samp_load(Samp& q, const RayVol& V, int rx, int 
         q.c[4] = __ldg(r10); q.c[5] = __ldg(r10 + 1); q.c[6] = __ldg(r11); q.c[7] = __ldg(r11 + 1);
     }
 }
+__device__ __forceinline__ void samp_fetch(Samp& q, float t, const RayConst& c, const ConstDiv& div_s, const RayVol& V, int rx, int plane) {
+    samp_pos(q, t, c, div_s, V);
+    samp_load(q, V, rx, plane);
+}
 __device__ __forceinline__ float samp_value(const Samp& q) {
     const float ax = fsub(q.vx, (float)__float2int_rz(q.vx)), ay = fsub(q.vy, (float)__float2int_rz(q.vy)),
                 az = fsub(q.vz, (float)__float2int_rz(q.vz));
@@ -270,6 +274,33 @@ __device__ __forceinline__ float samp_value(const Samp& q) {
     const float c00 = lerp1(bx, q.c[0], ax, q.c[1]), c01 = lerp1(bx, q.c[2], ax, q.c[3]);
     const float c10 = lerp1(bx, q.c[4], ax, q.c[5]), c11 = lerp1(bx, q.c[6], ax, q.c[7]);
     return lerp1(bz, lerp1(by, c00, ay, c01), az, lerp1(by, c10, ay, c11));
+}
+// the part of march_step after the TSDF sample fn at ray parameter r.tcur / position q is known; true = ray finished
+template <bool STATS>
+__device__ __forceinline__ bool samp_resolve(Ray& r, const RayConst& c, const ConstDiv& div_s, const RayVol& V, const Samp& q, float fn,
+                                             unsigned long long* st) {
+    if (STATS) { ++st[0]; if (r.f == 1.0f && fn == 1.0f) ++st[6]; }
+    if (r.f < 0.0f && fn > 0.0f) {
+        if (STATS) ++st[3];
+        if (trilinear_weight(V, q.vx, q.vy, q.vz) > 0.0f) return true;
+    }
+    if (fabsf(fn) < 1.0f) r.step = c.s;
+    if (fabsf(fn) < 0.8f) r.step = c.half_s;
+    if (r.f > 0.0f && fn < 0.0f) {
+        const float ts = fsub(r.tcur, fdiv(fmul(r.f, r.step), fsub(fn, r.f)));
+        const float mx = fmul(c.dx, ts), my = fmul(c.dy, ts), mz = fmul(c.dz, ts);
+        const float sx = fadd(c.hxh, div_s(fadd(c.ox, mx)));
+        const float sy = fadd(c.hyh, div_s(fadd(c.oy, my)));
+        const float sz = fadd(c.hzh, div_s(fadd(c.oz, mz)));
+        if (out_of_thr(sx, sy, sz, V.thr2)) return false;
+        if (trilinear_weight(V, sx, sy, sz) > 0.0f) {
+            r.hit = true; r.out_t = ts;
+            r.hvx = sx; r.hvy = sy; r.hvz = sz; r.hmx = mx; r.hmy = my; r.hmz = mz;
+            return true;
+        }
+    }
+    r.f = fn;
+    return false;
 }
 // The rare outcomes of a sample -- a sign change against the ray's previous value -- out of line: the back-face test
 // (TSDF.cu:532) and the front-face refinement (TSDF.cu:540-566) with their weight gathers.  The sample's position is
