@@ -518,8 +518,11 @@ EMF_API int emf_xchg_close(void* peer_ptr);
 EMF_API int emf_xchg_free(void* ptr);
 /* *flags[i] = value for i < n (n <= 16; local or peer pointers), after everything queued before it on the stream. */
 EMF_API int emf_xchg_signal(int n, uint32_t* const* flags, uint32_t value, emf_stream_t stream);
-/* The stream waits until flags[i] >= value (wrap-safe) for every i < n (n <= 32; LOCAL memory).  After timeout_s seconds
- * it gives up and stores 1 + i in *err (device memory, caller-zeroed) instead of hanging. */
+/* The stream waits until flags[i] >= value for every i < n (n <= 32; LOCAL memory).  ">=" is the sign of the 32-bit
+ * difference (int32_t)(flags[i] - value) >= 0: flags are frame counters that only grow and may wrap; a waiter must not be
+ * more than 2^31 - 1 signals behind its producer.  After timeout_s seconds it gives up and stores 1 + i in *err (device
+ * memory, caller-zeroed) instead of hanging; the host mirror (PeerExchange.poll_errors) turns that into an exception in
+ * the next frame. */
 EMF_API int emf_xchg_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, double timeout_s, emf_stream_t stream);
 /* out = parts[0] + parts[1] + ... in this order (W x H f32, continuous parts, 16-byte aligned; local or peer pointers). */
 EMF_API int emf_xchg_sum_images(int n_parts, const float* const* parts, const emf_image* out, emf_stream_t stream);
